@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Headline benchmark: MC-sample*examples / second of one ELBO train step
+(forward + likelihood + KL + backward [+ gradient all-reduce] + Adam) -- BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2] [--precision ...]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU path (oracle/torch_port.py)
+
+Workloads (synthetic data, reference initialisation):
+  c4  wide Bayesian MLP 4096-4096-4096-1000, MC=64, batch 512, num_samples 100000  (default: the
+      config north_star's targets are quoted on; fits one GPU; MC-sharded over N GPUs -> strong scaling)
+  c2  MNIST-shaped MLP 784-1200-1200-10, MC=32, batch 256, num_samples 55000
+
+One JSON line on stdout (rank 0).  `value` = device-resident inputs, CUDA-event timed, max over
+ranks.  `e2e` = the same step through the public API with pinned HOST inputs copied in and the
+loss read back every step.  `roofline` = the dominant kernel, timed live with CUDA events.
+`cpu_baseline` = oracle/torch_port.py (op-for-op port of the reference) on the host cores, on a
+bounded MC sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c4": dict(dims=[4096, 4096, 4096, 1000], mc=64, batch=512, num_samples=100000, lr=1e-3,
+               name="C4 wide Bayesian MLP 4096-4096-4096-1000, MC=64, batch 512"),
+    "c2": dict(dims=[784, 1200, 1200, 10], mc=32, batch=256, num_samples=55000, lr=1e-3,
+               name="C2 MNIST-shaped Bayesian MLP 784-1200-1200-10, MC=32, batch 256"),
+}
+METRIC = "mc_samples_x_examples_per_sec_per_train_step"
+UNIT = "MC-sample*examples/s"
+
+
+def step_flops(dims, mc, batch):
+    """Algorithmic FLOPs of one step: 2*MC*B*I*O x (fwd, dW, dX; no dX for
+    the first layer)."""
+    total = 0
+    for li in range(len(dims) - 1):
+        total += 2 * mc * batch * dims[li] * dims[li + 1] * (2 if li == 0 else 3)
+    return total
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
+                    tf_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0,
+                source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own path (port), all host threads
+# ------------------------------------------------------------------------------------------------
+def cpu_port_throughput(wl, mc_sample, steps, warmup):
+    import torch
+    from oracle import torch_port as tp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1234)
+    net = tp.build_mlp(wl["dims"], mc_sample, torch.nn.LeakyReLU)
+    crit = tp.MCCrossEntropyPort(wl["num_samples"])
+    opt = torch.optim.Adam(net.parameters(), wl["lr"])
+    x = torch.randn(wl["batch"], wl["dims"][0])
+    y = torch.randint(0, wl["dims"][-1], (wl["batch"],))
+    for _ in range(warmup):
+        tp.train_step(net, crit, opt, x, y, wl["num_samples"])
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        tp.train_step(net, crit, opt, x, y, wl["num_samples"])
+        times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return mc_sample * wl["batch"] / t, t * 1e3, cores
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mc_sample = 4 if args.workload == "c4" else 8
+    steps = max(1, min(args.steps, 10))
+    warmup = max(1, min(args.warmup, 2))
+    value, ms, cores = cpu_port_throughput(wl, mc_sample, steps, warmup)
+    sample = (f"MC={mc_sample} of {wl['mc']} (throughput in MC-sample*examples/s is ~MC-independent "
+              f"on the CPU path), full batch {wl['batch']}, {steps} timed steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "mc_sample": mc_sample,
+                   "note": "reference CPU path = oracle/torch_port.py (op-for-op port; the Python "
+                           "reference cannot travel to the GPU box)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            parts = [c.strip() for c in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        self.f.close()
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import pytorch_probabilisticlayers_b200 as plb
+    from pytorch_probabilisticlayers_b200 import functional as PF
+    from pytorch_probabilisticlayers_b200.train import ELBOTrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = plb._cabi.lib()
+    assert lib.pl_device_supported() == 1, "bench needs an sm_100 (B200) device"
+
+    plb.set_precision(args.precision)
+    plb.manual_seed(20261019)
+    torch.manual_seed(1234)                      # identical replicas + identical batch on all ranks
+    dims, mc_total, batch, ns = wl["dims"], wl["mc"], wl["batch"], wl["num_samples"]
+    assert mc_total % world == 0
+    mc_local = mc_total // world
+    mods = [plb.MC_ExpansionLayer(num_MC=mc_local, input_dim=2)]
+    for li in range(len(dims) - 1):
+        mods.append(plb.BayesLinear(dims[li], dims[li + 1]))
+        if li + 2 < len(dims):
+            mods.append(torch.nn.LeakyReLU())
+    net = torch.nn.Sequential(*mods).to(dev)
+    trainer = ELBOTrainStep(net, plb.MC_CrossEntropyLoss(ns), ns, lr=wl["lr"])
+    assert trainer.set_shard(mc_total) == mc_local
+
+    x_host = torch.randn(batch, dims[0]).pin_memory()
+    y_host = torch.randint(0, dims[-1], (batch,)).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident():
+        return trainer.step(x_dev, y_dev)
+
+    def step_e2e():
+        xs = x_host.to(dev, non_blocking=True)
+        ys = y_host.to(dev, non_blocking=True)
+        return trainer.step(xs, ys).cpu()        # D2H read of [LL, KL, ACC, loss] every step
+
+    for _ in range(max(args.warmup, 3)):
+        stats = step_resident()
+    torch.cuda.synchronize()
+
+    # ---- headline: device-resident inputs ----
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    l0 = lib.pl_launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = (lib.pl_launch_count() - l0) // 1
+    clock_info = clocks.stop() if clocks else None
+    ms_step = ms_total / args.steps
+    value = mc_total * batch / (ms_step * 1e-3)
+
+    # ---- e2e: host inputs, loss read back ----
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = mc_total * batch / (ms_e2e * 1e-3)
+
+    # ---- roofline leg: per-call CUDA events over a few more steps (same stream) ----
+    prof_steps = max(2, min(args.steps, 5))
+    barrier()
+    PF.profile_start()
+    for _ in range(prof_steps):
+        step_resident()
+    prof = PF.profile_stop()
+    final_stats = stats.tolist()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    per_call = {k: v[1] / v[0] for k, v in prof.items()}                  # ms per call
+    per_step = {k: v[1] / prof_steps for k, v in prof.items()}            # ms per step
+    top = max(per_step, key=per_step.get)
+    shape = top[top.index("[") + 1:-1]
+    if top.startswith("linear"):
+        m_, b_, i_, o_ = (int(v) for v in shape.split("x"))
+        flops = 2.0 * m_ * b_ * i_ * o_
+        achieved = flops / (per_call[top] * 1e-3) / 1e12
+        peak = pk["tf_sustained"]
+        roofline = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peak,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": pk["source"] + " bf16 dense sustained",
+                    "ms_per_launch": per_call[top],
+                    "algorithmic_flops_per_launch": flops}
+    else:
+        n_ = int(shape)
+        nbytes = (8.0 if top.startswith("kl_fwd") else 24.0) * n_
+        achieved = nbytes / (per_call[top] * 1e-3) / 1e9
+        roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": pk["hbm"],
+                    "unit": "GB/s", "frac": achieved / pk["hbm"], "traffic": None,
+                    "peak_source": pk["source"], "ms_per_launch": per_call[top],
+                    "algorithmic_bytes_per_launch": nbytes}
+    # secondary: the KL reduction against the HBM roofline (north_star target (c))
+    kl_tags = [k for k in per_call if k.startswith("kl_fwd")]
+    kl_info = None
+    if kl_tags:
+        k = max(kl_tags, key=lambda t: int(t[t.index("[") + 1:-1]))
+        n_ = int(k[k.index("[") + 1:-1])
+        gbs = 8.0 * n_ / (per_call[k] * 1e-3) / 1e9
+        kl_info = {"kernel": k, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm"],
+                   "note": "event pair around 2 launches (reduce + 1-CTA finish)"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        mc_sample = 4 if args.workload == "c4" else 8
+        v, ms, cores = cpu_port_throughput(wl, mc_sample, 3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step_sample": ms,
+               "sample": f"MC={mc_sample} of {wl['mc']}, full batch {wl['batch']}, 3 timed steps "
+                         f"after 1 warm-up, torch CPU fp32, {cores} threads"}
+
+    flops = step_flops(dims, mc_total, batch)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "bf16": "bf16", "auto": "bf16"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": wl["name"], "mc_total": mc_total, "mc_per_gpu": mc_local,
+                   "batch": batch, "num_samples": ns, "precision": args.precision,
+                   "parallelism": f"mc-shard x{world}" if world > 1 else "single",
+                   "l2": "per-step working set (parameters + activations >> 126 MB) exceeds L2; "
+                         "no explicit flush"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
+                "d2h_bytes_per_step": 16},
+        "gpu_launches": int(launches),
+        "clocks": clock_info,
+        "roofline": roofline,
+        "kl_roofline": kl_info,
+        "step_tflops": flops / (ms_step * 1e-3) / 1e12 * (1.0 / world),
+        "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+        "cpu_baseline": cpu,
+        "final_stats": {"LL": final_stats[0], "KL": final_stats[1], "ACC": final_stats[2],
+                        "loss": final_stats[3]},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c4")
+    ap.add_argument("--precision", choices=["fp32", "bf16", "auto"], default="fp32")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_b200(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,166 @@
+/*
+ * pl_b200.h -- C ABI of the B200-native MC-parallel variational layers.
+ *
+ * Drop-in boundary for the hot path of ludwigwinkler/pytorch_ProbabilisticLayers: the reference
+ * has no FFI of its own (pure PyTorch), so each entry point below replaces the torch call sites
+ * cited next to it (paths relative to the reference checkout).  All pointers are DEVICE pointers
+ * owned by the caller (PyTorch's caching allocator in the Python host layer), all work is
+ * enqueued asynchronously on `stream` (a cudaStream_t passed as void*), nothing is allocated or
+ * synchronised inside the library, no C++ types or exceptions cross the boundary.
+ *
+ * Return value: PL_OK or a negative pl_status; the text of the last error of the calling thread
+ * is available from pl_last_error().
+ *
+ * Tensor conventions (README.md:12 of the reference): dim 0 = Monte-Carlo sample, dim 1 = batch,
+ * row-major fp32.  Linear weights are [in_features, out_features] (src/ProbabilisticLayers.py:858),
+ * conv weights [Cout, Cin, k, k] (:993).
+ *
+ * eps: either injected (eps_w / eps_b non-NULL: the reference's own torch.randn draws, captured
+ * at src/ProbabilisticLayers.py:835) or synthesised on chip from Philox4x32-10 with
+ *     key = seed,  counter = (col/4, row, mc_global_offset + mc, 2*layer_id + is_bias)
+ * so that forward and backward regenerate the same numbers for any tiling and GPU count
+ * (oracle/philox.py is the CPU restatement).
+ */
+#ifndef PL_B200_H_
+#define PL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PL_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef enum pl_status {
+  PL_OK = 0,
+  PL_ERR_BAD_ARG = -1,     /* NULL / negative / inconsistent argument                        */
+  PL_ERR_UNSUPPORTED = -2, /* shape or mode not supported by the requested precision path    */
+  PL_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed; see pl_last_error()         */
+  PL_ERR_WORKSPACE = -4    /* caller-provided workspace too small                            */
+} pl_status;
+
+typedef enum pl_precision {
+  PL_PREC_FP32 = 0, /* fp32 FFMA kernels, any shape (exact-parity / tiny layers)              */
+  PL_PREC_BF16 = 1, /* tcgen05 kind::f16, bf16 operands, fp32 TMEM accumulators               */
+  PL_PREC_TF32 = 2  /* tcgen05 kind::tf32 (reserved)                                           */
+} pl_precision;
+
+typedef enum pl_param_mode {
+  PL_PARAM_SHARED_RHO = 0,  /* one (mu, rho) for all MC samples; sigma = softplus(rho);
+                               gradients are reduced over MC (BayesLinear / BayesConv2d)      */
+  PL_PARAM_PER_MC_SIGMA = 1 /* per-MC (mu, sigma) [MC, ...]; gradients keep the MC axis
+                               (SIVILayer, src/ProbabilisticLayers.py:307-326)                 */
+} pl_param_mode;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int pl_version(void);
+const char* pl_last_error(void);
+/* Number of kernels this library has launched in this process (all threads); bench.py reports
+ * the difference over its timed region as "gpu_launches". */
+uint64_t pl_launch_count(void);
+/* 1 if the tcgen05 path can run on the current device (compute capability 10.x), else 0. */
+int pl_device_supported(void);
+
+/* ---- eps stream (test bridge; replaces torch.distributions.utils._standard_normal as used at
+ *      src/ProbabilisticLayers.py:835) -----------------------------------------------------
+ * out: float [num_mc, rows, cols] standard normals (raw == 0) or uint32 [num_mc, rows,
+ * 4*ceil(cols/4)] raw Philox words (raw == 1) of stream `stream_id` (2*layer_id + is_bias). */
+int pl_eps_dump(uint64_t seed, uint32_t stream_id, uint32_t mc_global_offset, int32_t num_mc,
+                int32_t rows, int32_t cols, void* out, int32_t raw, void* stream);
+
+/* ---- KL(q||p) + entropy (replaces torch.distributions.kl_divergence(...).sum() and
+ *      Normal.entropy().sum() at src/ProbabilisticLayers.py:955-956 and :1059) ---------------
+ * out2[0] = sum 0.5[(s/sp)^2 + (mu/sp)^2 - 1 - log((s/sp)^2)],  out2[1] = sum 0.5+0.5log(2pi)+log s
+ * prior_scale_elem (optional, per-element prior scale, n floats) overrides prior_scale.
+ * workspace: pl_kl_workspace_bytes() bytes.  Deterministic (fixed reduction tree). */
+size_t pl_kl_workspace_bytes(void);
+int pl_kl_fwd(const float* mu, const float* rho, int64_t n, float prior_scale,
+              const float* prior_scale_elem, float* out2, void* workspace, size_t workspace_bytes,
+              void* stream);
+/* dmu (+)= g_kl * mu/sp^2 ; drho (+)= [g_kl*(s/sp^2 - 1/s) + g_ent/s] * sigmoid(rho), where
+ * g_kl = host_scale * (*grad_kl or 1), g_ent = host_scale * (*grad_ent or 0) (device scalars,
+ * may be NULL).  accumulate != 0 adds into dmu/drho. */
+int pl_kl_bwd(const float* mu, const float* rho, int64_t n, float prior_scale,
+              const float* prior_scale_elem, const float* grad_kl, const float* grad_ent,
+              float host_scale, float* dmu, float* drho, int32_t accumulate, void* stream);
+
+/* ---- BayesLinear / SIVILayer contraction (replaces VariationalNormal.rsample + torch.baddbmm /
+ *      torch.bmm at src/ProbabilisticLayers.py:925-935 and :321-326, and their autograd) ------ */
+typedef struct pl_linear_args {
+  int32_t mc, batch, in_features, out_features;
+  int32_t precision;  /* pl_precision */
+  int32_t param_mode; /* pl_param_mode */
+  /* input x: [mc, batch, in]; x_mc_stride in elements, 0 => one [batch,in] matrix broadcast over
+     MC (what MC_ExpansionLayer, src/ProbabilisticLayers.py:778-785, materialises by repeat) */
+  const float* x;
+  int64_t x_mc_stride;
+  /* parameters: w_mu/w_rho [in,out] (+ leading MC axis in PER_MC_SIGMA mode, where w_rho and
+     b_rho hold sigma itself); b_* may be NULL (bias=False) */
+  const float* w_mu;
+  const float* w_rho;
+  const float* b_mu;
+  const float* b_rho;
+  /* sampler */
+  uint64_t seed;
+  uint32_t layer_id;
+  uint32_t mc_global_offset; /* first global MC index owned by this rank (MC sharding) */
+  const float* eps_w;        /* optional injected eps [mc,in,out] */
+  const float* eps_b;        /* optional injected eps [mc,out]    */
+  /* forward output [mc,batch,out] */
+  float* y;
+  /* backward: dy [mc,batch,out] in; outputs (each may be NULL to skip) */
+  const float* dy;
+  float* dx;     /* [mc,batch,in] */
+  float* dw_mu;  /* [in,out]   (PER_MC_SIGMA: [mc,in,out]) */
+  float* dw_rho; /* [in,out]   (PER_MC_SIGMA: d/dsigma, [mc,in,out]) */
+  float* db_mu;  /* [out]      (PER_MC_SIGMA: [mc,out]) */
+  float* db_rho; /* [out]      (PER_MC_SIGMA: [mc,out]) */
+  /* scratch for the tensor-core path, see pl_linear_workspace_bytes */
+  void* workspace;
+  size_t workspace_bytes;
+  void* stream;
+} pl_linear_args;
+
+size_t pl_linear_workspace_bytes(const pl_linear_args* a);
+int pl_linear_fwd(const pl_linear_args* a);
+int pl_linear_bwd(const pl_linear_args* a);
+
+/* ---- BayesConv2d (replaces rsample + F.conv2d(groups=MC) at
+ *      src/ProbabilisticLayers.py:1032-1057 and its autograd).  Square kernel, scalar
+ *      stride/padding/dilation like the reference (:991).  x [mc,B,Cin,H,W] contiguous,
+ *      y [mc,B,Cout,H',W'] contiguous. ------------------------------------------------------- */
+typedef struct pl_conv2d_args {
+  int32_t mc, batch, cin, cout, h, w, k, stride, padding, dilation;
+  int32_t precision;
+  const float* x;
+  int64_t x_mc_stride; /* 0 => input broadcast over MC */
+  const float* w_mu;   /* [cout,cin,k,k] */
+  const float* w_rho;
+  const float* b_mu;   /* [cout] */
+  const float* b_rho;
+  uint64_t seed;
+  uint32_t layer_id;
+  uint32_t mc_global_offset;
+  const float* eps_w; /* optional [mc,cout,cin,k,k] */
+  const float* eps_b; /* optional [mc,cout] */
+  float* y;
+  const float* dy;
+  float* dx;
+  float* dw_mu;
+  float* dw_rho;
+  float* db_mu;
+  float* db_rho;
+  void* workspace;
+  size_t workspace_bytes;
+  void* stream;
+} pl_conv2d_args;
+
+int pl_conv2d_fwd(const pl_conv2d_args* a);
+int pl_conv2d_bwd(const pl_conv2d_args* a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PL_B200_H_ */

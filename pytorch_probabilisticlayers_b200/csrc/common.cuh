@@ -1,0 +1,128 @@
+// Shared device/host helpers for the pl_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pl_b200.h"
+
+namespace pl {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: negative pl_status + thread-local text, never throw / abort
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch();  // bumps the counter behind pl_launch_count()
+
+#define PL_CHECK_ARG(cond, ...)              \
+  do {                                       \
+    if (!(cond)) {                           \
+      ::pl::set_error(__VA_ARGS__);          \
+      return PL_ERR_BAD_ARG;                 \
+    }                                        \
+  } while (0)
+
+#define PL_CUDA(call)                                        \
+  do {                                                       \
+    cudaError_t e__ = (call);                                \
+    if (e__ != cudaSuccess) return ::pl::cuda_fail(e__, #call); \
+  } while (0)
+
+#define PL_LAUNCH_CHECK(name)                                   \
+  do {                                                          \
+    cudaError_t e__ = cudaGetLastError();                       \
+    if (e__ != cudaSuccess) return ::pl::cuda_fail(e__, name);  \
+    ::pl::count_launch();                                       \
+  } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// elementwise math shared by every kernel (must agree with oracle/closed_form.py)
+// ---------------------------------------------------------------------------------------------
+// softplus(beta=1, threshold=20) exactly like F.softplus (src/ProbabilisticLayers.py:826,836):
+// accurate log1p so that sigma ~ 1e-6 (fresh-init rho ~ -12) keeps full precision.
+__device__ __forceinline__ float softplus_f(float x) {
+  return x > 20.f ? x : log1pf(__expf(x));
+}
+__device__ __forceinline__ float sigmoid_f(float x) {
+  return x > 20.f ? 1.f : __fdividef(1.f, 1.f + __expf(-x));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 eps stream (contract in include/pl_b200.h, CPU restatement oracle/philox.py)
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
+constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
+constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
+    const uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += kPhiloxW0;
+    k1 += kPhiloxW1;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// float in [1,2) from the top 23 bits
+__device__ __forceinline__ float unit_float(uint32_t u) {
+  return __uint_as_float((u >> 9) | 0x3F800000u);
+}
+
+// one Box-Muller pair: f = 2 - t(u_r) in (0,1], r = sqrt(-2 ln f), theta = 2pi t(u_a) - 3pi
+__device__ __forceinline__ void box_muller(uint32_t u_r, uint32_t u_a, float& n_cos, float& n_sin) {
+  const float f = 2.0f - unit_float(u_r);
+  const float r = sqrtf(-1.3862943611198906f * __log2f(f));
+  const float theta = fmaf(unit_float(u_a), 6.283185307179586f, -9.42477796076938f);
+  n_cos = r * __cosf(theta);
+  n_sin = r * __sinf(theta);
+}
+
+struct Sampler {
+  uint32_t k0, k1;     // seed
+  uint32_t stream;     // 2*layer_id + is_bias
+  uint32_t mc_offset;  // global MC index of local sample 0
+};
+
+__host__ __device__ inline Sampler make_sampler(uint64_t seed, uint32_t layer_id, bool bias,
+                                                uint32_t mc_offset) {
+  Sampler s;
+  s.k0 = (uint32_t)(seed & 0xffffffffu);
+  s.k1 = (uint32_t)(seed >> 32);
+  s.stream = 2u * layer_id + (bias ? 1u : 0u);
+  s.mc_offset = mc_offset;
+  return s;
+}
+
+// 4 standard normals for columns 4*group .. 4*group+3 of `row` of MC sample `mc` (local index)
+__device__ __forceinline__ float4 eps4(const Sampler& s, uint32_t mc, uint32_t row, uint32_t group) {
+  const uint4 w = philox4x32_10(group, row, s.mc_offset + mc, s.stream, s.k0, s.k1);
+  float4 n;
+  box_muller(w.x, w.y, n.x, n.y);
+  box_muller(w.z, w.w, n.z, n.w);
+  return n;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace pl

@@ -1,0 +1,39 @@
+// pl_linear_* entry points: argument validation + dispatch on the requested precision path.
+#include "common.cuh"
+
+namespace pl {
+size_t linear_simt_workspace_bytes(const pl_linear_args* a);
+int linear_fwd_simt_launch(const pl_linear_args* a);
+int linear_bwd_simt_launch(const pl_linear_args* a);
+size_t linear_tc_workspace_bytes(const pl_linear_args* a);
+int linear_fwd_tc_launch(const pl_linear_args* a);
+int linear_bwd_tc_launch(const pl_linear_args* a);
+}  // namespace pl
+
+extern "C" size_t pl_linear_workspace_bytes(const pl_linear_args* a) {
+  if (!a) return 0;
+  if (a->precision == PL_PREC_BF16) return pl::linear_tc_workspace_bytes(a);
+  return pl::linear_simt_workspace_bytes(a);
+}
+
+extern "C" int pl_linear_fwd(const pl_linear_args* a) {
+  PL_CHECK_ARG(a, "pl_linear_fwd: NULL args");
+  switch (a->precision) {
+    case PL_PREC_FP32: return pl::linear_fwd_simt_launch(a);
+    case PL_PREC_BF16: return pl::linear_fwd_tc_launch(a);
+    default:
+      pl::set_error("pl_linear_fwd: precision %d not implemented", a->precision);
+      return PL_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int pl_linear_bwd(const pl_linear_args* a) {
+  PL_CHECK_ARG(a, "pl_linear_bwd: NULL args");
+  switch (a->precision) {
+    case PL_PREC_FP32: return pl::linear_bwd_simt_launch(a);
+    case PL_PREC_BF16: return pl::linear_bwd_tc_launch(a);
+    default:
+      pl::set_error("pl_linear_bwd: precision %d not implemented", a->precision);
+      return PL_ERR_UNSUPPORTED;
+  }
+}

@@ -1,0 +1,111 @@
+"""MC-sharded ELBO train step (the harness that stands in for the reference's Lightning loop).
+
+Semantics follow the reference's ``training_step`` (experiments/BNN.py:287-313,
+experiments/RegressionBNN.py:109-120, experiments/SIVILastLayer.py:287-296):
+
+    loss = LL(pred, y) / num_samples + sum_{BayesLinear, SIVILayer} kl_div / num_samples
+
+with Adam (BNN.py:349).  Sharding: the Monte-Carlo samples are independent given
+(mu, rho), so rank r of N owns global samples [r*MC/N, (r+1)*MC/N), holds a full parameter replica
+and sees the full batch.  The cross-entropy ELBO decomposes over samples, so the only exchange is
+ONE all-reduce(sum) per step over a flat fp32 buffer [all gradients | LL, KL, ACC scalars]; KL and
+its gradient are replica-identical and are pre-scaled by 1/N instead of being reduced separately.
+The KL gradient is streamed straight into the flat gradient buffer by ``pl_kl_bwd(accumulate=1)``
+(no autograd temporaries).
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi, layers
+from . import functional as PF
+from .layers import BayesConv2d, BayesLinear, SIVILayer
+from .loss import MC_Accuracy
+
+
+def collect_kl_div(net, kinds=(BayesLinear, SIVILayer)):
+    """Sum of ``kl_div`` over the layer kinds the reference's collect_kl_div matches
+    (experiments/BNN.py:269-276: BayesLinear only -- conv KL never reaches the reference's loss)."""
+    total = None
+    for m in net.modules():
+        if isinstance(m, tuple(kinds)) and hasattr(m, "kl_div"):
+            total = m.kl_div if total is None else total + m.kl_div
+    return total
+
+
+class ELBOTrainStep:
+    def __init__(self, net: torch.nn.Module, criterion, num_samples: int, lr: float = 1e-3,
+                 kl_kinds: Iterable = (BayesLinear, SIVILayer), with_accuracy: bool = True,
+                 group: Optional[dist.ProcessGroup] = None, mc_coupled_loss: bool = False):
+        self.net, self.criterion, self.num_samples = net, criterion, int(num_samples)
+        self.kl_kinds = tuple(kl_kinds)
+        self.with_accuracy = with_accuracy
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if mc_coupled_loss and self.world > 1:
+            # MC_NLL / MC_BatchNorm couple samples across MC (SURVEY.md 8e caveats): replicas only
+            raise ValueError("this criterion couples MC samples; run it unsharded (replicas only)")
+        self.params = [p for p in net.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n + 4, dtype=torch.float32, device=dev)   # grads | LL KL ACC pad
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.stats = self.flat[n:n + 4]
+        self.opt = torch.optim.Adam(self.params, lr, fused=True)
+        # fused KL gradient: layers compute kl_div without an autograd graph
+        self.kl_layers = [m for m in net.modules()
+                          if isinstance(m, (BayesLinear, BayesConv2d)) and isinstance(m, self.kl_kinds)]
+        for m in self.kl_layers:
+            m.kl_autograd = False
+
+    def set_shard(self, total_mc: int):
+        """Local MC count for a global ``total_mc`` and registers this rank's global MC offset."""
+        assert total_mc % self.world == 0, "MC must divide evenly across ranks"
+        local = total_mc // self.world
+        layers.set_mc_shard(self.rank * local)
+        return local
+
+    def step(self, x, y):
+        """One optimiser step; returns a device tensor [LL, KL, ACC, loss] (global values)."""
+        lib = _cabi.lib()
+        self.flat.zero_()
+        pred = self.net(x)
+        inv = 1.0 / (self.num_samples * self.world)
+        ll = self.criterion(pred, y) * inv
+        kl_graph = None      # KL terms that still need autograd (SIVI hyper-net, Laplace prior)
+        kl_value = torch.zeros((), device=pred.device)
+        for m in self.net.modules():
+            if isinstance(m, self.kl_kinds) and hasattr(m, "kl_div"):
+                if m.kl_div.requires_grad:
+                    kl_graph = m.kl_div if kl_graph is None else kl_graph + m.kl_div
+                kl_value = kl_value + m.kl_div.detach()
+        loss = ll if kl_graph is None else ll + kl_graph * inv
+        loss.backward()
+        stream = _cabi.current_stream(pred.device)
+        for m in self.kl_layers:
+            if m.kl_div.requires_grad:      # e.g. Laplace prior: went through autograd above
+                continue
+            w = m.weight
+            prior = m.prior.scale if isinstance(m, BayesLinear) else m.prior_scale
+            PF._timed(f"kl_bwd_acc[{w.loc.numel()}]", lambda: _cabi.check(
+                lib.pl_kl_bwd(w.loc.data_ptr(), w.logscale.data_ptr(), w.loc.numel(), float(prior),
+                              None, None, None, inv, w.loc.grad.data_ptr(),
+                              w.logscale.grad.data_ptr(), 1, stream), "pl_kl_bwd"))
+        with torch.no_grad():
+            self.stats[0] = ll.detach()
+            self.stats[1] = kl_value * inv
+            if self.with_accuracy:
+                self.stats[2] = MC_Accuracy(pred.detach(), y)[0] / self.world
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.opt.step()
+        out = self.stats.clone()
+        out[3] = out[0] + out[1]
+        return out

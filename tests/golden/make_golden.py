@@ -265,6 +265,21 @@ def init_case(PL):
          conv_w_mu_absmax=npy(c.weight.loc.abs().max()), conv_b_mu_absmax=npy(c.bias.loc.abs().max()))
 
 
+def seeded_init_case(PL):
+    """state_dicts of freshly constructed layers under a fixed global seed (drop-in init parity)."""
+    arrs = {}
+    torch.manual_seed(3)
+    for k, v in PL.BayesLinear(7, 5).state_dict().items():
+        arrs["lin__" + k.replace(".", "__")] = npy(v)
+    torch.manual_seed(4)
+    for k, v in PL.BayesConv2d(2, 3, 3).state_dict().items():
+        arrs["conv__" + k.replace(".", "__")] = npy(v)
+    torch.manual_seed(5)
+    for k, v in PL.SIVILayer(6, 1, 5).state_dict().items():
+        arrs["sivi__" + k.replace(".", "__")] = npy(v)
+    save("seeded_init", **arrs)
+
+
 def main():
     torch.set_num_threads(4)
     PL, LOSS = load_reference()
@@ -288,6 +303,7 @@ def main():
     loss_cases(PL, LOSS)
     aux_layer_cases(PL)
     init_case(PL)
+    seeded_init_case(PL)
 
 
 if __name__ == "__main__":

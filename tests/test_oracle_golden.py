@@ -133,3 +133,63 @@ def test_philox_normals_are_standard_and_tiling_invariant():
     # different stream / seed decorrelates
     other = philox.eps_normal(1234, 1, 0, 4, 128, 130)
     assert abs(np.corrcoef(e.ravel(), other.ravel())[0, 1]) < 0.02
+
+
+# ----------------------------------------------------------------------------------------------
+# torch_port (the CPU baseline that bench.py times) must be the reference, op for op
+# ----------------------------------------------------------------------------------------------
+def test_torch_port_layer_reproduces_reference_draws_and_outputs():
+    import torch
+    from oracle import torch_port as tp
+    g = load_golden("linear_small")           # generated with torch.manual_seed(11 + 1) before forward
+    layer = tp.BayesLinearPort(5, 4, prior=0.7)
+    with torch.no_grad():
+        layer.weight.loc.copy_(torch.from_numpy(g["w_mu"]))
+        layer.weight.logscale.copy_(torch.from_numpy(g["w_rho"]))
+        layer.bias.loc.copy_(torch.from_numpy(g["b_mu"]))
+        layer.bias.logscale.copy_(torch.from_numpy(g["b_rho"]))
+    torch.manual_seed(12)
+    out = layer(torch.from_numpy(g["x"]))
+    assert np.array_equal(layer.weight.eps.numpy(), g["eps_w"])
+    assert np.array_equal(layer.bias.eps.numpy(), g["eps_b"])
+    assert np.allclose(out.detach().numpy(), g["out"], rtol=1e-6, atol=1e-6)
+    assert abs(layer.kl_div.item() - g["kl"]) / abs(g["kl"]) < 1e-6
+
+    gc = load_golden("conv_k5")
+    conv = tp.BayesConv2dPort(3, 6, 5, stride=1, padding=2, dilation=1, num_MC=2, prior_scale=1.3)
+    with torch.no_grad():
+        conv.weight.loc.copy_(torch.from_numpy(gc["w_mu"]))
+        conv.weight.logscale.copy_(torch.from_numpy(gc["w_rho"]))
+        conv.bias.loc.copy_(torch.from_numpy(gc["b_mu"]))
+        conv.bias.logscale.copy_(torch.from_numpy(gc["b_rho"]))
+    torch.manual_seed(24)
+    out = conv(torch.from_numpy(gc["x"]))
+    assert np.allclose(out.detach().numpy(), gc["out"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,act,loss", [("train_c1_regression", "relu", "nll"),
+                                           ("train_mlp_ce", "leaky", "ce")])
+def test_torch_port_train_step_reproduces_reference_trajectory(name, act, loss):
+    import torch
+    from oracle import torch_port as tp
+    g = load_golden(name)
+    seed = 31 if loss == "nll" else 32
+    dims = [int(d) for d in g["dims"]]
+    mc, ns = int(g["mc"]), int(g["num_samples"])
+    net = tp.build_mlp(dims, mc, torch.nn.ReLU if act == "relu" else torch.nn.LeakyReLU)
+    layers = [m for m in net if isinstance(m, tp.BayesLinearPort)]
+    with torch.no_grad():
+        for li, l in enumerate(layers):
+            l.weight.loc.copy_(torch.from_numpy(g[f"init_w_mu{li}"]))
+            l.weight.logscale.copy_(torch.from_numpy(g[f"init_w_rho{li}"]))
+            l.bias.loc.copy_(torch.from_numpy(g[f"init_b_mu{li}"]))
+            l.bias.logscale.copy_(torch.from_numpy(g[f"init_b_rho{li}"]))
+    crit = tp.MCNLLPort(ns) if loss == "nll" else tp.MCCrossEntropyPort(ns)
+    opt = torch.optim.Adam(net.parameters(), float(g["lr"]))
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    for s in range(int(g["steps"])):
+        torch.manual_seed(seed + 100 + s)
+        r = tp.train_step(net, crit, opt, x, y, ns, with_accuracy=(loss == "ce"))
+        assert abs(r["loss"] - float(g[f"s{s}_loss"])) / abs(float(g[f"s{s}_loss"])) < 1e-5, s
+    for li, l in enumerate(layers):
+        assert np.allclose(l.weight.loc.detach().numpy(), g[f"final_w_mu{li}"], rtol=1e-4, atol=1e-6)
