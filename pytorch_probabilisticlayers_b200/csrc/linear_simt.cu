@@ -295,7 +295,9 @@ static int fill_params(const pl_linear_args* a, LinearParams& p, const char* who
   PL_CHECK_ARG(a, "%s: NULL args", who);
   PL_CHECK_ARG(a->mc >= 0 && a->batch >= 0 && a->in_features >= 0 && a->out_features >= 0,
                "%s: negative dimension", who);
-  PL_CHECK_ARG(a->x && a->w_mu && a->w_rho, "%s: NULL x / w_mu / w_rho", who);
+  const bool empty_x = (int64_t)a->mc * a->batch * a->in_features == 0;
+  const bool empty_w = (int64_t)a->in_features * a->out_features == 0;
+  PL_CHECK_ARG((a->x || empty_x) && ((a->w_mu && a->w_rho) || empty_w), "%s: NULL x / w_mu / w_rho", who);
   PL_CHECK_ARG((a->b_mu == nullptr) == (a->b_rho == nullptr), "%s: b_mu and b_rho must both be set or NULL", who);
   PL_CHECK_ARG(a->param_mode == PL_PARAM_SHARED_RHO || a->param_mode == PL_PARAM_PER_MC_SIGMA,
                "%s: bad param_mode %d", who, a->param_mode);
