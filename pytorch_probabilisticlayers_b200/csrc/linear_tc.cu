@@ -285,6 +285,189 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fused weight-gradient kernel: one CTA owns a [128 in-rows x 128 out-cols] tile of the weight and
+// walks over all MC samples.  Per sample, dW[mc] = X[mc]^T . dY[mc] (K = batch) is accumulated in
+// TMEM by tcgen05.mma (both operands MN-major straight from the [batch, features] activations via
+// TMA), the accumulator is double-buffered, and the epilogue warps regenerate eps[mc] for the tile
+// from the Philox counter and fold the tile into register accumulators
+//     acc_mu += dW[mc]        acc_rho += dW[mc] * eps[mc]
+// while the tensor core already works on sample mc+1.  dW [MC,I,O] never exists in HBM.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDwStages = 6;
+constexpr int kDwStageBytes = 2 * kSubTileBytes;  // A [128 i x 64 b] + B [128 o x 64 b], bf16
+constexpr int kDwSmemBytes = kDwStages * kDwStageBytes + 1024 + 1024;
+
+struct TcDwParams {
+  int mc, batch, w_in, w_out;
+  int mc_per_split;        // MC samples per blockIdx.z
+  int x_broadcast;         // input has no MC axis
+  int atomic_out;          // several MC splits add into zero-initialised outputs
+  const float* w_rho;      // [I, O]
+  const float* eps_w;      // optional injected eps [mc, I, O]
+  Sampler sw;
+  float* dw_mu;
+  float* dw_rho;
+};
+
+template <bool kInjected>
+__global__ void __launch_bounds__(kTcThreads, 1)
+dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+      const TcDwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sStage = smem_base;
+  const uint32_t bar0 = sStage + kDwStages * kDwStageBytes;
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (kDwStages + s); };
+  auto acc_full = [&](int b) { return bar0 + 8u * (2 * kDwStages + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (2 * kDwStages + 2 + b); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * kDwStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o0 = blockIdx.x * 128, i0 = blockIdx.y * 128;
+  const int mc_begin = blockIdx.z * p.mc_per_split;
+  const int mc_end = min(p.mc, mc_begin + p.mc_per_split);
+  const int num_kb = (p.batch + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDwStages; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), kGenWarps * 32);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_dy);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int mc = mc_begin; mc < mc_end; ++mc) {
+        const int xm = p.x_broadcast ? 0 : mc;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kDwStages, ph = (it / kDwStages) & 1;
+          mbar_wait(empty(s), ph ^ 1);
+          mbar_expect_tx(full(s), kDwStageBytes);
+          const uint32_t dst = sStage + s * kDwStageBytes;
+          // MN-major operand sub-tiles: [64 batch rows] x [64 features = 128 B], two per operand
+          tma_load_3d(dst, &tmap_x, full(s), i0, kb * kBK, xm);
+          tma_load_3d(dst + 8192, &tmap_x, full(s), i0 + 64, kb * kBK, xm);
+          tma_load_3d(dst + kSubTileBytes, &tmap_dy, full(s), o0, kb * kBK, mc);
+          tma_load_3d(dst + kSubTileBytes + 8192, &tmap_dy, full(s), o0 + 64, kb * kBK, mc);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(128, 128, 1, 1);
+      int it = 0;
+      for (int mc = mc_begin, n = 0; mc < mc_end; ++mc, ++n) {
+        const int buf = n & 1;
+        mbar_wait(acc_empty(buf), ((n >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kDwStages, ph = (it / kDwStages) & 1;
+          mbar_wait(full(s), ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = sStage + s * kDwStageBytes, b_addr = a_addr + kSubTileBytes;
+#pragma unroll
+          for (int ks = 0; ks < kBK / 16; ++ks) {
+            // 16 batch rows = two 8-row swizzle groups = 2048 B; 64-feature groups 8192 B apart
+            const uint64_t a_desc = smem_desc_sw128(a_addr + ks * 2048, 8192, 1024);
+            const uint64_t b_desc = smem_desc_sw128(b_addr + ks * 2048, 8192, 1024);
+            mma_bf16_ss(tmem_base + buf * 128, a_desc, b_desc, idesc, (kb | ks) != 0);
+          }
+          mma_commit(empty(s));
+        }
+        mma_commit(acc_full(buf));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: eps regeneration + MC reduction =====================
+    const int gw = warp - 2, q = warp & 3, h = gw >> 2;
+    const int row = i0 + q * 32 + lane;          // weight row (in-feature) this thread owns
+    const int col0 = o0 + h * 64;                // first of its 64 weight columns
+    float acc_mu[64], acc_rho[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc_mu[j] = acc_rho[j] = 0.f;
+    for (int mc = mc_begin, n = 0; mc < mc_end; ++mc, ++n) {
+      const int buf = n & 1;
+      mbar_wait(acc_full(buf), (n >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + h * 64 + c * 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = col0 + c * 16 + g * 4;
+          float4 e;
+          if (kInjected) {
+            e = (row < p.w_in && col < p.w_out)
+                    ? __ldg(reinterpret_cast<const float4*>(
+                          p.eps_w + ((int64_t)mc * p.w_in + row) * p.w_out + col))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+            e = eps4(p.sw, mc, row, col >> 2);
+          }
+          const int j = c * 16 + g * 4;
+          const float d0 = __uint_as_float(v[g * 4 + 0]), d1 = __uint_as_float(v[g * 4 + 1]),
+                      d2 = __uint_as_float(v[g * 4 + 2]), d3 = __uint_as_float(v[g * 4 + 3]);
+          acc_mu[j + 0] += d0; acc_rho[j + 0] = fmaf(d0, e.x, acc_rho[j + 0]);
+          acc_mu[j + 1] += d1; acc_rho[j + 1] = fmaf(d1, e.y, acc_rho[j + 1]);
+          acc_mu[j + 2] += d2; acc_rho[j + 2] = fmaf(d2, e.z, acc_rho[j + 2]);
+          acc_mu[j + 3] += d3; acc_rho[j + 3] = fmaf(d3, e.w, acc_rho[j + 3]);
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(acc_empty(buf));
+    }
+    if (row < p.w_in) {
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        const int col = col0 + j;
+        if (col < p.w_out) {
+          const int64_t idx = (int64_t)row * p.w_out + col;
+          const float4 r = __ldg(reinterpret_cast<const float4*>(p.w_rho + idx));
+          float4 gm = make_float4(acc_mu[j], acc_mu[j + 1], acc_mu[j + 2], acc_mu[j + 3]);
+          float4 gr = make_float4(acc_rho[j] * sigmoid_f(r.x), acc_rho[j + 1] * sigmoid_f(r.y),
+                                  acc_rho[j + 2] * sigmoid_f(r.z), acc_rho[j + 3] * sigmoid_f(r.w));
+          if (p.atomic_out) {
+            atomicAdd(p.dw_mu + idx + 0, gm.x); atomicAdd(p.dw_mu + idx + 1, gm.y);
+            atomicAdd(p.dw_mu + idx + 2, gm.z); atomicAdd(p.dw_mu + idx + 3, gm.w);
+            atomicAdd(p.dw_rho + idx + 0, gr.x); atomicAdd(p.dw_rho + idx + 1, gr.y);
+            atomicAdd(p.dw_rho + idx + 2, gr.z); atomicAdd(p.dw_rho + idx + 3, gr.w);
+          } else {
+            *reinterpret_cast<float4*>(p.dw_mu + idx) = gm;
+            *reinterpret_cast<float4*>(p.dw_rho + idx) = gr;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -323,6 +506,29 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %llu cols %llu)", (int)r,
               (unsigned long long)rows, (unsigned long long)cols);
+    return PL_ERR_CUDA;
+  }
+  return PL_OK;
+}
+
+// 3-D bf16 tensor [mc, rows, cols] (cols innermost), box [1, box_rows, box_cols]: out-of-range rows
+// of one MC sample are zero-filled instead of running into the next sample
+static int make_tmap_bf16_3d(CUtensorMap* m, const void* base, uint64_t mc, uint64_t rows, uint64_t cols,
+                             uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return PL_ERR_CUDA;
+  }
+  const cuuint64_t dims[3] = {cols, rows, mc};
+  const cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
+  const cuuint32_t box[3] = {box_cols, box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
     return PL_ERR_CUDA;
   }
   return PL_OK;
@@ -473,10 +679,56 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
     rc = a->eps_w ? launch_gemm<true, true>(tm, p, st) : launch_gemm<true, false>(tm, p, st);
     if (rc != PL_OK) return rc;
   }
-  if (a->dw_mu || a->db_mu) {
-    // weight / bias gradients: fp32 kernels for now (tcgen05 dW kernel is the next step)
+  if (a->dw_mu) {
+    PL_CHECK_ARG(a->dw_rho, "pl_linear_bwd: dw_mu/dw_rho must both be set or NULL");
+    if (!a->dx) {
+      cast_bf16_kernel<<<ew_grid(MC * B * O / 8, 1024), 256, 0, st>>>(a->dy, w.a_bf16, MC * B * O / 8);
+      PL_LAUNCH_CHECK("cast_bf16_kernel");
+    }
+    const int64_t x_rows = a->x_mc_stride == 0 ? B : MC * B;
+    cast_bf16_kernel<<<ew_grid(x_rows * I / 8, 1024), 256, 0, st>>>(a->x, w.x_bf16, x_rows * I / 8);
+    PL_LAUNCH_CHECK("cast_bf16_kernel");
+    CUtensorMap tmx, tmdy;
+    rc = make_tmap_bf16_3d(&tmx, w.x_bf16, a->x_mc_stride == 0 ? 1 : (uint64_t)MC, (uint64_t)B,
+                           (uint64_t)I, kBK, 64);
+    if (rc != PL_OK) return rc;
+    rc = make_tmap_bf16_3d(&tmdy, w.a_bf16, (uint64_t)MC, (uint64_t)B, (uint64_t)O, kBK, 64);
+    if (rc != PL_OK) return rc;
+    TcDwParams p;
+    p.mc = (int)MC; p.batch = (int)B; p.w_in = (int)I; p.w_out = (int)O;
+    p.x_broadcast = a->x_mc_stride == 0;
+    p.w_rho = a->w_rho; p.eps_w = a->eps_w;
+    p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
+    p.dw_mu = a->dw_mu; p.dw_rho = a->dw_rho;
+    const int tiles = (int)(((I + 127) / 128) * ((O + 127) / 128));
+    int splits = 1;
+    if (tiles < 148) {  // too few weight tiles to fill the GPU: split MC, combine with atomics
+      splits = (2 * 148) / tiles;
+      if (splits > MC) splits = (int)MC;
+      if (splits < 1) splits = 1;
+    }
+    p.mc_per_split = (int)((MC + splits - 1) / splits);
+    splits = (int)((MC + p.mc_per_split - 1) / p.mc_per_split);
+    p.atomic_out = splits > 1;
+    if (p.atomic_out) {
+      PL_CUDA(cudaMemsetAsync(a->dw_mu, 0, sizeof(float) * I * O, st));
+      PL_CUDA(cudaMemsetAsync(a->dw_rho, 0, sizeof(float) * I * O, st));
+    }
+    dim3 grid((unsigned)((O + 127) / 128), (unsigned)((I + 127) / 128), (unsigned)splits);
+    if (a->eps_w) {
+      PL_CUDA(cudaFuncSetAttribute(dw_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes));
+      dw_tc<true><<<grid, kTcThreads, kDwSmemBytes, st>>>(tmx, tmdy, p);
+    } else {
+      PL_CUDA(cudaFuncSetAttribute(dw_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes));
+      dw_tc<false><<<grid, kTcThreads, kDwSmemBytes, st>>>(tmx, tmdy, p);
+    }
+    PL_LAUNCH_CHECK("dw_tc");
+  }
+  if (a->db_mu) {
+    // bias gradients: HBM-bound column sums of dY (fp32 kernels)
     pl_linear_args b = *a;
     b.dx = nullptr;
+    b.dw_mu = b.dw_rho = nullptr;
     b.precision = PL_PREC_FP32;
     rc = linear_bwd_simt_launch(&b);
     if (rc != PL_OK) return rc;

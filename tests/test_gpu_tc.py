@@ -1,0 +1,137 @@
+"""bf16 tensor-core path (tcgen05/TMEM/TMA kernels) against the reference's golden vectors, the
+fp64 oracle and the fp32 path.  Tolerance: rel 2e-2 (north_star's bf16 mode)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import closed_form as cf
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def plb():
+    import pytorch_probabilisticlayers_b200 as p
+    assert torch.cuda.is_available()
+    p.set_precision("fp32")
+    p.set_eps_source("philox")
+    return p
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_tc_injected_eps_matches_reference_golden(plb):
+    """The reference's own torch.randn draws through the tcgen05 kernels (128^3 tile, MC=2)."""
+    g = load_golden("linear_tile")
+    layer = plb.BayesLinear(128, 128, prior=float(g["prior"])).cuda()
+    layer.precision = "bf16"
+    with torch.no_grad():
+        layer.weight.loc.copy_(dev(g["w_mu"]))
+        layer.weight.logscale.copy_(dev(g["w_rho"]))
+        layer.bias.loc.copy_(dev(g["b_mu"]))
+        layer.bias.logscale.copy_(dev(g["b_rho"]))
+    layer.inject_eps(dev(g["eps_w"]), dev(g["eps_b"]))
+    x = dev(g["x"]).requires_grad_(True)
+    out = layer(x)
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < BF16_TOL
+    assert abs(layer.kl_div.item() - g["kl"]) / abs(g["kl"]) < 1e-5
+    (out * dev(g["gy"])).sum().backward()
+    assert rel_err(x.grad.cpu().numpy(), g["dx"]) < BF16_TOL
+    assert rel_err(layer.weight.loc.grad.cpu().numpy(), g["dw_mu"]) < BF16_TOL
+    assert rel_err(layer.weight.logscale.grad.cpu().numpy(), g["dw_rho"]) < BF16_TOL
+    assert rel_err(layer.bias.loc.grad.cpu().numpy(), g["db_mu"]) < 1e-4
+    assert rel_err(layer.bias.logscale.grad.cpu().numpy(), g["db_rho"]) < 1e-4
+
+
+@pytest.mark.parametrize("mc,b,i,o,bias,expand", [
+    (2, 128, 128, 128, True, False),      # one tile
+    (1, 128, 64, 128, False, False),      # single k-block, no bias
+    (3, 512, 256, 384, True, False),      # MT=4: full-batch tile, 512 TMEM columns
+    (2, 256, 192, 256, True, False),      # MT=2
+    (2, 200, 192, 200, True, False),      # ragged batch rows and ragged N tile
+    (2, 300, 200, 136, True, False),      # K tail (200 % 64 = 8), batch tail in the dW reduction
+    (1, 640, 128, 128, True, False),      # more than 512 rows: two row blocks
+    (4, 512, 512, 256, True, True),       # MC-broadcast input (stride 0)
+    (5, 64, 1024, 8, True, False),        # minimum width
+])
+def test_tc_philox_matches_fp64_oracle(plb, mc, b, i, o, bias, expand):
+    """Production mode (eps synthesised on chip): dump the stream, evaluate the closed forms in fp64."""
+    torch.manual_seed(mc * 1000 + b)
+    plb.manual_seed(4242 + o)
+    layer = plb.BayesLinear(i, o, bias=bias).cuda()
+    layer.precision = "bf16"
+    with torch.no_grad():
+        layer.weight.logscale.uniform_(-5, -1)
+        if bias:
+            layer.bias.logscale.uniform_(-3, 0)
+    if expand:
+        x = torch.randn(b, i, device="cuda").unsqueeze(0).expand(mc, b, i)
+    else:
+        x = torch.randn(mc, b, i, device="cuda", requires_grad=True)
+    gy = torch.randn(mc, b, o, device="cuda")
+    out = layer(x)
+    (out * gy).sum().backward()
+    n = lambda t: t.detach().cpu().numpy()
+    eps_w = n(layer.weight.eps)
+    eps_b = n(layer.bias.eps) if bias else None
+    want = cf.linear_fwd(n(x), n(layer.weight.loc), n(layer.weight.logscale), eps_w,
+                         n(layer.bias.loc) if bias else None,
+                         n(layer.bias.logscale) if bias else None, eps_b)
+    assert rel_err(n(out), want) < BF16_TOL
+    bw = cf.linear_bwd(n(gy), n(x), n(layer.weight.loc), n(layer.weight.logscale), eps_w,
+                       n(layer.bias.logscale) if bias else None, eps_b)
+    if not expand:
+        assert rel_err(n(x.grad), bw["dx"]) < BF16_TOL
+    assert rel_err(n(layer.weight.loc.grad), bw["dw_mu"]) < BF16_TOL
+    assert rel_err(n(layer.weight.logscale.grad), bw["dw_rho"]) < BF16_TOL
+    if bias:
+        assert rel_err(n(layer.bias.loc.grad), bw["db_mu"]) < 1e-4
+        assert rel_err(n(layer.bias.logscale.grad), bw["db_rho"]) < 1e-4
+
+
+def test_tc_full_size_properties(plb):
+    """C4 layer shape (MC=8 of 64, B=512, 4096x4096): size-independent properties instead of an
+    oracle run -- linearity in x, MC-shard invariance and agreement with the fp32 path."""
+    torch.manual_seed(9)
+    plb.manual_seed(99)
+    layer = plb.BayesLinear(4096, 4096).cuda()
+    layer.precision = "bf16"
+    x = torch.randn(8, 512, 4096, device="cuda")
+
+    def fwd(inp, lo=0):
+        layer._calls = 0
+        plb.set_mc_shard(lo)
+        try:
+            return layer(inp)
+        finally:
+            plb.set_mc_shard(0)
+
+    with torch.no_grad():
+        y = fwd(x)
+        # linearity: f(2x) - b = 2 (f(x) - b)
+        y0 = fwd(torch.zeros_like(x))
+        y2 = fwd(2 * x)
+        assert rel_err((y2 - y0).cpu().numpy(), (2 * (y - y0)).cpu().numpy()) < 1e-3
+        # MC shards see exactly the unsharded samples (same counter -> bit-identical)
+        ya = fwd(x[:4], 0)
+        yb = fwd(x[4:], 4)
+        assert torch.equal(torch.cat([ya, yb]), y)
+        # fp32 path on the same eps
+        layer.precision = "fp32"
+        yf = fwd(x[:2])
+        assert rel_err(y[:2].cpu().numpy(), yf.cpu().numpy()) < BF16_TOL
+
+
+def test_tc_rejects_unsupported_shapes_loudly(plb):
+    layer = plb.BayesLinear(30, 20).cuda()
+    layer.precision = "bf16"
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        layer(torch.zeros(2, 4, 30, device="cuda"))
+    auto = plb.BayesLinear(30, 20).cuda()
+    auto.precision = "auto"                      # auto falls back to the fp32 kernels by shape
+    assert auto(torch.zeros(2, 4, 30, device="cuda")).shape == (2, 4, 20)
