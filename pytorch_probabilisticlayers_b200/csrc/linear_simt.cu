@@ -324,8 +324,8 @@ int linear_fwd_simt_launch(const pl_linear_args* a) {
   LinearParams p;
   int rc = fill_params(a, p, "pl_linear_fwd");
   if (rc != PL_OK) return rc;
-  PL_CHECK_ARG(a->y, "pl_linear_fwd: NULL y");
   if (p.mc == 0 || p.batch == 0 || p.out == 0) return PL_OK;
+  PL_CHECK_ARG(a->y, "pl_linear_fwd: NULL y");
   PL_CHECK_ARG(p.mc <= 65535 && ceil_div64(p.batch, kT) <= 65535, "pl_linear_fwd: grid too large");
   dim3 grid((unsigned)ceil_div64(p.out, kT), (unsigned)ceil_div64(p.batch, kT), (unsigned)p.mc);
   linear_fwd_simt<<<grid, kThreads, 0, (cudaStream_t)a->stream>>>(p);

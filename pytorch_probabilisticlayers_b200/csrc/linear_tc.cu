@@ -610,11 +610,12 @@ static int launch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_
 int linear_bwd_simt_launch(const pl_linear_args* a);
 
 int linear_fwd_tc_launch(const pl_linear_args* a) {
-  PL_CHECK_ARG(a && a->x && a->w_mu && a->w_rho && a->y, "pl_linear_fwd: NULL pointer");
+  PL_CHECK_ARG(a, "pl_linear_fwd: NULL args");
+  if (a->mc == 0 || a->batch == 0) return PL_OK;
+  PL_CHECK_ARG(a->x && a->w_mu && a->w_rho && a->y, "pl_linear_fwd: NULL pointer");
   PL_CHECK_ARG((a->b_mu == nullptr) == (a->b_rho == nullptr), "pl_linear_fwd: b_mu and b_rho must both be set or NULL");
   int rc = tc_shape_ok(a, "pl_linear_fwd");
   if (rc != PL_OK) return rc;
-  if (a->mc == 0 || a->batch == 0) return PL_OK;
   PL_CHECK_ARG(a->mc <= 65535, "pl_linear_fwd: mc too large");
   if (!a->workspace || a->workspace_bytes < linear_tc_workspace_bytes(a)) {
     set_error("pl_linear_fwd: workspace %zu < %zu bytes", a->workspace_bytes, linear_tc_workspace_bytes(a));
@@ -649,10 +650,11 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
 }
 
 int linear_bwd_tc_launch(const pl_linear_args* a) {
-  PL_CHECK_ARG(a && a->x && a->w_mu && a->w_rho && a->dy, "pl_linear_bwd: NULL pointer");
+  PL_CHECK_ARG(a, "pl_linear_bwd: NULL args");
+  if (a->mc == 0 || a->batch == 0) return linear_bwd_simt_launch(a);
+  PL_CHECK_ARG(a->x && a->w_mu && a->w_rho && a->dy, "pl_linear_bwd: NULL pointer");
   int rc = tc_shape_ok(a, "pl_linear_bwd");
   if (rc != PL_OK) return rc;
-  if (a->mc == 0 || a->batch == 0) return linear_bwd_simt_launch(a);
   if (!a->workspace || a->workspace_bytes < linear_tc_workspace_bytes(a)) {
     set_error("pl_linear_bwd: workspace %zu < %zu bytes", a->workspace_bytes, linear_tc_workspace_bytes(a));
     return PL_ERR_WORKSPACE;
