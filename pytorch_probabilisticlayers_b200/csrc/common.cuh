@@ -63,8 +63,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
                                                uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
-    const uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
+    // one IMAD.WIDE.U32 per product (hi and lo halves of the 64-bit result)
+    const uint64_t p0 = (uint64_t)kPhiloxM0 * c0, p1 = (uint64_t)kPhiloxM1 * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
     c0 = hi1 ^ c1 ^ k0;
     c1 = lo1;
     c2 = hi0 ^ c3 ^ k1;
@@ -82,11 +84,17 @@ __device__ __forceinline__ float unit_float(uint32_t u) {
 
 // one Box-Muller pair: f = 2 - t(u_r) in (0,1], r = sqrt(-2 ln f), theta = 2pi t(u_a) - 3pi
 __device__ __forceinline__ void box_muller(uint32_t u_r, uint32_t u_a, float& n_cos, float& n_sin) {
+  // MUFU-rate math (lg2 / sqrt / sin / cos .approx): f is a normal number in [2^-23, 1], so no
+  // denormal or slow-path handling is needed
   const float f = 2.0f - unit_float(u_r);
-  const float r = sqrtf(-1.3862943611198906f * __log2f(f));
+  float lg, r, sn, cs;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(f));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg));
   const float theta = fmaf(unit_float(u_a), 6.283185307179586f, -9.42477796076938f);
-  n_cos = r * __cosf(theta);
-  n_sin = r * __sinf(theta);
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(theta));
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(theta));
+  n_cos = r * cs;
+  n_sin = r * sn;
 }
 
 struct Sampler {

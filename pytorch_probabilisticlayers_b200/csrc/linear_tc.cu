@@ -23,6 +23,8 @@
 // sampler's ALU/MUFU budget: every generated element feeds only 2*B flops.
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -32,8 +34,8 @@ using namespace tc;
 
 constexpr int kBN = 128;               // output-column tile (UMMA N)
 constexpr int kBK = 64;                // k-block (one 128-byte swizzle row of bf16)
-constexpr int kTcThreads = 320;        // 10 warps
-constexpr int kGenWarps = 8;
+constexpr int kGenWarps = 16;          // generator / epilogue warps (4 per SM sub-partition)
+constexpr int kTcThreads = 64 + kGenWarps * 32;  // + TMA warp + MMA warp = 18 warps
 constexpr int kSubTileBytes = 128 * kBK * 2;  // one [128 x 64] bf16 operand sub-tile = 16 KB
 
 struct TcGemmParams {
@@ -202,79 +204,90 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
     __syncwarp();
   } else {
     // ===================== W-tile generators =====================
-    const int gw = warp - 2;  // 0..7
-    for (int kb = 0; kb < num_kb; ++kb) {
+    // operand element (n, k): forward W[i = k0+k][o = n0+n]; dX W[i = n0+n][o = k0+k].
+    // Each thread owns 4 groups of 4 consecutive o per k-block (one Philox call per group).
+    const int gw = warp - 2;  // 0..15
+    int wrow[4], wcol;        // weight coordinates of the thread's groups at k-block 0
+    uint32_t soff[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (!kDx) {
+        // k = gw + 16 r, n = 4 lane.  MN-major SW128:
+        // [n/64]*8192 + [k/8]*1024 + (k%8)*128 + (((n%64)/8) ^ (k%8))*16 + (n%8)*2
+        wrow[r] = gw + 16 * r;
+        soff[r] = (uint32_t)((lane >> 4) * 8192 + ((gw >> 3) + 2 * r) * 1024 + (gw & 7) * 128 +
+                             ((((lane & 15) >> 1) ^ (gw & 7)) << 4) + ((lane & 1) << 3));
+      } else {
+        // n = 8 gw + 2 r + lane/16, k = 4 (lane%16).  K-major SW128: n*128 + (((k/8) ^ (n%8))*16) + (k%8)*2
+        const int n = 8 * gw + 2 * r + (lane >> 4);
+        wrow[r] = n0 + n;
+        soff[r] = (uint32_t)(n * 128 + ((((lane & 15) >> 1) ^ (n & 7)) << 4) + ((lane & 1) << 3));
+      }
+    }
+    wcol = kDx ? 4 * (lane & 15) : n0 + 4 * lane;
+    const int64_t ldw = p.w_out;
+    const float* eps_base = kInjected ? p.eps_w + (int64_t)mc * p.w_in * p.w_out : nullptr;
+
+    auto gen_block = [&](int kb, auto full_tag) {
+      constexpr bool kFull = decltype(full_tag)::value;
       const int s = kb % Cfg::kStagesB, ph = (kb / Cfg::kStagesB) & 1;
       const int k0 = kb * kBK;
-      float4 mu[8], sg[8], ep[8];
-      int wrow[8], wcol[8];
-      uint32_t soff[8];
-      // operand element (n, k): forward W[i = k0+k][o = n0+n]; dX W[i = n0+n][o = k0+k].
-      // Each thread owns 8 groups of 4 consecutive o (one Philox call each).
+      float4 mu[4], sg[4], ep[4];
+      int row[4];
+      const int col = kDx ? k0 + wcol : wcol;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if (!kDx) {
-          const int k = gw + 8 * r, n = 4 * lane;          // k row, 4 consecutive n
-          wrow[r] = k0 + k;
-          wcol[r] = n0 + n;
-          // MN-major SW128: [n/64]*8192 + [k/8]*1024 + (k%8)*128 + (((n%64)/8) ^ (k%8))*16 + (n%8)*2
-          soff[r] = (uint32_t)((lane >> 4) * 8192 + r * 1024 + gw * 128 +
-                               ((((lane & 15) >> 1) ^ gw) << 4) + ((lane & 1) << 3));
-        } else {
-          const int n = 16 * gw + 2 * r + (lane >> 4), k = 4 * (lane & 15);  // n row, 4 consecutive k
-          wrow[r] = n0 + n;
-          wcol[r] = k0 + k;
-          // K-major SW128: n*128 + (((k/8) ^ (n%8)) * 16) + (k%8)*2
-          soff[r] = (uint32_t)(n * 128 + ((((lane & 15) >> 1) ^ (n & 7)) << 4) + ((lane & 1) << 3));
-        }
-        const bool ok = wrow[r] < p.w_in && wcol[r] < p.w_out;
-        const int64_t idx = (int64_t)wrow[r] * p.w_out + wcol[r];
-        mu[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_mu + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        sg[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_sigma + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kInjected)
-          ep[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.eps_w + (int64_t)mc * p.w_in * p.w_out + idx))
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < 4; ++r) {
+        row[r] = kDx ? wrow[r] : k0 + wrow[r];
+        const bool ok = kFull || (row[r] < p.w_in && col < p.w_out);
+        const int64_t idx = (int64_t)row[r] * ldw + col;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        mu[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_mu + idx)) : z;
+        sg[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_sigma + idx)) : z;
+        if (kInjected) ep[r] = ok ? __ldg(reinterpret_cast<const float4*>(eps_base + idx)) : z;
       }
       mbar_wait(b_empty(s), ph ^ 1);
       const uint32_t dst = sB + s * kSubTileBytes;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
+      for (int r = 0; r < 4; ++r) {
         float4 e;
         if (kInjected) e = ep[r];
-        else e = eps4(p.sw, mc, wrow[r], wcol[r] >> 2);
+        else e = eps4(p.sw, mc, row[r], col >> 2);
         const uint32_t lo = pack_bf16x2(fmaf(sg[r].x, e.x, mu[r].x), fmaf(sg[r].y, e.y, mu[r].y));
         const uint32_t hi = pack_bf16x2(fmaf(sg[r].z, e.z, mu[r].z), fmaf(sg[r].w, e.w, mu[r].w));
         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + soff[r]), "r"(lo), "r"(hi) : "memory");
       }
       fence_proxy_async_smem();
       mbar_arrive(b_full(s));
+    };
+    // tiles fully inside the weight matrix take the predicate-free path
+    const bool n_full = kDx ? (n0 + kBN <= p.w_in) : (n0 + kBN <= p.w_out);
+    const int k_extent = kDx ? p.w_out : p.w_in;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      if (n_full && (kb + 1) * kBK <= k_extent) gen_block(kb, std::true_type{});
+      else gen_block(kb, std::false_type{});
     }
     // ===================== epilogue: TMEM -> registers -> HBM =====================
     mbar_wait(acc_full, 0);
     tc_fence_after_sync();
     const int q = warp & 3;        // TMEM lane quadrant this warp may access
-    const int h = gw >> 2;         // which 64-column half of the tile
+    const int col = (gw >> 2) * 32;  // which 32-column quarter of the tile
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
       const int row = m0 + mt * 128 + q * 32 + lane;
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int col = h * 64 + cc * 32;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * kBN + col), v);
-        tmem_ld_wait();
-        if (row < p.rows) {
-          float* o = p.out + ((int64_t)mc * p.rows + row) * p.ndim + n0 + col;
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * kBN + col), v);
+      tmem_ld_wait();
+      if (row < p.rows) {
+        float* o = p.out + ((int64_t)mc * p.rows + row) * p.ndim + n0 + col;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n0 + col + j < p.ndim) {
-              float4 w;
-              w.x = __uint_as_float(v[j + 0]) + bias_s[col + j + 0];
-              w.y = __uint_as_float(v[j + 1]) + bias_s[col + j + 1];
-              w.z = __uint_as_float(v[j + 2]) + bias_s[col + j + 2];
-              w.w = __uint_as_float(v[j + 3]) + bias_s[col + j + 3];
-              *reinterpret_cast<float4*>(o + j) = w;
-            }
+        for (int j = 0; j < 32; j += 4) {
+          if (n0 + col + j < p.ndim) {
+            float4 w;
+            w.x = __uint_as_float(v[j + 0]) + bias_s[col + j + 0];
+            w.y = __uint_as_float(v[j + 1]) + bias_s[col + j + 1];
+            w.z = __uint_as_float(v[j + 2]) + bias_s[col + j + 2];
+            w.w = __uint_as_float(v[j + 3]) + bias_s[col + j + 3];
+            *reinterpret_cast<float4*>(o + j) = w;
           }
         }
       }
@@ -402,19 +415,20 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
   } else {
     // ===================== epilogue: eps regeneration + MC reduction =====================
     const int gw = warp - 2, q = warp & 3, h = gw >> 2;
+    constexpr int kCols = 128 / (kGenWarps / 4);   // weight columns per thread (32)
     const int row = i0 + q * 32 + lane;          // weight row (in-feature) this thread owns
-    const int col0 = o0 + h * 64;                // first of its 64 weight columns
-    float acc_mu[64], acc_rho[64];
+    const int col0 = o0 + h * kCols;             // first of its weight columns
+    float acc_mu[kCols], acc_rho[kCols];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc_mu[j] = acc_rho[j] = 0.f;
+    for (int j = 0; j < kCols; ++j) acc_mu[j] = acc_rho[j] = 0.f;
     for (int mc = mc_begin, n = 0; mc < mc_end; ++mc, ++n) {
       const int buf = n & 1;
       mbar_wait(acc_full(buf), (n >> 1) & 1);
       tc_fence_after_sync();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < kCols / 16; ++c) {
         uint32_t v[16];
-        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + h * 64 + c * 16), v);
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + h * kCols + c * 16), v);
         tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -442,7 +456,7 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
     }
     if (row < p.w_in) {
 #pragma unroll
-      for (int j = 0; j < 64; j += 4) {
+      for (int j = 0; j < kCols; j += 4) {
         const int col = col0 + j;
         if (col < p.w_out) {
           const int64_t idx = (int64_t)row * p.w_out + col;
