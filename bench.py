@@ -334,7 +334,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c4")
-    ap.add_argument("--precision", choices=["fp32", "bf16", "auto"], default="fp32")
+    ap.add_argument("--precision", choices=["fp32", "bf16", "auto"], default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -32,7 +32,7 @@ from . import functional as PF
 # ------------------------------------------------------------------------------------------------
 _STATE = {
     "seed": 0x5EEDB200,          # base Philox key; combined with a per-layer call counter
-    "precision": "fp32",         # 'fp32' | 'bf16' | 'auto'
+    "precision": "auto",         # 'fp32' | 'bf16' | 'auto' (bf16 tensor cores when the shape tiles)
     "eps_source": "philox",      # 'philox' | 'torch_cpu'
     "mc_global_offset": 0,       # first global MC index of this rank (MC sharding)
     "next_layer_id": 0,

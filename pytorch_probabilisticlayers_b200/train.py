@@ -58,7 +58,7 @@ class ELBOTrainStep:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.stats = self.flat[n:n + 4]
-        self.opt = torch.optim.Adam(self.params, lr, fused=True)
+        self.opt = torch.optim.Adam(self.params, lr, fused=dev.type == "cuda")
         # fused KL gradient: layers compute kl_div without an autograd graph
         self.kl_layers = [m for m in net.modules()
                           if isinstance(m, (BayesLinear, BayesConv2d)) and isinstance(m, self.kl_kinds)]
@@ -88,7 +88,7 @@ class ELBOTrainStep:
                 kl_value = kl_value + m.kl_div.detach()
         loss = ll if kl_graph is None else ll + kl_graph * inv
         loss.backward()
-        stream = _cabi.current_stream(pred.device)
+        stream = _cabi.current_stream(pred.device) if self.kl_layers else None
         for m in self.kl_layers:
             if m.kl_div.requires_grad:      # e.g. Laplace prior: went through autograd above
                 continue
