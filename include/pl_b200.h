@@ -74,7 +74,9 @@ int pl_eps_dump(uint64_t seed, uint32_t stream_id, uint32_t mc_global_offset, in
  *      Normal.entropy().sum() at src/ProbabilisticLayers.py:955-956 and :1059) ---------------
  * out2[0] = sum 0.5[(s/sp)^2 + (mu/sp)^2 - 1 - log((s/sp)^2)],  out2[1] = sum 0.5+0.5log(2pi)+log s
  * prior_scale_elem (optional, per-element prior scale, n floats) overrides prior_scale.
- * workspace: pl_kl_workspace_bytes() bytes.  Deterministic (fixed reduction tree). */
+ * workspace: pl_kl_workspace_bytes() bytes, ZERO-INITIALISED before its first use; every call
+ * leaves it zeroed again, so one buffer can be reused by successive calls on the same stream.
+ * Single launch, deterministic (fixed reduction tree). */
 size_t pl_kl_workspace_bytes(void);
 int pl_kl_fwd(const float* mu, const float* rho, int64_t n, float prior_scale,
               const float* prior_scale_elem, float* out2, void* workspace, size_t workspace_bytes,

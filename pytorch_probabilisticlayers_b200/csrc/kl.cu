@@ -6,7 +6,8 @@
 // Roofline: HBM.  Algorithmic bytes: forward 8*n (mu, rho fp32; +4*n with a per-element prior),
 // backward 16*n (24*n when accumulating).  One pass, 128-bit loads, 4 independent loads per thread
 // in flight, grid = 4 CTAs x 148 SMs, warp-shuffle + one block tree reduction, fp64 across blocks
-// in a fixed order (deterministic; a second 1-CTA launch finishes the tree).
+// in a fixed order (deterministic; the block that draws the last ticket finishes the tree, so the
+// reduction is a single launch).
 #include <math.h>
 
 #include "common.cuh"
@@ -49,11 +50,14 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   return v;
 }
 
-// partials[block] = (sum A, sum log sigma, sum log prior_scale_elem) as doubles
+// partials[block] = (sum A, sum log sigma, sum log prior_scale_elem) as doubles; the block that
+// takes the last ticket reduces the partials in a fixed order (deterministic), writes out2 and
+// resets the ticket, so the whole reduction is ONE launch.
 template <bool kElemPrior, bool kVec>
 __global__ void __launch_bounds__(kKlThreads)
 kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ rho,
-              const float* __restrict__ pse, int64_t n, float ip2, double* __restrict__ partials) {
+              const float* __restrict__ pse, int64_t n, float ip2, double* __restrict__ partials,
+              unsigned int* __restrict__ ticket, double log_ps_total, float* __restrict__ out2) {
   float a = 0.f, l = 0.f, p = 0.f;
   const int64_t tid = (int64_t)blockIdx.x * kKlThreads + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * kKlThreads;
@@ -118,38 +122,41 @@ kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ rho,
       partials[3 * blockIdx.x + 2] = dp;
     }
   }
-}
-
-// kl = sumA - sumL + sumP - n/2 ; entropy = sumL + n (0.5 + 0.5 log 2pi)
-__global__ void __launch_bounds__(kKlThreads)
-kl_finish_kernel(const double* __restrict__ partials, int nblocks, int64_t n, double log_ps_total,
-                 float* __restrict__ out2) {
-  double a = 0.0, l = 0.0, p = 0.0;
-  for (int i = threadIdx.x; i < nblocks; i += kKlThreads) {
-    a += partials[3 * i + 0];
-    l += partials[3 * i + 1];
-    p += partials[3 * i + 2];
+  // ---- last block finishes ----
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
-  a = warp_sum(a);
-  l = warp_sum(l);
-  p = warp_sum(p);
-  __shared__ double sm[3][kKlThreads / 32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double a2 = 0.0, l2 = 0.0, p2 = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += kKlThreads) {
+    a2 += __ldcg(partials + 3 * i + 0);
+    l2 += __ldcg(partials + 3 * i + 1);
+    p2 += __ldcg(partials + 3 * i + 2);
+  }
+  a2 = warp_sum(a2);
+  l2 = warp_sum(l2);
+  p2 = warp_sum(p2);
+  __syncthreads();
   if (lane == 0) {
-    sm[0][warp] = a;
-    sm[1][warp] = l;
-    sm[2][warp] = p;
+    sm[0][warp] = a2;
+    sm[1][warp] = l2;
+    sm[2][warp] = p2;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    a = l = p = 0.0;
+    a2 = l2 = p2 = 0.0;
     for (int w = 0; w < kKlThreads / 32; ++w) {
-      a += sm[0][w];
-      l += sm[1][w];
-      p += sm[2][w];
+      a2 += sm[0][w];
+      l2 += sm[1][w];
+      p2 += sm[2][w];
     }
-    out2[0] = (float)(a - l + p + log_ps_total - 0.5 * (double)n);
-    out2[1] = (float)(l + (double)n * (0.5 + 0.9189385332046727));
+    out2[0] = (float)(a2 - l2 + p2 + log_ps_total - 0.5 * (double)n);
+    out2[1] = (float)(l2 + (double)n * (0.5 + 0.9189385332046727));
+    *ticket = 0;   // leave the workspace ready for the next call
   }
 }
 
@@ -240,7 +247,7 @@ static inline int kl_grid(int64_t n) {
 
 }  // namespace pl
 
-extern "C" size_t pl_kl_workspace_bytes(void) { return sizeof(double) * 3 * pl::kKlBlocks; }
+extern "C" size_t pl_kl_workspace_bytes(void) { return sizeof(double) * 3 * pl::kKlBlocks + 64; }
 
 extern "C" int pl_kl_fwd(const float* mu, const float* rho, int64_t n, float prior_scale,
                          const float* prior_scale_elem, float* out2, void* workspace,
@@ -255,20 +262,23 @@ extern "C" int pl_kl_fwd(const float* mu, const float* rho, int64_t n, float pri
   }
   cudaStream_t st = (cudaStream_t)stream;
   double* partials = (double*)workspace;
+  unsigned int* ticket = (unsigned int*)((char*)workspace + sizeof(double) * 3 * kKlBlocks);
   const int grid = kl_grid(n);
+  const double log_ps_total = prior_scale_elem ? 0.0 : (double)n * log((double)prior_scale);
   const bool vec = aligned16(mu) && aligned16(rho) && (!prior_scale_elem || aligned16(prior_scale_elem));
   const float ip2 = prior_scale_elem ? 1.f : 1.f / (prior_scale * prior_scale);
+#define PL_KL_FWD(EP, VEC)                                                                        \
+  kl_fwd_kernel<EP, VEC><<<grid, kKlThreads, 0, st>>>(mu, rho, prior_scale_elem, n, ip2, partials, \
+                                                      ticket, log_ps_total, out2)
   if (prior_scale_elem) {
-    if (vec) kl_fwd_kernel<true, true><<<grid, kKlThreads, 0, st>>>(mu, rho, prior_scale_elem, n, ip2, partials);
-    else     kl_fwd_kernel<true, false><<<grid, kKlThreads, 0, st>>>(mu, rho, prior_scale_elem, n, ip2, partials);
+    if (vec) PL_KL_FWD(true, true);
+    else PL_KL_FWD(true, false);
   } else {
-    if (vec) kl_fwd_kernel<false, true><<<grid, kKlThreads, 0, st>>>(mu, rho, nullptr, n, ip2, partials);
-    else     kl_fwd_kernel<false, false><<<grid, kKlThreads, 0, st>>>(mu, rho, nullptr, n, ip2, partials);
+    if (vec) PL_KL_FWD(false, true);
+    else PL_KL_FWD(false, false);
   }
+#undef PL_KL_FWD
   PL_LAUNCH_CHECK("kl_fwd_kernel");
-  const double log_ps_total = prior_scale_elem ? 0.0 : (double)n * log((double)prior_scale);
-  kl_finish_kernel<<<1, kKlThreads, 0, st>>>(partials, grid, n, log_ps_total, out2);
-  PL_LAUNCH_CHECK("kl_finish_kernel");
   return PL_OK;
 }
 

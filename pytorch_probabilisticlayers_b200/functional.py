@@ -54,6 +54,20 @@ def _timed(tag, fn):
     return r
 
 
+_KL_WS = {}
+
+
+def _kl_workspace(device):
+    """Zero-initialised, self-resetting ticket workspace of pl_kl_fwd, one per (device, stream)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _KL_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_cabi.lib().pl_kl_workspace_bytes()), dtype=torch.uint8, device=device)
+        _KL_WS[key] = ws
+    return ws
+
+
 def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -244,7 +258,7 @@ class _KLFn(torch.autograd.Function):
         mu_c, rho_c = mu.contiguous(), rho.contiguous()
         pse = prior_scale_elem.contiguous() if prior_scale_elem is not None else None
         out = torch.empty(2, dtype=torch.float32, device=mu.device)
-        ws = _workspace(lib.pl_kl_workspace_bytes(), mu.device)
+        ws = _kl_workspace(mu.device)
         with torch.cuda.device(mu.device):
             _timed(f"kl_fwd[{mu_c.numel()}]", lambda: _cabi.check(
                 lib.pl_kl_fwd(_cabi.ptr(mu_c), _cabi.ptr(rho_c), mu_c.numel(), float(prior_scale),

@@ -8,10 +8,14 @@ experiments/RegressionBNN.py:109-120, experiments/SIVILastLayer.py:287-296):
 with Adam (BNN.py:349).  Sharding: the Monte-Carlo samples are independent given
 (mu, rho), so rank r of N owns global samples [r*MC/N, (r+1)*MC/N), holds a full parameter replica
 and sees the full batch.  The cross-entropy ELBO decomposes over samples, so the only exchange is
-ONE all-reduce(sum) per step over a flat fp32 buffer [all gradients | LL, KL, ACC scalars]; KL and
+an all-reduce(sum) of one flat fp32 buffer [all gradients | LL, KL, ACC scalars] per step; KL and
 its gradient are replica-identical and are pre-scaled by 1/N instead of being reduced separately.
 The KL gradient is streamed straight into the flat gradient buffer by ``pl_kl_bwd(accumulate=1)``
-(no autograd temporaries).
+(no autograd temporaries).  With ``overlap=True`` (default) the flat buffer is reduced in per-layer
+slices: a layer's slice is handed to NCCL (async, on NCCL's own stream) from a
+post-accumulate-grad hook as soon as that layer's backward kernels have been enqueued, so the
+transfer of layer L runs under the backward of layer L-1 and only the first layer's slice is
+exposed (SURVEY.md hard part H3).
 """
 from __future__ import annotations
 
@@ -39,7 +43,8 @@ def collect_kl_div(net, kinds=(BayesLinear, SIVILayer)):
 class ELBOTrainStep:
     def __init__(self, net: torch.nn.Module, criterion, num_samples: int, lr: float = 1e-3,
                  kl_kinds: Iterable = (BayesLinear, SIVILayer), with_accuracy: bool = True,
-                 group: Optional[dist.ProcessGroup] = None, mc_coupled_loss: bool = False):
+                 group: Optional[dist.ProcessGroup] = None, mc_coupled_loss: bool = False,
+                 overlap: bool = True):
         self.net, self.criterion, self.num_samples = net, criterion, int(num_samples)
         self.kl_kinds = tuple(kl_kinds)
         self.with_accuracy = with_accuracy
@@ -64,6 +69,63 @@ class ELBOTrainStep:
                           if isinstance(m, (BayesLinear, BayesConv2d)) and isinstance(m, self.kl_kinds)]
         for m in self.kl_layers:
             m.kl_autograd = False
+        # per-layer slices of the flat buffer for the overlapped all-reduce
+        self.overlap = overlap and self.world > 1
+        self._handles = []
+        self._slices = []          # (start, end, layer or None)
+        self._inv = 1.0 / (self.num_samples * self.world)
+        if self.overlap:
+            start_of = {}
+            off = 0
+            for p in self.params:
+                start_of[id(p)] = off
+                off += p.numel()
+            covered = []
+            self._uncovered = []
+            for m in self.kl_layers:
+                ps = [p for p in m.parameters() if p.requires_grad]
+                lo = min(start_of[id(p)] for p in ps)
+                hi = max(start_of[id(p)] + p.numel() for p in ps)
+                if hi - lo != sum(p.numel() for p in ps):
+                    self._uncovered.append(m)     # not contiguous in the flat buffer: leave to the tail
+                    continue
+                state = {"left": len(ps), "n": len(ps), "lo": lo, "hi": hi, "layer": m}
+                covered.append((lo, hi))
+                for p in ps:
+                    p.register_post_accumulate_grad_hook(self._make_hook(state))
+            # everything not covered by a layer slice (+ the stats tail) goes in the final reduce
+            covered.sort()
+            cur, rest = 0, []
+            for lo, hi in covered:
+                if lo > cur:
+                    rest.append((cur, lo))
+                cur = hi
+            rest.append((cur, n + 4))
+            self._rest = rest
+
+    def _kl_backward(self, m):
+        """Stream the analytic KL gradient of layer m (scaled 1/(N*num_samples)) into its .grad."""
+        if m.kl_div.requires_grad:               # e.g. Laplace prior: went through autograd
+            return
+        lib = _cabi.lib()
+        w = m.weight
+        prior = m.prior.scale if isinstance(m, BayesLinear) else m.prior_scale
+        stream = _cabi.current_stream(w.loc.device)
+        PF._timed(f"kl_bwd_acc[{w.loc.numel()}]", lambda: _cabi.check(
+            lib.pl_kl_bwd(w.loc.data_ptr(), w.logscale.data_ptr(), w.loc.numel(), float(prior),
+                          None, None, None, self._inv, w.loc.grad.data_ptr(),
+                          w.logscale.grad.data_ptr(), 1, stream), "pl_kl_bwd"))
+
+    def _make_hook(self, state):
+        def hook(_param):
+            state["left"] -= 1
+            if state["left"] == 0:
+                state["left"] = state["n"]
+                self._kl_backward(state["layer"])
+                self._handles.append(dist.all_reduce(self.flat[state["lo"]:state["hi"]],
+                                                     op=dist.ReduceOp.SUM, group=self.group,
+                                                     async_op=True))
+        return hook
 
     def set_shard(self, total_mc: int):
         """Local MC count for a global ``total_mc`` and registers this rank's global MC offset."""
@@ -74,7 +136,6 @@ class ELBOTrainStep:
 
     def step(self, x, y):
         """One optimiser step; returns a device tensor [LL, KL, ACC, loss] (global values)."""
-        lib = _cabi.lib()
         self.flat.zero_()
         pred = self.net(x)
         inv = 1.0 / (self.num_samples * self.world)
@@ -87,24 +148,26 @@ class ELBOTrainStep:
                     kl_graph = m.kl_div if kl_graph is None else kl_graph + m.kl_div
                 kl_value = kl_value + m.kl_div.detach()
         loss = ll if kl_graph is None else ll + kl_graph * inv
-        loss.backward()
-        stream = _cabi.current_stream(pred.device) if self.kl_layers else None
-        for m in self.kl_layers:
-            if m.kl_div.requires_grad:      # e.g. Laplace prior: went through autograd above
-                continue
-            w = m.weight
-            prior = m.prior.scale if isinstance(m, BayesLinear) else m.prior_scale
-            PF._timed(f"kl_bwd_acc[{w.loc.numel()}]", lambda: _cabi.check(
-                lib.pl_kl_bwd(w.loc.data_ptr(), w.logscale.data_ptr(), w.loc.numel(), float(prior),
-                              None, None, None, inv, w.loc.grad.data_ptr(),
-                              w.logscale.grad.data_ptr(), 1, stream), "pl_kl_bwd"))
-        with torch.no_grad():
+        with torch.no_grad():               # before backward: the tail slice is reduced last
             self.stats[0] = ll.detach()
             self.stats[1] = kl_value * inv
             if self.with_accuracy:
                 self.stats[2] = MC_Accuracy(pred.detach(), y)[0] / self.world
-        if self.world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        loss.backward()                     # overlap mode: hooks launch per-layer KL grad + all-reduce
+        if not self.overlap:
+            for m in self.kl_layers:
+                self._kl_backward(m)
+            if self.world > 1:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            for m in self._uncovered:
+                self._kl_backward(m)
+            for lo, hi in self._rest:
+                self._handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM,
+                                                     group=self.group, async_op=True))
+            for h in self._handles:
+                h.wait()
+            self._handles.clear()
         self.opt.step()
         out = self.stats.clone()
         out[3] = out[0] + out[1]
