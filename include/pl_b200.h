@@ -123,9 +123,15 @@ typedef struct pl_linear_args {
   void* workspace;
   size_t workspace_bytes;
   void* stream;
+  /* optional forward->backward state (pl_linear_state_bytes): pl_linear_fwd leaves
+     sigma = softplus(rho) and the bf16 copy of x there; pl_linear_bwd called with the same
+     buffer skips recomputing them (and then does not read x).  NULL = stateless. */
+  void* fwd_state;
+  size_t fwd_state_bytes;
 } pl_linear_args;
 
 size_t pl_linear_workspace_bytes(const pl_linear_args* a);
+size_t pl_linear_state_bytes(const pl_linear_args* a);
 int pl_linear_fwd(const pl_linear_args* a);
 int pl_linear_bwd(const pl_linear_args* a);
 

@@ -23,7 +23,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32}
 EXPORTS = (
     "pl_version", "pl_last_error", "pl_launch_count", "pl_device_supported", "pl_eps_dump",
     "pl_kl_workspace_bytes", "pl_kl_fwd", "pl_kl_bwd",
-    "pl_linear_workspace_bytes", "pl_linear_fwd", "pl_linear_bwd",
+    "pl_linear_workspace_bytes", "pl_linear_state_bytes", "pl_linear_fwd", "pl_linear_bwd",
     "pl_conv2d_fwd", "pl_conv2d_bwd",
 )
 
@@ -39,6 +39,7 @@ class LinearArgs(C.Structure):
         ("y", C.c_void_p), ("dy", C.c_void_p), ("dx", C.c_void_p),
         ("dw_mu", C.c_void_p), ("dw_rho", C.c_void_p), ("db_mu", C.c_void_p), ("db_rho", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("stream", C.c_void_p),
+        ("fwd_state", C.c_void_p), ("fwd_state_bytes", C.c_size_t),
     ]
 
 
@@ -90,6 +91,8 @@ def lib():
                                         C.c_int32, C.c_void_p]
                 l.pl_linear_workspace_bytes.restype = C.c_size_t
                 l.pl_linear_workspace_bytes.argtypes = [C.POINTER(LinearArgs)]
+                l.pl_linear_state_bytes.restype = C.c_size_t
+                l.pl_linear_state_bytes.argtypes = [C.POINTER(LinearArgs)]
                 for name in ("pl_linear_fwd", "pl_linear_bwd"):
                     getattr(l, name).restype = C.c_int
                     getattr(l, name).argtypes = [C.POINTER(LinearArgs)]

@@ -6,6 +6,7 @@ size_t linear_simt_workspace_bytes(const pl_linear_args* a);
 int linear_fwd_simt_launch(const pl_linear_args* a);
 int linear_bwd_simt_launch(const pl_linear_args* a);
 size_t linear_tc_workspace_bytes(const pl_linear_args* a);
+size_t linear_tc_state_bytes(const pl_linear_args* a);
 int linear_fwd_tc_launch(const pl_linear_args* a);
 int linear_bwd_tc_launch(const pl_linear_args* a);
 }  // namespace pl
@@ -14,6 +15,11 @@ extern "C" size_t pl_linear_workspace_bytes(const pl_linear_args* a) {
   if (!a) return 0;
   if (a->precision == PL_PREC_BF16) return pl::linear_tc_workspace_bytes(a);
   return pl::linear_simt_workspace_bytes(a);
+}
+
+extern "C" size_t pl_linear_state_bytes(const pl_linear_args* a) {
+  if (!a || a->precision != PL_PREC_BF16) return 0;
+  return pl::linear_tc_state_bytes(a);
 }
 
 extern "C" int pl_linear_fwd(const pl_linear_args* a) {

@@ -93,6 +93,70 @@ __global__ void __launch_bounds__(256) sample_bias_kernel(const float* __restric
   }
 }
 
+// dY fp32 -> bf16 (operand of the dX / dW MMAs) fused with the per-sample column sums the bias
+// gradients need: colsum[mc][o] = sum_b dY[mc][b][o].  One pass over dY instead of two.
+// grid (ceil(O/128), MC), 256 threads = 16 row lanes x 16 column groups of 8.
+__global__ void __launch_bounds__(256) cast_dy_colsum_kernel(const float* __restrict__ dy,
+                                                             __nv_bfloat16* __restrict__ dst,
+                                                             float* __restrict__ colsum, int batch,
+                                                             int out) {
+  __shared__ float red[16][129];
+  const int mc = blockIdx.y, cg = threadIdx.x & 15, ry = threadIdx.x >> 4;
+  const int col = blockIdx.x * 128 + cg * 8;
+  const bool ok = col < out;  // out % 8 == 0
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int64_t base = (int64_t)mc * batch * out;
+  if (ok) {
+    for (int b = ry; b < batch; b += 16) {
+      const int64_t idx = base + (int64_t)b * out + col;
+      const float4 v0 = *reinterpret_cast<const float4*>(dy + idx);
+      const float4 v1 = *reinterpret_cast<const float4*>(dy + idx + 4);
+      *reinterpret_cast<uint4*>(dst + idx) =
+          make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y),
+                     pack_bf16x2(v1.z, v1.w));
+      s[0] += v0.x; s[1] += v0.y; s[2] += v0.z; s[3] += v0.w;
+      s[4] += v1.x; s[5] += v1.y; s[6] += v1.z; s[7] += v1.w;
+    }
+  }
+  if (colsum == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ry][cg * 8 + j] = s[j];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t += red[r][threadIdx.x];
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c < out) colsum[(int64_t)mc * out + c] = t;
+  }
+}
+
+// db_mu[o] = sum_mc colsum ; db_rho[o] = sigmoid(b_rho) sum_mc colsum * eps_b   (deterministic order)
+__global__ void __launch_bounds__(128) bias_grad_tc_kernel(const float* __restrict__ colsum,
+                                                           const float* __restrict__ b_rho,
+                                                           const float* __restrict__ eps_b, Sampler sb,
+                                                           int mc, int out, float* __restrict__ db_mu,
+                                                           float* __restrict__ db_rho) {
+  const int o = blockIdx.x * 128 + threadIdx.x;
+  if (o >= out) return;
+  float am = 0.f, ar = 0.f;
+  for (int m = 0; m < mc; ++m) {
+    const float s = colsum[(int64_t)m * out + o];
+    float e;
+    if (eps_b) {
+      e = eps_b[(int64_t)m * out + o];
+    } else {
+      const float4 n = eps4(sb, m, 0, o >> 2);
+      const float v[4] = {n.x, n.y, n.z, n.w};
+      e = v[o & 3];
+    }
+    am += s;
+    ar = fmaf(s, e, ar);
+  }
+  db_mu[o] = am;
+  db_rho[o] = ar * sigmoid_f(b_rho[o]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // fused sample + GEMM (forward: kDx = false, B operand MN-major; dX: kDx = true, B operand K-major)
 // ---------------------------------------------------------------------------------------------
@@ -550,33 +614,60 @@ static int make_tmap_bf16_3d(CUtensorMap* m, const void* base, uint64_t mc, uint
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-struct TcWorkspace {
-  float* sigma;            // [I*O]
-  __nv_bfloat16* a_bf16;   // x (forward) / dy (backward) as bf16
-  float* bias;             // [mc*O]
-  __nv_bfloat16* x_bf16;   // backward: x as bf16 (dW)
+// forward->backward state: sigma [I*O] f32 | x as bf16 [x_rows*I]
+struct TcState {
+  float* sigma;
+  __nv_bfloat16* x_bf16;
+  size_t total;
+};
+// per-call scratch: [state, when the caller keeps none] | sampled bias [mc*O] | colsum [mc*O] |
+// dy as bf16 [mc*B*O]
+struct TcScratch {
+  TcState st;
+  float* bias;
+  float* colsum;
+  __nv_bfloat16* dy_bf16;
   size_t total;
 };
 
-static TcWorkspace carve(const pl_linear_args* a, void* base) {
+static TcState carve_state(const pl_linear_args* a, void* base) {
   const size_t I = a->in_features, O = a->out_features, MC = a->mc, B = a->batch;
   const size_t x_rows = a->x_mc_stride == 0 ? B : MC * B;
-  TcWorkspace w;
+  uint8_t* b = (uint8_t*)(((uintptr_t)base + 255) & ~(uintptr_t)255);
+  TcState s;
   size_t off = 0;
-  uint8_t* b = (uint8_t*)base;
-  w.sigma = (float*)(b + off); off += align256(I * O * 4);
+  s.sigma = (float*)(b + off); off += align256(I * O * 4);
+  s.x_bf16 = (__nv_bfloat16*)(b + off); off += align256(x_rows * I * 2);
+  s.total = off + 256;
+  return s;
+}
+
+static TcScratch carve_scratch(const pl_linear_args* a, void* base, bool with_state, bool backward) {
+  const size_t O = a->out_features, MC = a->mc, B = a->batch;
+  uint8_t* b = (uint8_t*)(((uintptr_t)base + 255) & ~(uintptr_t)255);
+  TcScratch w;
+  size_t off = 0;
+  if (with_state) {
+    w.st = carve_state(a, b);
+    off += w.st.total;
+  } else {
+    w.st = TcState{nullptr, nullptr, 0};
+  }
   w.bias = (float*)(b + off); off += align256(MC * O * 4);
-  // forward: x bf16; backward: dy bf16 (+ x bf16 for dW)
-  const size_t big = MC * B * (I > O ? I : O) * 2;
-  w.a_bf16 = (__nv_bfloat16*)(b + off); off += align256(big);
-  w.x_bf16 = (__nv_bfloat16*)(b + off); off += align256(x_rows * I * 2);
-  w.total = off;
+  w.colsum = (float*)(b + off); off += align256(MC * O * 4);
+  w.dy_bf16 = (__nv_bfloat16*)(b + off);
+  if (backward) off += align256(MC * B * O * 2);
+  w.total = off + 256;
   return w;
 }
 
+size_t linear_tc_state_bytes(const pl_linear_args* a) { return carve_state(a, nullptr).total; }
+
 size_t linear_tc_workspace_bytes(const pl_linear_args* a) {
   if (!a) return 0;
-  return carve(a, nullptr).total + 256;
+  const bool backward = a->dy != nullptr;
+  const bool need_state = a->fwd_state == nullptr;
+  return carve_scratch(a, nullptr, need_state, backward).total;
 }
 
 static int tc_shape_ok(const pl_linear_args* a, const char* who) {
@@ -623,6 +714,18 @@ static int launch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_
 
 int linear_bwd_simt_launch(const pl_linear_args* a);
 
+static int check_buffers(const pl_linear_args* a, const char* who) {
+  if (!a->workspace || a->workspace_bytes < linear_tc_workspace_bytes(a)) {
+    set_error("%s: workspace %zu < %zu bytes", who, a->workspace_bytes, linear_tc_workspace_bytes(a));
+    return PL_ERR_WORKSPACE;
+  }
+  if (a->fwd_state && a->fwd_state_bytes < linear_tc_state_bytes(a)) {
+    set_error("%s: fwd_state %zu < %zu bytes", who, a->fwd_state_bytes, linear_tc_state_bytes(a));
+    return PL_ERR_WORKSPACE;
+  }
+  return PL_OK;
+}
+
 int linear_fwd_tc_launch(const pl_linear_args* a) {
   PL_CHECK_ARG(a, "pl_linear_fwd: NULL args");
   if (a->mc == 0 || a->batch == 0) return PL_OK;
@@ -631,17 +734,18 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   int rc = tc_shape_ok(a, "pl_linear_fwd");
   if (rc != PL_OK) return rc;
   PL_CHECK_ARG(a->mc <= 65535, "pl_linear_fwd: mc too large");
-  if (!a->workspace || a->workspace_bytes < linear_tc_workspace_bytes(a)) {
-    set_error("pl_linear_fwd: workspace %zu < %zu bytes", a->workspace_bytes, linear_tc_workspace_bytes(a));
-    return PL_ERR_WORKSPACE;
-  }
+  pl_linear_args fa = *a;
+  fa.dy = nullptr;  // sizing: forward scratch
+  rc = check_buffers(&fa, "pl_linear_fwd");
+  if (rc != PL_OK) return rc;
   cudaStream_t st = (cudaStream_t)a->stream;
-  TcWorkspace w = carve(a, (void*)(((uintptr_t)a->workspace + 255) & ~(uintptr_t)255));
+  TcScratch w = carve_scratch(&fa, a->workspace, a->fwd_state == nullptr, false);
+  const TcState state = a->fwd_state ? carve_state(a, a->fwd_state) : w.st;
   const int64_t I = a->in_features, O = a->out_features, MC = a->mc, B = a->batch;
   const int64_t x_rows = a->x_mc_stride == 0 ? B : MC * B;
-  softplus_kernel<<<ew_grid(I * O, 1024), 256, 0, st>>>(a->w_rho, w.sigma, I * O);
+  softplus_kernel<<<ew_grid(I * O, 1024), 256, 0, st>>>(a->w_rho, state.sigma, I * O);
   PL_LAUNCH_CHECK("softplus_kernel");
-  cast_bf16_kernel<<<ew_grid(x_rows * I / 8, 1024), 256, 0, st>>>(a->x, w.a_bf16, x_rows * I / 8);
+  cast_bf16_kernel<<<ew_grid(x_rows * I / 8, 1024), 256, 0, st>>>(a->x, state.x_bf16, x_rows * I / 8);
   PL_LAUNCH_CHECK("cast_bf16_kernel");
   if (a->b_mu) {
     sample_bias_kernel<<<ew_grid(MC * ((O + 3) / 4), 256), 256, 0, st>>>(
@@ -650,13 +754,13 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
     PL_LAUNCH_CHECK("sample_bias_kernel");
   }
   CUtensorMap tm;
-  rc = make_tmap_bf16(&tm, w.a_bf16, (uint64_t)x_rows, (uint64_t)I, 128, kBK);
+  rc = make_tmap_bf16(&tm, state.x_bf16, (uint64_t)x_rows, (uint64_t)I, 128, kBK);
   if (rc != PL_OK) return rc;
   TcGemmParams p;
   p.mc = (int)MC; p.rows = (int)B; p.ndim = (int)O; p.kdim = (int)I;
   p.w_in = (int)I; p.w_out = (int)O;
   p.a_mc_rows = a->x_mc_stride == 0 ? 0 : B;
-  p.w_mu = a->w_mu; p.w_sigma = w.sigma; p.eps_w = a->eps_w;
+  p.w_mu = a->w_mu; p.w_sigma = state.sigma; p.eps_w = a->eps_w;
   p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
   p.bias = a->b_mu ? w.bias : nullptr;
   p.out = a->y;
@@ -666,29 +770,51 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
 int linear_bwd_tc_launch(const pl_linear_args* a) {
   PL_CHECK_ARG(a, "pl_linear_bwd: NULL args");
   if (a->mc == 0 || a->batch == 0) return linear_bwd_simt_launch(a);
-  PL_CHECK_ARG(a->x && a->w_mu && a->w_rho && a->dy, "pl_linear_bwd: NULL pointer");
+  const bool have_state = a->fwd_state != nullptr;
+  PL_CHECK_ARG((a->x || have_state) && a->w_mu && a->w_rho && a->dy, "pl_linear_bwd: NULL pointer");
+  PL_CHECK_ARG((a->db_mu == nullptr) == (a->db_rho == nullptr), "pl_linear_bwd: db_mu/db_rho must both be set or NULL");
+  PL_CHECK_ARG(!a->db_mu || a->b_rho, "pl_linear_bwd: bias gradients requested without a bias");
   int rc = tc_shape_ok(a, "pl_linear_bwd");
   if (rc != PL_OK) return rc;
-  if (!a->workspace || a->workspace_bytes < linear_tc_workspace_bytes(a)) {
-    set_error("pl_linear_bwd: workspace %zu < %zu bytes", a->workspace_bytes, linear_tc_workspace_bytes(a));
-    return PL_ERR_WORKSPACE;
-  }
+  rc = check_buffers(a, "pl_linear_bwd");
+  if (rc != PL_OK) return rc;
   cudaStream_t st = (cudaStream_t)a->stream;
-  TcWorkspace w = carve(a, (void*)(((uintptr_t)a->workspace + 255) & ~(uintptr_t)255));
+  TcScratch w = carve_scratch(a, a->workspace, !have_state, true);
+  const TcState state = have_state ? carve_state(a, a->fwd_state) : w.st;
   const int64_t I = a->in_features, O = a->out_features, MC = a->mc, B = a->batch;
+  const int64_t x_rows = a->x_mc_stride == 0 ? B : MC * B;
+  if (!have_state) {
+    if (a->dx) {
+      softplus_kernel<<<ew_grid(I * O, 1024), 256, 0, st>>>(a->w_rho, state.sigma, I * O);
+      PL_LAUNCH_CHECK("softplus_kernel");
+    }
+    if (a->dw_mu) {
+      cast_bf16_kernel<<<ew_grid(x_rows * I / 8, 1024), 256, 0, st>>>(a->x, state.x_bf16, x_rows * I / 8);
+      PL_LAUNCH_CHECK("cast_bf16_kernel");
+    }
+  }
+  if (a->dx || a->dw_mu || a->db_mu) {
+    // one pass over dY: bf16 operand copy + per-sample column sums for the bias gradients
+    dim3 grid((unsigned)((O + 127) / 128), (unsigned)MC);
+    cast_dy_colsum_kernel<<<grid, 256, 0, st>>>(a->dy, w.dy_bf16, a->db_mu ? w.colsum : nullptr,
+                                                (int)B, (int)O);
+    PL_LAUNCH_CHECK("cast_dy_colsum_kernel");
+  }
+  if (a->db_mu) {
+    bias_grad_tc_kernel<<<(unsigned)((O + 127) / 128), 128, 0, st>>>(
+        w.colsum, a->b_rho, a->eps_b, make_sampler(a->seed, a->layer_id, true, a->mc_global_offset),
+        (int)MC, (int)O, a->db_mu, a->db_rho);
+    PL_LAUNCH_CHECK("bias_grad_tc_kernel");
+  }
   if (a->dx) {
-    softplus_kernel<<<ew_grid(I * O, 1024), 256, 0, st>>>(a->w_rho, w.sigma, I * O);
-    PL_LAUNCH_CHECK("softplus_kernel");
-    cast_bf16_kernel<<<ew_grid(MC * B * O / 8, 1024), 256, 0, st>>>(a->dy, w.a_bf16, MC * B * O / 8);
-    PL_LAUNCH_CHECK("cast_bf16_kernel");
     CUtensorMap tm;
-    rc = make_tmap_bf16(&tm, w.a_bf16, (uint64_t)(MC * B), (uint64_t)O, 128, kBK);
+    rc = make_tmap_bf16(&tm, w.dy_bf16, (uint64_t)(MC * B), (uint64_t)O, 128, kBK);
     if (rc != PL_OK) return rc;
     TcGemmParams p;
     p.mc = (int)MC; p.rows = (int)B; p.ndim = (int)I; p.kdim = (int)O;
     p.w_in = (int)I; p.w_out = (int)O;
     p.a_mc_rows = B;
-    p.w_mu = a->w_mu; p.w_sigma = w.sigma; p.eps_w = a->eps_w;
+    p.w_mu = a->w_mu; p.w_sigma = state.sigma; p.eps_w = a->eps_w;
     p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
     p.bias = nullptr;
     p.out = a->dx;
@@ -697,18 +823,11 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
   }
   if (a->dw_mu) {
     PL_CHECK_ARG(a->dw_rho, "pl_linear_bwd: dw_mu/dw_rho must both be set or NULL");
-    if (!a->dx) {
-      cast_bf16_kernel<<<ew_grid(MC * B * O / 8, 1024), 256, 0, st>>>(a->dy, w.a_bf16, MC * B * O / 8);
-      PL_LAUNCH_CHECK("cast_bf16_kernel");
-    }
-    const int64_t x_rows = a->x_mc_stride == 0 ? B : MC * B;
-    cast_bf16_kernel<<<ew_grid(x_rows * I / 8, 1024), 256, 0, st>>>(a->x, w.x_bf16, x_rows * I / 8);
-    PL_LAUNCH_CHECK("cast_bf16_kernel");
     CUtensorMap tmx, tmdy;
-    rc = make_tmap_bf16_3d(&tmx, w.x_bf16, a->x_mc_stride == 0 ? 1 : (uint64_t)MC, (uint64_t)B,
+    rc = make_tmap_bf16_3d(&tmx, state.x_bf16, a->x_mc_stride == 0 ? 1 : (uint64_t)MC, (uint64_t)B,
                            (uint64_t)I, kBK, 64);
     if (rc != PL_OK) return rc;
-    rc = make_tmap_bf16_3d(&tmdy, w.a_bf16, (uint64_t)MC, (uint64_t)B, (uint64_t)O, kBK, 64);
+    rc = make_tmap_bf16_3d(&tmdy, w.dy_bf16, (uint64_t)MC, (uint64_t)B, (uint64_t)O, kBK, 64);
     if (rc != PL_OK) return rc;
     TcDwParams p;
     p.mc = (int)MC; p.batch = (int)B; p.w_in = (int)I; p.w_out = (int)O;
@@ -739,15 +858,6 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
       dw_tc<false><<<grid, kTcThreads, kDwSmemBytes, st>>>(tmx, tmdy, p);
     }
     PL_LAUNCH_CHECK("dw_tc");
-  }
-  if (a->db_mu) {
-    // bias gradients: HBM-bound column sums of dY (fp32 kernels)
-    pl_linear_args b = *a;
-    b.dx = nullptr;
-    b.dw_mu = b.dw_rho = nullptr;
-    b.precision = PL_PREC_FP32;
-    rc = linear_bwd_simt_launch(&b);
-    if (rc != PL_OK) return rc;
   }
   return PL_OK;
 }

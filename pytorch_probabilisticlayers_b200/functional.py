@@ -110,19 +110,26 @@ class _BayesLinearFn(torch.autograd.Function):
         a.seed, a.layer_id, a.mc_global_offset = spec.seed, spec.layer_id, spec.mc_global_offset
         a.eps_w, a.eps_b = _cabi.ptr(eps_w_c), _cabi.ptr(eps_b_c)
         a.y = _cabi.ptr(y)
+        # tensor-core path: sigma and the bf16 copy of x are kept for the backward instead of fp32 x
+        state = None
+        nstate = lib.pl_linear_state_bytes(C.byref(a))
+        if nstate and any(ctx.needs_input_grad[:5]):
+            state = torch.empty(int(nstate), dtype=torch.uint8, device=x.device)
+            a.fwd_state, a.fwd_state_bytes = _cabi.ptr(state), state.numel()
         ws = _workspace(lib.pl_linear_workspace_bytes(C.byref(a)), x.device)
         a.workspace, a.workspace_bytes = _cabi.ptr(ws), ws.numel()
         a.stream = _cabi.current_stream(x.device)
         with torch.cuda.device(x.device):
             _timed(f"linear_fwd[{mc}x{batch}x{fin}x{fout}]",
                    lambda: _cabi.check(lib.pl_linear_fwd(C.byref(a)), "pl_linear_fwd"))
-        ctx.save_for_backward(xb, w_mu_c, w_rho_c, b_mu_c, b_rho_c, eps_w_c, eps_b_c)
+        ctx.save_for_backward(None if state is not None else xb, w_mu_c, w_rho_c, b_mu_c, b_rho_c,
+                              eps_w_c, eps_b_c, state)
         ctx.meta = (spec, param_mode, x_stride, mc, batch, fin, fout, tuple(x.shape))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        xb, w_mu, w_rho, b_mu, b_rho, eps_w, eps_b = ctx.saved_tensors
+        xb, w_mu, w_rho, b_mu, b_rho, eps_w, eps_b, state = ctx.saved_tensors
         spec, param_mode, x_stride, mc, batch, fin, fout, x_shape = ctx.meta
         lib = _cabi.lib()
         dy = dy.contiguous()
@@ -149,6 +156,8 @@ class _BayesLinearFn(torch.autograd.Function):
         a.dy, a.dx = _cabi.ptr(dy), _cabi.ptr(dx)
         a.dw_mu, a.dw_rho = _cabi.ptr(dw_mu), _cabi.ptr(dw_rho)
         a.db_mu, a.db_rho = _cabi.ptr(db_mu), _cabi.ptr(db_rho)
+        if state is not None:
+            a.fwd_state, a.fwd_state_bytes = _cabi.ptr(state), state.numel()
         ws = _workspace(lib.pl_linear_workspace_bytes(C.byref(a)), dev)
         a.workspace, a.workspace_bytes = _cabi.ptr(ws), ws.numel()
         a.stream = _cabi.current_stream(dev)
