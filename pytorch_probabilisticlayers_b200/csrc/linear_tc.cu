@@ -23,6 +23,8 @@
 // sampler's ALU/MUFU budget: every generated element feeds only 2*B flops.
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -203,7 +205,7 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < Cfg::kStagesB; ++s) {
-      mbar_init(b_full(s), kGenWarps * 32);
+      mbar_init(b_full(s), kGenWarps);   // one elected arrival per generator warp
       mbar_init(b_empty(s), 1);
     }
     mbar_init(acc_full, 1);
@@ -321,7 +323,8 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + soff[r]), "r"(lo), "r"(hi) : "memory");
       }
       fence_proxy_async_smem();
-      mbar_arrive(b_full(s));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_full(s));
     };
     // tiles fully inside the weight matrix take the predicate-free path
     const bool n_full = kDx ? (n0 + kBN <= p.w_in) : (n0 + kBN <= p.w_out);
@@ -362,6 +365,218 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// 2-CTA version of sampled_gemm_tc (cta_group::2): a CTA pair on one TPC owns a
+// [MT2 x 256 batch rows] x [256 output columns] tile.  Each CTA stages its own 128 rows of every
+// 256-row activation sub-tile (TMA) and synthesises its own 128 of the 256 weight columns; the
+// leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256) which reads both
+// CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.  Per SM this halves the
+// shared-memory operand traffic of the 1-CTA kernel (8 KB per 128 MMA cycles instead of 8 KB per 64)
+// and the activation bytes per k-block, at the same generated-elements-per-flop ratio.
+//   full barriers live in the leader CTA (peer producers arrive remotely, TMA bytes of both CTAs
+//   are credited to it); empty / accumulator barriers are multicast to both CTAs by tcgen05.commit.
+// ---------------------------------------------------------------------------------------------
+template <int MT2>
+struct Tc2Cfg {
+  static constexpr int kStagesA = 4;
+  static constexpr int kStagesB = 4;
+  static constexpr int kABytes = MT2 * kSubTileBytes;          // this CTA's rows of one k-block
+  static constexpr int kSmemBytes = kStagesA * kABytes + kStagesB * kSubTileBytes + 2048 + 1024;
+  static constexpr int kTmemCols = MT2 * 256;                   // 256 or 512
+};
+
+template <int MT2, bool kDx, bool kInjected>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+sampled_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p) {
+  using Cfg = Tc2Cfg<MT2>;
+  constexpr int kTileN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + Cfg::kStagesA * Cfg::kABytes;
+  const uint32_t sMisc = sB + Cfg::kStagesB * kSubTileBytes;
+  float* bias_s = reinterpret_cast<float*>(smem + (sMisc - smem_base));  // 256 floats
+  const uint32_t bar0 = sMisc + 1024;
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (Cfg::kStagesA + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * Cfg::kStagesA + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (2 * Cfg::kStagesA + Cfg::kStagesB + s); };
+  const uint32_t acc_full = bar0 + 8u * (2 * Cfg::kStagesA + 2 * Cfg::kStagesB);
+  const uint32_t tmem_slot = acc_full + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();        // 0 = leader
+  const int n0 = (blockIdx.x >> 1) * kTileN;      // pair tile: 256 output columns
+  const int nb0 = n0 + (int)rank * 128;           // the 128 columns this CTA synthesises
+  const int m0 = blockIdx.y * (MT2 * 256);
+  const int mc = blockIdx.z;
+  const int num_kb = (p.kdim + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStagesA; ++s) {
+      mbar_init(a_full(s), 2);                    // leader producer (+tx) and peer producer
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < Cfg::kStagesB; ++s) {
+      mbar_init(b_full(s), 2 * kGenWarps);        // one elected arrival per generator warp, both CTAs
+      mbar_init(b_empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_a);
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    if (t < kTileN) bias_s[t] = (p.bias && n0 + t < p.ndim) ? p.bias[(int64_t)mc * p.ndim + n0 + t] : 0.f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs, own rows) =====================
+    if (lane == 0) {
+      const int row0 = (int)(mc * p.a_mc_rows) + m0 + (int)rank * 128;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::kStagesA, ph = (kb / Cfg::kStagesA) & 1;
+        mbar_wait(a_empty(s), ph ^ 1);
+        if (rank == 0) mbar_expect_tx(a_full(s), 2 * Cfg::kABytes);
+        else mbar_arrive_cluster(a_full(s), 0);
+#pragma unroll
+        for (int t = 0; t < MT2; ++t)
+          tma_load_2d_2cta(sA + s * Cfg::kABytes + t * kSubTileBytes, &tmap_a, a_full(s), kb * kBK,
+                           row0 + t * 256);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(256, kTileN, 0, kDx ? 0 : 1);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int sa = kb % Cfg::kStagesA, pa = (kb / Cfg::kStagesA) & 1;
+        const int sb = kb % Cfg::kStagesB, pb = (kb / Cfg::kStagesB) & 1;
+        mbar_wait_cluster(a_full(sa), pa);
+        mbar_wait_cluster(b_full(sb), pb);
+        tc_fence_after_sync();
+        const uint32_t a_addr = sA + sa * Cfg::kABytes;
+        const uint32_t b_addr = sB + sb * kSubTileBytes;
+#pragma unroll
+        for (int ks = 0; ks < kBK / 16; ++ks) {
+          const uint64_t b_desc = kDx ? smem_desc_sw128(b_addr + ks * 32, 16, 1024)
+                                      : smem_desc_sw128(b_addr + ks * 2048, 8192, 1024);
+#pragma unroll
+          for (int t = 0; t < MT2; ++t) {
+            const uint64_t a_desc = smem_desc_sw128(a_addr + t * kSubTileBytes + ks * 32, 16, 1024);
+            mma_bf16_ss_2cta(tmem_base + t * kTileN, a_desc, b_desc, idesc, (kb | ks) != 0);
+          }
+        }
+        mma_commit_2cta(a_empty(sa));
+        mma_commit_2cta(b_empty(sb));
+      }
+      mma_commit_2cta(acc_full);
+    }
+    __syncwarp();
+  } else {
+    // ===================== W-tile generators (both CTAs, own 128 columns) =====================
+    const int gw = warp - 2;  // 0..15
+    int wrow[4], wcol;
+    uint32_t soff[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (!kDx) {
+        wrow[r] = gw + 16 * r;
+        soff[r] = (uint32_t)((lane >> 4) * 8192 + ((gw >> 3) + 2 * r) * 1024 + (gw & 7) * 128 +
+                             ((((lane & 15) >> 1) ^ (gw & 7)) << 4) + ((lane & 1) << 3));
+      } else {
+        const int n = 8 * gw + 2 * r + (lane >> 4);
+        wrow[r] = nb0 + n;
+        soff[r] = (uint32_t)(n * 128 + ((((lane & 15) >> 1) ^ (n & 7)) << 4) + ((lane & 1) << 3));
+      }
+    }
+    wcol = kDx ? 4 * (lane & 15) : nb0 + 4 * lane;
+    const int64_t ldw = p.w_out;
+    const float* eps_base = kInjected ? p.eps_w + (int64_t)mc * p.w_in * p.w_out : nullptr;
+
+    auto gen_block = [&](int kb, auto full_tag) {
+      constexpr bool kFull = decltype(full_tag)::value;
+      const int s = kb % Cfg::kStagesB, ph = (kb / Cfg::kStagesB) & 1;
+      const int k0 = kb * kBK;
+      float4 mu[4], sg[4], ep[4];
+      int row[4];
+      const int col = kDx ? k0 + wcol : wcol;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        row[r] = kDx ? wrow[r] : k0 + wrow[r];
+        const bool ok = kFull || (row[r] < p.w_in && col < p.w_out);
+        const int64_t idx = (int64_t)row[r] * ldw + col;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        mu[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_mu + idx)) : z;
+        sg[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_sigma + idx)) : z;
+        if (kInjected) ep[r] = ok ? __ldg(reinterpret_cast<const float4*>(eps_base + idx)) : z;
+      }
+      mbar_wait(b_empty(s), ph ^ 1);
+      const uint32_t dst = sB + s * kSubTileBytes;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float4 e;
+        if (kInjected) e = ep[r];
+        else e = eps4(p.sw, mc, row[r], col >> 2);
+        const uint32_t lo = pack_bf16x2(fmaf(sg[r].x, e.x, mu[r].x), fmaf(sg[r].y, e.y, mu[r].y));
+        const uint32_t hi = pack_bf16x2(fmaf(sg[r].z, e.z, mu[r].z), fmaf(sg[r].w, e.w, mu[r].w));
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + soff[r]), "r"(lo), "r"(hi) : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(b_full(s), 0);   // signal the leader's barrier
+    };
+    const bool n_full = kDx ? (nb0 + 128 <= p.w_in) : (nb0 + 128 <= p.w_out);
+    const int k_extent = kDx ? p.w_out : p.w_in;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      if (n_full && (kb + 1) * kBK <= k_extent) gen_block(kb, std::true_type{});
+      else gen_block(kb, std::false_type{});
+    }
+    // ===================== epilogue: this CTA's 128 rows of every sub-tile, all 256 columns ==========
+    mbar_wait(acc_full, 0);
+    tc_fence_after_sync();
+    const int q = warp & 3;
+#pragma unroll 1
+    for (int t = 0; t < MT2; ++t) {
+      const int row = m0 + t * 256 + (int)rank * 128 + q * 32 + lane;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col = (gw >> 2) * 64 + cc * 32;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * kTileN + col), v);
+        tmem_ld_wait();
+        if (row < p.rows) {
+          float* o = p.out + ((int64_t)mc * p.rows + row) * p.ndim + n0 + col;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n0 + col + j < p.ndim) {
+              float4 w;
+              w.x = __uint_as_float(v[j + 0]) + bias_s[col + j + 0];
+              w.y = __uint_as_float(v[j + 1]) + bias_s[col + j + 1];
+              w.z = __uint_as_float(v[j + 2]) + bias_s[col + j + 2];
+              w.w = __uint_as_float(v[j + 3]) + bias_s[col + j + 3];
+              *reinterpret_cast<float4*>(o + j) = w;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();     // the peer's smem / TMEM must outlive the leader's MMAs
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+}
 
 // ---------------------------------------------------------------------------------------------
 // fused weight-gradient kernel: one CTA owns a [128 in-rows x 128 out-cols] tile of the weight and
@@ -417,7 +632,7 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), kGenWarps * 32);
+      mbar_init(acc_empty(b), kGenWarps);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmap_x);
@@ -516,7 +731,8 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
         }
       }
       tc_fence_before_sync();
-      mbar_arrive(acc_empty(buf));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
     }
     if (row < p.w_in) {
 #pragma unroll
@@ -692,8 +908,34 @@ static inline int ew_grid(int64_t n, int per_block) {
   return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
 }
 
+// PL_TC_2CTA=1 selects the cta_group::2 kernels.  Measured on C4 (r01): 2.22 ms vs 1.78 ms per
+// 4096^2 forward for the 1-CTA kernel -- the kernels are bound by the sampler's issue rate, not by
+// shared-memory operand traffic, and pairing two SMs per stage hand-off costs more than it saves.
+// Kept (parity-tested) for when the sampler gets cheaper.
+static int g_force_1cta = -1;
+
 template <bool kDx, bool kInj>
 static int launch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_t st) {
+  if (g_force_1cta < 0) {
+    const char* e = getenv("PL_TC_2CTA");
+    g_force_1cta = (e && e[0] == '1') ? 0 : 1;
+  }
+  if (!g_force_1cta && p.rows > 128 && p.ndim > 128) {
+    const int pair_rows = p.rows > 256 ? 512 : 256;
+    dim3 grid(2u * (unsigned)((p.ndim + 255) / 256), (unsigned)((p.rows + pair_rows - 1) / pair_rows),
+              (unsigned)p.mc);
+    if (pair_rows == 512) {
+      auto kern = sampled_gemm_tc2<2, kDx, kInj>;
+      PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<2>::kSmemBytes));
+      kern<<<grid, kTcThreads, Tc2Cfg<2>::kSmemBytes, st>>>(tm, p);
+    } else {
+      auto kern = sampled_gemm_tc2<1, kDx, kInj>;
+      PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<1>::kSmemBytes));
+      kern<<<grid, kTcThreads, Tc2Cfg<1>::kSmemBytes, st>>>(tm, p);
+    }
+    PL_LAUNCH_CHECK("sampled_gemm_tc2");
+    return PL_OK;
+  }
   const int mt_rows = p.rows > 256 ? 512 : (p.rows > 128 ? 256 : 128);
   dim3 grid((unsigned)((p.ndim + kBN - 1) / kBN), (unsigned)((p.rows + mt_rows - 1) / mt_rows),
             (unsigned)p.mc);
