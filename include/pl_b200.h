@@ -138,7 +138,9 @@ int pl_linear_bwd(const pl_linear_args* a);
 /* ---- BayesConv2d (replaces rsample + F.conv2d(groups=MC) at
  *      src/ProbabilisticLayers.py:1032-1057 and its autograd).  Square kernel, scalar
  *      stride/padding/dilation like the reference (:991).  x [mc,B,Cin,H,W] contiguous,
- *      y [mc,B,Cout,H',W'] contiguous. ------------------------------------------------------- */
+ *      y [mc,B,Cout,H',W'] contiguous.  PL_PREC_FP32: fp32 implicit GEMM; PL_PREC_BF16: tcgen05
+ *      GEMMs over a bf16 im2col matrix (workspace: pl_conv2d_workspace_bytes, sized for the call's
+ *      dy / dx pointers). ---------------------------------------------------------------------- */
 typedef struct pl_conv2d_args {
   int32_t mc, batch, cin, cout, h, w, k, stride, padding, dilation;
   int32_t precision;
@@ -165,6 +167,7 @@ typedef struct pl_conv2d_args {
   void* stream;
 } pl_conv2d_args;
 
+size_t pl_conv2d_workspace_bytes(const pl_conv2d_args* a);
 int pl_conv2d_fwd(const pl_conv2d_args* a);
 int pl_conv2d_bwd(const pl_conv2d_args* a);
 

@@ -24,7 +24,7 @@ EXPORTS = (
     "pl_version", "pl_last_error", "pl_launch_count", "pl_device_supported", "pl_eps_dump",
     "pl_kl_workspace_bytes", "pl_kl_fwd", "pl_kl_bwd",
     "pl_linear_workspace_bytes", "pl_linear_state_bytes", "pl_linear_fwd", "pl_linear_bwd",
-    "pl_conv2d_fwd", "pl_conv2d_bwd",
+    "pl_conv2d_workspace_bytes", "pl_conv2d_fwd", "pl_conv2d_bwd",
 )
 
 
@@ -96,6 +96,8 @@ def lib():
                 for name in ("pl_linear_fwd", "pl_linear_bwd"):
                     getattr(l, name).restype = C.c_int
                     getattr(l, name).argtypes = [C.POINTER(LinearArgs)]
+                l.pl_conv2d_workspace_bytes.restype = C.c_size_t
+                l.pl_conv2d_workspace_bytes.argtypes = [C.POINTER(Conv2dArgs)]
                 for name in ("pl_conv2d_fwd", "pl_conv2d_bwd"):
                     getattr(l, name).restype = C.c_int
                     getattr(l, name).argtypes = [C.POINTER(Conv2dArgs)]

@@ -325,16 +325,32 @@ static int fill_conv(const pl_conv2d_args* a, ConvParams& p, const char* who) {
   return PL_OK;
 }
 
+size_t conv_tc_workspace_bytes(const pl_conv2d_args* a);
+int conv_fwd_tc_launch(const pl_conv2d_args* a);
+int conv_bwd_tc_launch(const pl_conv2d_args* a);
+
 }  // namespace pl
+
+extern "C" size_t pl_conv2d_workspace_bytes(const pl_conv2d_args* a) {
+  if (!a) return 0;
+  const size_t colsum = sizeof(float) * (size_t)(a->mc > 0 ? a->mc : 0) * (size_t)(a->cout > 0 ? a->cout : 0) + 256;
+  if (a->precision == PL_PREC_BF16) {
+    const size_t tc = pl::conv_tc_workspace_bytes(a);
+    return tc > colsum ? tc : colsum;
+  }
+  return colsum;
+}
 
 extern "C" int pl_conv2d_fwd(const pl_conv2d_args* a) {
   using namespace pl;
+  PL_CHECK_ARG(a, "pl_conv2d_fwd: NULL args");
+  if (a->precision == PL_PREC_BF16) return conv_fwd_tc_launch(a);
   ConvParams p;
   int rc = fill_conv(a, p, "pl_conv2d_fwd");
   if (rc != PL_OK) return rc;
   PL_CHECK_ARG(a->y, "pl_conv2d_fwd: NULL y");
   if (a->precision != PL_PREC_FP32) {
-    set_error("pl_conv2d_fwd: precision %d not available for conv yet (use PL_PREC_FP32)", a->precision);
+    set_error("pl_conv2d_fwd: precision %d not implemented", a->precision);
     return PL_ERR_UNSUPPORTED;
   }
   if (p.mc == 0 || p.batch == 0) return PL_OK;
@@ -348,14 +364,25 @@ extern "C" int pl_conv2d_fwd(const pl_conv2d_args* a) {
 
 extern "C" int pl_conv2d_bwd(const pl_conv2d_args* a) {
   using namespace pl;
+  PL_CHECK_ARG(a, "pl_conv2d_bwd: NULL args");
+  if (a->precision == PL_PREC_BF16 && a->mc > 0 && a->batch > 0) {
+    // tensor-core kernels for dX / dW; the bias gradients are HBM-bound column sums (fp32 kernels)
+    int rc = conv_bwd_tc_launch(a);
+    if (rc != PL_OK || !a->db_mu) return rc;
+    pl_conv2d_args b = *a;
+    b.precision = PL_PREC_FP32;
+    b.dx = nullptr;
+    b.dw_mu = b.dw_rho = nullptr;
+    return pl_conv2d_bwd(&b);
+  }
   ConvParams p;
   int rc = fill_conv(a, p, "pl_conv2d_bwd");
   if (rc != PL_OK) return rc;
   PL_CHECK_ARG(a->dy, "pl_conv2d_bwd: NULL dy");
   PL_CHECK_ARG((a->dw_mu == nullptr) == (a->dw_rho == nullptr), "pl_conv2d_bwd: dw_mu/dw_rho must both be set or NULL");
   PL_CHECK_ARG((a->db_mu == nullptr) == (a->db_rho == nullptr), "pl_conv2d_bwd: db_mu/db_rho must both be set or NULL");
-  if (a->precision != PL_PREC_FP32) {
-    set_error("pl_conv2d_bwd: precision %d not available for conv yet (use PL_PREC_FP32)", a->precision);
+  if (a->precision != PL_PREC_FP32 && a->precision != PL_PREC_BF16) {
+    set_error("pl_conv2d_bwd: precision %d not implemented", a->precision);
     return PL_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)a->stream;

@@ -1,0 +1,298 @@
+// BayesConv2d on the tensor-core kernels (PL_PREC_BF16).
+//
+// Per MC sample the convolution is the GEMM  Y[M = B*H'*W', Cout] = A[M, K = Cin*k*k] . Wc[Cout, K]^T
+// with Wc[mc] = mu + softplus(rho)*eps[mc] synthesised on chip (Philox row = cout, col = cin*k*k +
+// kh*k + kw, the same stream the fp32 kernels and the oracle use).  This round the im2col matrix A is
+// materialised once per call as bf16 (an HBM-bound pre-pass; TMA-im2col = next step) and the three
+// GEMMs reuse the Linear kernels of tc_kernels.cuh with the roles mapped as
+//     forward  Y   = A   . Wc^T      -> sampled_gemm_tc<kDx = true>   (w_in = Cout, w_out = K),
+//                                       epilogue writes NCHW directly (out_hw = H'*W')
+//     dWc      dWc = dYt^T . A       -> dw_tc (x-operand = dY pixel-major, dy-operand = A), reduction
+//                                       over pixels split across CTAs when Cout*K has few tiles
+//     dX       dA  = dYt . Wc        -> sampled_gemm_tc<kDx = false>, written K-major, then col2im
+// Replaces src/ProbabilisticLayers.py:1032-1057 (F.conv2d(groups=MC) + two permute copies) and its
+// autograd; parity: tests/test_gpu_tc.py::test_tc_conv_*.
+#include "tc_kernels.cuh"
+
+namespace pl {
+
+struct ConvGeom {
+  int mc, mcx, batch, cin, cout, h, w, k, stride, pad, dil, ho, wo;
+  int K, Kp, Coutp;  // K = cin*k*k; Kp, Coutp = rounded up to 8 (16-byte bf16 rows for TMA)
+  int64_t M;         // batch*ho*wo output pixels per MC sample
+};
+
+// A[mcx][m][Kp] (bf16) = im2col(x); one thread per 8 consecutive K entries (16-byte store)
+__global__ void __launch_bounds__(256) im2col_bf16_kernel(const float* __restrict__ x,
+                                                          int64_t x_mc_stride,
+                                                          __nv_bfloat16* __restrict__ A, ConvGeom g) {
+  const int chunks = g.Kp >> 3, kk2 = g.k * g.k, hw = g.ho * g.wo;
+  const int64_t total = (int64_t)g.mcx * g.M * chunks;
+  for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+    const int kc = (int)(t % chunks);
+    const int64_t mm = t / chunks;
+    const int m = (int)(mm % g.M), mc = (int)(mm / g.M);
+    const int b = m / hw, pix = m - b * hw, oh = pix / g.wo, ow = pix - oh * g.wo;
+    const int ih0 = oh * g.stride - g.pad, iw0 = ow * g.stride - g.pad;
+    const float* xb = x + (int64_t)mc * x_mc_stride + (int64_t)b * g.cin * g.h * g.w;
+    int kidx = kc << 3;
+    int c = kidx / kk2, r = kidx - c * kk2, kh = r / g.k, kw = r - kh * g.k;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float val = 0.f;
+      if (kidx + j < g.K) {
+        const int ih = ih0 + kh * g.dil, iw = iw0 + kw * g.dil;
+        if (ih >= 0 && ih < g.h && iw >= 0 && iw < g.w) val = __ldg(xb + ((int64_t)c * g.h + ih) * g.w + iw);
+      }
+      v[j] = val;
+      if (++kw == g.k) {
+        kw = 0;
+        if (++kh == g.k) {
+          kh = 0;
+          ++c;
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(A + t * 8) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                      pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// dy [mc*B, Cout, HW] fp32 -> dYt [mc*B*HW, Coutp] bf16 (pixel-major rows = GEMM operand), zero padded
+// grid (ceil(HW/32), ceil(Coutp/32), mc*B), block (32, 8)
+__global__ void __launch_bounds__(256) dy_pixel_major_kernel(const float* __restrict__ dy,
+                                                             __nv_bfloat16* __restrict__ dyt, int cout,
+                                                             int coutp, int hw) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = c0 + ty + 8 * i, pix = p0 + tx;
+    tile[ty + 8 * i][tx] = (co < cout && pix < hw) ? __ldg(dy + ((int64_t)img * cout + co) * hw + pix) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pix = p0 + ty + 8 * i, co = c0 + tx;
+    if (pix < hw && co < coutp)
+      dyt[((int64_t)img * hw + pix) * coutp + co] = __float2bfloat16(tile[tx][ty + 8 * i]);
+  }
+}
+
+// dx[mc][b][c][h][w] = sum_{kh,kw} dA[mc][c*k*k + kh*k + kw][b*HWo + oh*Wo + ow]   (gather, no atomics)
+__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dA, float* __restrict__ dx,
+                                                     ConvGeom g) {
+  const int64_t per_mc = (int64_t)g.batch * g.cin * g.h * g.w, total = (int64_t)g.mc * per_mc;
+  const int kk2 = g.k * g.k, hwo = g.ho * g.wo;
+  for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+    const int iw = (int)(t % g.w);
+    int64_t r = t / g.w;
+    const int ih = (int)(r % g.h);
+    r /= g.h;
+    const int c = (int)(r % g.cin);
+    r /= g.cin;
+    const int b = (int)(r % g.batch), mc = (int)(r / g.batch);
+    const float* base = dA + ((int64_t)mc * g.K + (int64_t)c * kk2) * g.M + (int64_t)b * hwo;
+    float s = 0.f;
+    for (int kh = 0; kh < g.k; ++kh) {
+      const int th = ih + g.pad - kh * g.dil;
+      if (th < 0 || th % g.stride) continue;
+      const int oh = th / g.stride;
+      if (oh >= g.ho) continue;
+      for (int kw = 0; kw < g.k; ++kw) {
+        const int tw = iw + g.pad - kw * g.dil;
+        if (tw < 0 || tw % g.stride) continue;
+        const int ow = tw / g.stride;
+        if (ow >= g.wo) continue;
+        s += __ldg(base + (int64_t)(kh * g.k + kw) * g.M + oh * g.wo + ow);
+      }
+    }
+    dx[t] = s;
+  }
+}
+
+static int conv_geom(const pl_conv2d_args* a, ConvGeom& g, const char* who) {
+  PL_CHECK_ARG(a, "%s: NULL args", who);
+  PL_CHECK_ARG(a->mc >= 0 && a->batch >= 0 && a->cin > 0 && a->cout > 0 && a->h > 0 && a->w > 0,
+               "%s: bad dimension", who);
+  PL_CHECK_ARG(a->k > 0 && a->stride > 0 && a->padding >= 0 && a->dilation > 0,
+               "%s: bad kernel_size/stride/padding/dilation", who);
+  g.mc = a->mc; g.batch = a->batch; g.cin = a->cin; g.cout = a->cout; g.h = a->h; g.w = a->w;
+  g.k = a->k; g.stride = a->stride; g.pad = a->padding; g.dil = a->dilation;
+  g.ho = (a->h + 2 * a->padding - a->dilation * (a->k - 1) - 1) / a->stride + 1;
+  g.wo = (a->w + 2 * a->padding - a->dilation * (a->k - 1) - 1) / a->stride + 1;
+  PL_CHECK_ARG(g.ho > 0 && g.wo > 0, "%s: empty output", who);
+  g.mcx = a->x_mc_stride == 0 ? 1 : a->mc;
+  g.K = a->cin * a->k * a->k;
+  g.Kp = (g.K + 7) & ~7;
+  g.Coutp = (g.cout + 7) & ~7;
+  g.M = (int64_t)a->batch * g.ho * g.wo;
+  PL_CHECK_ARG(g.M < (1ll << 31) && (int64_t)a->batch * a->h * a->w < (1ll << 31),
+               "%s: per-sample pixel count overflows int32", who);
+  PL_CHECK_ARG(a->x_mc_stride == 0 || a->x_mc_stride == (int64_t)a->batch * a->cin * a->h * a->w,
+               "%s: PL_PREC_BF16 needs a dense [mc,B,C,H,W] input (or mc stride 0)", who);
+  return PL_OK;
+}
+
+struct ConvScratch {
+  float* sigma;            // [cout*K]
+  float* bias;             // [mc*cout] sampled bias (fwd) / column sums (bwd)
+  __nv_bfloat16* A;        // [mcx*M*Kp]
+  __nv_bfloat16* dyt;      // [mc*M*Coutp]        (bwd)
+  float* dA;               // [mc*K*M]            (bwd, when dx is wanted)
+  size_t total;
+};
+
+static ConvScratch conv_carve(const ConvGeom& g, void* base, bool backward, bool want_dx) {
+  uint8_t* b = (uint8_t*)(((uintptr_t)base + 255) & ~(uintptr_t)255);
+  ConvScratch w;
+  size_t off = 0;
+  w.sigma = (float*)(b + off); off += align256((size_t)g.cout * g.K * 4);
+  w.bias = (float*)(b + off); off += align256((size_t)g.mc * g.cout * 4);
+  w.A = (__nv_bfloat16*)(b + off); off += align256((size_t)g.mcx * g.M * g.Kp * 2);
+  w.dyt = (__nv_bfloat16*)(b + off);
+  if (backward) off += align256((size_t)g.mc * g.M * g.Coutp * 2);
+  w.dA = (float*)(b + off);
+  if (backward && want_dx) off += align256((size_t)g.mc * g.K * g.M * 4);
+  w.total = off + 256;
+  return w;
+}
+
+size_t conv_tc_workspace_bytes(const pl_conv2d_args* a) {
+  ConvGeom g;
+  if (conv_geom(a, g, "pl_conv2d_workspace_bytes") != PL_OK) return 0;
+  return conv_carve(g, nullptr, a->dy != nullptr, a->dx != nullptr).total;
+}
+
+int conv_fwd_tc_launch(const pl_conv2d_args* a) {
+  ConvGeom g;
+  int rc = conv_geom(a, g, "pl_conv2d_fwd");
+  if (rc != PL_OK) return rc;
+  if (g.mc == 0 || g.batch == 0) return PL_OK;
+  PL_CHECK_ARG(a->x && a->w_mu && a->w_rho && a->b_mu && a->b_rho && a->y, "pl_conv2d_fwd: NULL tensor");
+  PL_CHECK_ARG(g.mc <= 65535, "pl_conv2d_fwd: mc too large");
+  pl_conv2d_args fa = *a;
+  fa.dy = nullptr;
+  fa.dx = nullptr;
+  if (!a->workspace || a->workspace_bytes < conv_tc_workspace_bytes(&fa)) {
+    set_error("pl_conv2d_fwd: workspace %zu < %zu bytes", a->workspace_bytes, conv_tc_workspace_bytes(&fa));
+    return PL_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)a->stream;
+  ConvScratch w = conv_carve(g, a->workspace, false, false);
+  const int64_t nw = (int64_t)g.cout * g.K;
+  softplus_kernel<<<ew_grid(nw, 1024), 256, 0, st>>>(a->w_rho, w.sigma, nw);
+  PL_LAUNCH_CHECK("softplus_kernel");
+  sample_bias_kernel<<<ew_grid((int64_t)g.mc * ((g.cout + 3) / 4), 256), 256, 0, st>>>(
+      a->b_mu, a->b_rho, a->eps_b, make_sampler(a->seed, a->layer_id, true, a->mc_global_offset), g.mc,
+      g.cout, w.bias);
+  PL_LAUNCH_CHECK("sample_bias_kernel");
+  im2col_bf16_kernel<<<ew_grid((int64_t)g.mcx * g.M * (g.Kp / 8), 256), 256, 0, st>>>(a->x, a->x_mc_stride,
+                                                                                       w.A, g);
+  PL_LAUNCH_CHECK("im2col_bf16_kernel");
+  CUtensorMap tm;
+  rc = make_tmap_bf16(&tm, w.A, (uint64_t)g.mcx * g.M, (uint64_t)g.Kp, 128, kBK);
+  if (rc != PL_OK) return rc;
+  TcGemmParams p;
+  p.mc = g.mc; p.rows = (int)g.M; p.ndim = g.cout; p.kdim = g.K;
+  p.w_in = g.cout; p.w_out = g.K;
+  p.a_mc_rows = g.mcx == 1 ? 0 : g.M;
+  p.w_mu = a->w_mu; p.w_sigma = w.sigma; p.eps_w = a->eps_w;
+  p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
+  p.bias = w.bias;
+  p.out = a->y;
+  p.out_hw = g.ho * g.wo;
+  p.w_aligned = (g.K % 4) == 0;
+  return a->eps_w ? launch_gemm<true, true>(tm, p, st) : launch_gemm<true, false>(tm, p, st);
+}
+
+int conv_bwd_tc_launch(const pl_conv2d_args* a) {
+  ConvGeom g;
+  int rc = conv_geom(a, g, "pl_conv2d_bwd");
+  if (rc != PL_OK) return rc;
+  PL_CHECK_ARG(a->x && a->w_mu && a->w_rho && a->b_rho && a->dy, "pl_conv2d_bwd: NULL tensor");
+  PL_CHECK_ARG((a->dw_mu == nullptr) == (a->dw_rho == nullptr), "pl_conv2d_bwd: dw_mu/dw_rho must both be set or NULL");
+  if (!a->workspace || a->workspace_bytes < conv_tc_workspace_bytes(a)) {
+    set_error("pl_conv2d_bwd: workspace %zu < %zu bytes", a->workspace_bytes, conv_tc_workspace_bytes(a));
+    return PL_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)a->stream;
+  ConvScratch w = conv_carve(g, a->workspace, true, a->dx != nullptr);
+  const int hwo = g.ho * g.wo;
+  const int64_t nw = (int64_t)g.cout * g.K;
+  if (a->dx || a->dw_mu) {
+    dim3 grid((unsigned)((hwo + 31) / 32), (unsigned)((g.Coutp + 31) / 32), (unsigned)(g.mc * g.batch));
+    PL_CHECK_ARG((int64_t)g.mc * g.batch <= 65535, "pl_conv2d_bwd: mc*batch too large for the transpose grid");
+    dy_pixel_major_kernel<<<grid, dim3(32, 8), 0, st>>>(a->dy, w.dyt, g.cout, g.Coutp, hwo);
+    PL_LAUNCH_CHECK("dy_pixel_major_kernel");
+  }
+  if (a->dw_mu) {
+    im2col_bf16_kernel<<<ew_grid((int64_t)g.mcx * g.M * (g.Kp / 8), 256), 256, 0, st>>>(
+        a->x, a->x_mc_stride, w.A, g);
+    PL_LAUNCH_CHECK("im2col_bf16_kernel");
+    CUtensorMap tmx, tmdy;
+    rc = make_tmap_bf16_3d(&tmx, w.dyt, (uint64_t)g.mc, (uint64_t)g.M, (uint64_t)g.Coutp, kBK, 64);
+    if (rc != PL_OK) return rc;
+    rc = make_tmap_bf16_3d(&tmdy, w.A, (uint64_t)g.mcx, (uint64_t)g.M, (uint64_t)g.Kp, kBK, 64);
+    if (rc != PL_OK) return rc;
+    TcDwParams p;
+    p.mc = g.mc; p.batch = (int)g.M; p.w_in = g.cout; p.w_out = g.K;
+    p.x_broadcast = 0;
+    p.dy_broadcast = g.mcx == 1;
+    p.w_aligned = (g.K % 4) == 0;
+    p.w_rho = a->w_rho; p.eps_w = a->eps_w;
+    p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
+    p.dw_mu = a->dw_mu; p.dw_rho = a->dw_rho;
+    // few weight tiles, long pixel reduction: one CTA per (tile, MC sample, pixel chunk)
+    const int tiles = ((g.cout + 127) / 128) * ((g.K + 127) / 128);
+    const int num_kb = (int)((g.M + kBK - 1) / kBK);
+    p.mc_per_split = 1;
+    int want = (4 * 148) / (tiles * g.mc);
+    if (want < 1) want = 1;
+    if (want > num_kb) want = num_kb;
+    p.kb_per_split = (num_kb + want - 1) / want;
+    p.kb_splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    p.atomic_out = (g.mc * p.kb_splits) > 1;
+    if (p.atomic_out) {
+      PL_CUDA(cudaMemsetAsync(a->dw_mu, 0, sizeof(float) * nw, st));
+      PL_CUDA(cudaMemsetAsync(a->dw_rho, 0, sizeof(float) * nw, st));
+    }
+    PL_CHECK_ARG((int64_t)g.mc * p.kb_splits <= 65535, "pl_conv2d_bwd: too many reduction splits");
+    dim3 grid((unsigned)((g.K + 127) / 128), (unsigned)((g.cout + 127) / 128), (unsigned)(g.mc * p.kb_splits));
+    if (a->eps_w) {
+      PL_CUDA(cudaFuncSetAttribute(dw_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes));
+      dw_tc<true><<<grid, kTcThreads, kDwSmemBytes, st>>>(tmx, tmdy, p);
+    } else {
+      PL_CUDA(cudaFuncSetAttribute(dw_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes));
+      dw_tc<false><<<grid, kTcThreads, kDwSmemBytes, st>>>(tmx, tmdy, p);
+    }
+    PL_LAUNCH_CHECK("dw_tc");
+  }
+  if (a->dx) {
+    softplus_kernel<<<ew_grid(nw, 1024), 256, 0, st>>>(a->w_rho, w.sigma, nw);
+    PL_LAUNCH_CHECK("softplus_kernel");
+    CUtensorMap tm;
+    rc = make_tmap_bf16(&tm, w.dyt, (uint64_t)g.mc * g.M, (uint64_t)g.Coutp, 128, kBK);
+    if (rc != PL_OK) return rc;
+    TcGemmParams p;
+    p.mc = g.mc; p.rows = (int)g.M; p.ndim = g.K; p.kdim = g.cout;
+    p.w_in = g.cout; p.w_out = g.K;
+    p.a_mc_rows = g.M;
+    p.w_mu = a->w_mu; p.w_sigma = w.sigma; p.eps_w = a->eps_w;
+    p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
+    p.bias = nullptr;
+    p.out = w.dA;                 // [mc][K][M]: K-major so that col2im reads contiguous pixels
+    p.out_hw = (int)g.M;
+    p.w_aligned = (g.K % 4) == 0;
+    rc = a->eps_w ? launch_gemm<false, true>(tm, p, st) : launch_gemm<false, false>(tm, p, st);
+    if (rc != PL_OK) return rc;
+    const int64_t n = (int64_t)g.mc * g.batch * g.cin * g.h * g.w;
+    col2im_kernel<<<ew_grid(n, 256), 256, 0, st>>>(w.dA, a->dx, g);
+    PL_LAUNCH_CHECK("col2im_kernel");
+  }
+  return PL_OK;
+}
+
+}  // namespace pl

@@ -1,0 +1,943 @@
+// Tensor-core kernels (tcgen05 / TMEM / TMA) shared by the BayesLinear and BayesConv2d paths.
+// Included by linear_tc.cu and conv_tc.cu (kernel templates + launch helpers).
+#pragma once
+
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace pl {
+
+using namespace tc;
+
+constexpr int kBN = 128;               // output-column tile (UMMA N)
+constexpr int kBK = 64;                // k-block (one 128-byte swizzle row of bf16)
+constexpr int kGenWarps = 16;          // generator / epilogue warps (4 per SM sub-partition)
+constexpr int kTcThreads = 64 + kGenWarps * 32;  // + TMA warp + MMA warp = 18 warps
+constexpr int kSubTileBytes = 128 * kBK * 2;  // one [128 x 64] bf16 operand sub-tile = 16 KB
+
+struct TcGemmParams {
+  int mc, rows, ndim, kdim;     // rows = batch; C[mc] is [rows, ndim], reduction over kdim
+  int w_in, w_out;              // weight matrix [I, O]
+  int64_t a_mc_rows;            // rows per MC sample in the A tensor map (0 => broadcast input)
+  const float* w_mu;            // [I, O]
+  const float* w_sigma;         // softplus(rho), [I, O]
+  const float* eps_w;           // optional injected eps [mc, I, O]
+  Sampler sw;
+  const float* bias;            // optional sampled bias [mc, ndim] (forward only)
+  float* out;                   // [mc, rows, ndim]
+  int out_hw;                   // 0: row-major out; >0: out[(mc*rows/out_hw + row/out_hw)][n][row%out_hw]
+                                //    (conv: rows = pixels of all images, NCHW output)
+  int w_aligned;                // weight rows 16-byte aligned (w_out % 4 == 0): 128-bit parameter loads
+};
+
+// ---------------------------------------------------------------------------------------------
+// HBM-bound pre-passes
+// ---------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256) softplus_kernel(const float* __restrict__ rho,
+                                                       float* __restrict__ sigma, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+    sigma[i] = softplus_f(rho[i]);
+}
+
+// fp32 -> bf16, 8 elements per thread per iteration (n % 8 == 0, 16-byte aligned)
+static __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src,
+                                                        __nv_bfloat16* __restrict__ dst, int64_t n8) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (int64_t)gridDim.x * 256) {
+    const float4 a = s4[2 * i], b = s4[2 * i + 1];
+    d4[i] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y),
+                       pack_bf16x2(b.z, b.w));
+  }
+}
+
+// sampled bias b[mc][o] = b_mu + softplus(b_rho) * eps_b[mc][o]
+static __global__ void __launch_bounds__(256) sample_bias_kernel(const float* __restrict__ b_mu,
+                                                          const float* __restrict__ b_rho,
+                                                          const float* __restrict__ eps_b, Sampler sb,
+                                                          int mc, int out, float* __restrict__ dst) {
+  const int groups = (out + 3) / 4;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < mc * groups; t += gridDim.x * 256) {
+    const int m = t / groups, g = t - m * groups;
+    float e[4];
+    if (eps_b) {
+      for (int j = 0; j < 4; ++j) e[j] = (4 * g + j < out) ? eps_b[(int64_t)m * out + 4 * g + j] : 0.f;
+    } else {
+      const float4 n = eps4(sb, m, 0, g);
+      e[0] = n.x; e[1] = n.y; e[2] = n.z; e[3] = n.w;
+    }
+    for (int j = 0; j < 4 && 4 * g + j < out; ++j) {
+      const int o = 4 * g + j;
+      dst[(int64_t)m * out + o] = fmaf(softplus_f(b_rho[o]), e[j], b_mu[o]);
+    }
+  }
+}
+
+// dY fp32 -> bf16 (operand of the dX / dW MMAs) fused with the per-sample column sums the bias
+// gradients need: colsum[mc][o] = sum_b dY[mc][b][o].  One pass over dY instead of two.
+// grid (ceil(O/128), MC), 256 threads = 16 row lanes x 16 column groups of 8.
+static __global__ void __launch_bounds__(256) cast_dy_colsum_kernel(const float* __restrict__ dy,
+                                                             __nv_bfloat16* __restrict__ dst,
+                                                             float* __restrict__ colsum, int batch,
+                                                             int out) {
+  __shared__ float red[16][129];
+  const int mc = blockIdx.y, cg = threadIdx.x & 15, ry = threadIdx.x >> 4;
+  const int col = blockIdx.x * 128 + cg * 8;
+  const bool ok = col < out;  // out % 8 == 0
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int64_t base = (int64_t)mc * batch * out;
+  if (ok) {
+    for (int b = ry; b < batch; b += 16) {
+      const int64_t idx = base + (int64_t)b * out + col;
+      const float4 v0 = *reinterpret_cast<const float4*>(dy + idx);
+      const float4 v1 = *reinterpret_cast<const float4*>(dy + idx + 4);
+      *reinterpret_cast<uint4*>(dst + idx) =
+          make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y),
+                     pack_bf16x2(v1.z, v1.w));
+      s[0] += v0.x; s[1] += v0.y; s[2] += v0.z; s[3] += v0.w;
+      s[4] += v1.x; s[5] += v1.y; s[6] += v1.z; s[7] += v1.w;
+    }
+  }
+  if (colsum == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ry][cg * 8 + j] = s[j];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t += red[r][threadIdx.x];
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c < out) colsum[(int64_t)mc * out + c] = t;
+  }
+}
+
+// db_mu[o] = sum_mc colsum ; db_rho[o] = sigmoid(b_rho) sum_mc colsum * eps_b   (deterministic order)
+static __global__ void __launch_bounds__(128) bias_grad_tc_kernel(const float* __restrict__ colsum,
+                                                           const float* __restrict__ b_rho,
+                                                           const float* __restrict__ eps_b, Sampler sb,
+                                                           int mc, int out, float* __restrict__ db_mu,
+                                                           float* __restrict__ db_rho) {
+  const int o = blockIdx.x * 128 + threadIdx.x;
+  if (o >= out) return;
+  float am = 0.f, ar = 0.f;
+  for (int m = 0; m < mc; ++m) {
+    const float s = colsum[(int64_t)m * out + o];
+    float e;
+    if (eps_b) {
+      e = eps_b[(int64_t)m * out + o];
+    } else {
+      const float4 n = eps4(sb, m, 0, o >> 2);
+      const float v[4] = {n.x, n.y, n.z, n.w};
+      e = v[o & 3];
+    }
+    am += s;
+    ar = fmaf(s, e, ar);
+  }
+  db_mu[o] = am;
+  db_rho[o] = ar * sigmoid_f(b_rho[o]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused sample + GEMM (forward: kDx = false, B operand MN-major; dX: kDx = true, B operand K-major)
+// ---------------------------------------------------------------------------------------------
+template <int MT>
+struct TcCfg {
+  static constexpr int kStagesA = MT == 4 ? 2 : 4;
+  static constexpr int kStagesB = 4;
+  static constexpr int kABytes = MT * kSubTileBytes;
+  static constexpr int kSmemBytes = kStagesA * kABytes + kStagesB * kSubTileBytes + 1024 /*bias + barriers*/
+                                    + 1024 /*alignment slack*/;
+  static constexpr int kTmemCols = MT * kBN;  // 128, 256 or 512: powers of two
+};
+
+template <int MT, bool kDx, bool kInjected>
+__global__ void __launch_bounds__(kTcThreads, 1)
+sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p) {
+  using Cfg = TcCfg<MT>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + Cfg::kStagesA * Cfg::kABytes;
+  const uint32_t sMisc = sB + Cfg::kStagesB * kSubTileBytes;
+  float* bias_s = reinterpret_cast<float*>(smem + (sMisc - smem_base));  // 128 floats
+  const uint32_t bar0 = sMisc + 512;
+  // barrier map (8 bytes each)
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (Cfg::kStagesA + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * Cfg::kStagesA + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (2 * Cfg::kStagesA + Cfg::kStagesB + s); };
+  const uint32_t acc_full = bar0 + 8u * (2 * Cfg::kStagesA + 2 * Cfg::kStagesB);
+  const uint32_t tmem_slot = acc_full + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * kBN;
+  const int m0 = blockIdx.y * (MT * 128);
+  const int mc = blockIdx.z;
+  const int num_kb = (p.kdim + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStagesA; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < Cfg::kStagesB; ++s) {
+      mbar_init(b_full(s), kGenWarps);   // one elected arrival per generator warp
+      mbar_init(b_empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_a);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp >= 2) {  // stage the sampled bias of this column tile
+    const int t = threadIdx.x - 64;
+    if (t < kBN) bias_s[t] = (p.bias && n0 + t < p.ndim) ? p.bias[(int64_t)mc * p.ndim + n0 + t] : 0.f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int row0 = (int)(mc * p.a_mc_rows) + m0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::kStagesA, ph = (kb / Cfg::kStagesA) & 1;
+        mbar_wait(a_empty(s), ph ^ 1);
+        mbar_expect_tx(a_full(s), Cfg::kABytes);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+          tma_load_2d(sA + s * Cfg::kABytes + mt * kSubTileBytes, &tmap_a, a_full(s), kb * kBK,
+                      row0 + mt * 128);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(128, kBN, /*a MN-major*/ 0, /*b MN-major*/ kDx ? 0 : 1);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int sa = kb % Cfg::kStagesA, pa = (kb / Cfg::kStagesA) & 1;
+        const int sb = kb % Cfg::kStagesB, pb = (kb / Cfg::kStagesB) & 1;
+        mbar_wait(a_full(sa), pa);
+        mbar_wait(b_full(sb), pb);
+        tc_fence_after_sync();
+        const uint32_t a_addr = sA + sa * Cfg::kABytes;
+        const uint32_t b_addr = sB + sb * kSubTileBytes;
+#pragma unroll
+        for (int ks = 0; ks < kBK / 16; ++ks) {
+          // A: K-major SW128 (8-row groups 1024 B apart); advancing K by 16 bf16 = 32 B
+          // B: forward MN-major SW128 (64-col groups 8192 B apart = LBO, 8-k groups 1024 B = SBO,
+          //    16 k = 2 groups = 2048 B); dX K-major SW128 like A
+          const uint64_t b_desc = kDx ? smem_desc_sw128(b_addr + ks * 32, 16, 1024)
+                                      : smem_desc_sw128(b_addr + ks * 2048, 8192, 1024);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t a_desc = smem_desc_sw128(a_addr + mt * kSubTileBytes + ks * 32, 16, 1024);
+            mma_bf16_ss(tmem_base + mt * kBN, a_desc, b_desc, idesc, (kb | ks) != 0);
+          }
+        }
+        mma_commit(a_empty(sa));   // frees the activation stage when these MMAs retire
+        mma_commit(b_empty(sb));   // frees the generated-weight stage
+      }
+      mma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    // ===================== W-tile generators =====================
+    // operand element (n, k): forward W[i = k0+k][o = n0+n]; dX W[i = n0+n][o = k0+k].
+    // Each thread owns 4 groups of 4 consecutive o per k-block (one Philox call per group).
+    const int gw = warp - 2;  // 0..15
+    int wrow[4], wcol;        // weight coordinates of the thread's groups at k-block 0
+    uint32_t soff[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (!kDx) {
+        // k = gw + 16 r, n = 4 lane.  MN-major SW128:
+        // [n/64]*8192 + [k/8]*1024 + (k%8)*128 + (((n%64)/8) ^ (k%8))*16 + (n%8)*2
+        wrow[r] = gw + 16 * r;
+        soff[r] = (uint32_t)((lane >> 4) * 8192 + ((gw >> 3) + 2 * r) * 1024 + (gw & 7) * 128 +
+                             ((((lane & 15) >> 1) ^ (gw & 7)) << 4) + ((lane & 1) << 3));
+      } else {
+        // n = 8 gw + 2 r + lane/16, k = 4 (lane%16).  K-major SW128: n*128 + (((k/8) ^ (n%8))*16) + (k%8)*2
+        const int n = 8 * gw + 2 * r + (lane >> 4);
+        wrow[r] = n0 + n;
+        soff[r] = (uint32_t)(n * 128 + ((((lane & 15) >> 1) ^ (n & 7)) << 4) + ((lane & 1) << 3));
+      }
+    }
+    wcol = kDx ? 4 * (lane & 15) : n0 + 4 * lane;
+    const int64_t ldw = p.w_out;
+    const float* eps_base = kInjected ? p.eps_w + (int64_t)mc * p.w_in * p.w_out : nullptr;
+
+    auto gen_block = [&](int kb, auto full_tag) {
+      constexpr bool kFull = decltype(full_tag)::value;
+      const int s = kb % Cfg::kStagesB, ph = (kb / Cfg::kStagesB) & 1;
+      const int k0 = kb * kBK;
+      float4 mu[4], sg[4], ep[4];
+      int row[4];
+      const int col = kDx ? k0 + wcol : wcol;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        row[r] = kDx ? wrow[r] : k0 + wrow[r];
+        const bool ok = kFull || (row[r] < p.w_in && col < p.w_out);
+        const int64_t idx = (int64_t)row[r] * ldw + col;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kFull || p.w_aligned) {
+          mu[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_mu + idx)) : z;
+          sg[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_sigma + idx)) : z;
+          if (kInjected) ep[r] = ok ? __ldg(reinterpret_cast<const float4*>(eps_base + idx)) : z;
+        } else {  // rows not 16-byte aligned / ragged last group (conv K = Cin*k*k): scalar loads
+          float m4[4], s4[4], e4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool okj = ok && col + j < p.w_out;
+            m4[j] = okj ? __ldg(p.w_mu + idx + j) : 0.f;
+            s4[j] = okj ? __ldg(p.w_sigma + idx + j) : 0.f;
+            e4[j] = (kInjected && okj) ? __ldg(eps_base + idx + j) : 0.f;
+          }
+          mu[r] = make_float4(m4[0], m4[1], m4[2], m4[3]);
+          sg[r] = make_float4(s4[0], s4[1], s4[2], s4[3]);
+          if (kInjected) ep[r] = make_float4(e4[0], e4[1], e4[2], e4[3]);
+        }
+      }
+      mbar_wait(b_empty(s), ph ^ 1);
+      const uint32_t dst = sB + s * kSubTileBytes;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float4 e;
+        if (kInjected) e = ep[r];
+        else e = eps4(p.sw, mc, row[r], col >> 2);
+        const uint32_t lo = pack_bf16x2(fmaf(sg[r].x, e.x, mu[r].x), fmaf(sg[r].y, e.y, mu[r].y));
+        const uint32_t hi = pack_bf16x2(fmaf(sg[r].z, e.z, mu[r].z), fmaf(sg[r].w, e.w, mu[r].w));
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + soff[r]), "r"(lo), "r"(hi) : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_full(s));
+    };
+    // tiles fully inside the weight matrix take the predicate-free path
+    const bool n_full = p.w_aligned && (kDx ? (n0 + kBN <= p.w_in) : (n0 + kBN <= p.w_out));
+    const int k_extent = kDx ? p.w_out : p.w_in;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      if (n_full && (kb + 1) * kBK <= k_extent) gen_block(kb, std::true_type{});
+      else gen_block(kb, std::false_type{});
+    }
+    // ===================== epilogue: TMEM -> registers -> HBM =====================
+    mbar_wait(acc_full, 0);
+    tc_fence_after_sync();
+    const int q = warp & 3;        // TMEM lane quadrant this warp may access
+    const int col = (gw >> 2) * 32;  // which 32-column quarter of the tile
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int row = m0 + mt * 128 + q * 32 + lane;
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * kBN + col), v);
+      tmem_ld_wait();
+      if (row < p.rows) {
+        if (p.out_hw == 0) {
+          float* o = p.out + ((int64_t)mc * p.rows + row) * p.ndim + n0 + col;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n0 + col + j < p.ndim) {
+              float4 w;
+              w.x = __uint_as_float(v[j + 0]) + bias_s[col + j + 0];
+              w.y = __uint_as_float(v[j + 1]) + bias_s[col + j + 1];
+              w.z = __uint_as_float(v[j + 2]) + bias_s[col + j + 2];
+              w.w = __uint_as_float(v[j + 3]) + bias_s[col + j + 3];
+              *reinterpret_cast<float4*>(o + j) = w;
+            }
+          }
+        } else {
+          // channel-major output: consecutive lanes (rows = pixels) are contiguous in memory
+          const int img = row / p.out_hw, pix = row - img * p.out_hw;
+          float* o = p.out + (((int64_t)mc * (p.rows / p.out_hw) + img) * p.ndim + n0 + col) * p.out_hw + pix;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + col + j < p.ndim) o[(int64_t)j * p.out_hw] = __uint_as_float(v[j]) + bias_s[col + j];
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// 2-CTA version of sampled_gemm_tc (cta_group::2): a CTA pair on one TPC owns a
+// [MT2 x 256 batch rows] x [256 output columns] tile.  Each CTA stages its own 128 rows of every
+// 256-row activation sub-tile (TMA) and synthesises its own 128 of the 256 weight columns; the
+// leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256) which reads both
+// CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.  Per SM this halves the
+// shared-memory operand traffic of the 1-CTA kernel (8 KB per 128 MMA cycles instead of 8 KB per 64)
+// and the activation bytes per k-block, at the same generated-elements-per-flop ratio.
+//   full barriers live in the leader CTA (peer producers arrive remotely, TMA bytes of both CTAs
+//   are credited to it); empty / accumulator barriers are multicast to both CTAs by tcgen05.commit.
+// ---------------------------------------------------------------------------------------------
+template <int MT2>
+struct Tc2Cfg {
+  static constexpr int kStagesA = 4;
+  static constexpr int kStagesB = 4;
+  static constexpr int kABytes = MT2 * kSubTileBytes;          // this CTA's rows of one k-block
+  static constexpr int kSmemBytes = kStagesA * kABytes + kStagesB * kSubTileBytes + 2048 + 1024;
+  static constexpr int kTmemCols = MT2 * 256;                   // 256 or 512
+};
+
+template <int MT2, bool kDx, bool kInjected>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+sampled_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p) {
+  using Cfg = Tc2Cfg<MT2>;
+  constexpr int kTileN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + Cfg::kStagesA * Cfg::kABytes;
+  const uint32_t sMisc = sB + Cfg::kStagesB * kSubTileBytes;
+  float* bias_s = reinterpret_cast<float*>(smem + (sMisc - smem_base));  // 256 floats
+  const uint32_t bar0 = sMisc + 1024;
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (Cfg::kStagesA + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * Cfg::kStagesA + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (2 * Cfg::kStagesA + Cfg::kStagesB + s); };
+  const uint32_t acc_full = bar0 + 8u * (2 * Cfg::kStagesA + 2 * Cfg::kStagesB);
+  const uint32_t tmem_slot = acc_full + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();        // 0 = leader
+  const int n0 = (blockIdx.x >> 1) * kTileN;      // pair tile: 256 output columns
+  const int nb0 = n0 + (int)rank * 128;           // the 128 columns this CTA synthesises
+  const int m0 = blockIdx.y * (MT2 * 256);
+  const int mc = blockIdx.z;
+  const int num_kb = (p.kdim + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStagesA; ++s) {
+      mbar_init(a_full(s), 2);                    // leader producer (+tx) and peer producer
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < Cfg::kStagesB; ++s) {
+      mbar_init(b_full(s), 2 * kGenWarps);        // one elected arrival per generator warp, both CTAs
+      mbar_init(b_empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_a);
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    if (t < kTileN) bias_s[t] = (p.bias && n0 + t < p.ndim) ? p.bias[(int64_t)mc * p.ndim + n0 + t] : 0.f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs, own rows) =====================
+    if (lane == 0) {
+      const int row0 = (int)(mc * p.a_mc_rows) + m0 + (int)rank * 128;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::kStagesA, ph = (kb / Cfg::kStagesA) & 1;
+        mbar_wait(a_empty(s), ph ^ 1);
+        if (rank == 0) mbar_expect_tx(a_full(s), 2 * Cfg::kABytes);
+        else mbar_arrive_cluster(a_full(s), 0);
+#pragma unroll
+        for (int t = 0; t < MT2; ++t)
+          tma_load_2d_2cta(sA + s * Cfg::kABytes + t * kSubTileBytes, &tmap_a, a_full(s), kb * kBK,
+                           row0 + t * 256);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(256, kTileN, 0, kDx ? 0 : 1);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int sa = kb % Cfg::kStagesA, pa = (kb / Cfg::kStagesA) & 1;
+        const int sb = kb % Cfg::kStagesB, pb = (kb / Cfg::kStagesB) & 1;
+        mbar_wait_cluster(a_full(sa), pa);
+        mbar_wait_cluster(b_full(sb), pb);
+        tc_fence_after_sync();
+        const uint32_t a_addr = sA + sa * Cfg::kABytes;
+        const uint32_t b_addr = sB + sb * kSubTileBytes;
+#pragma unroll
+        for (int ks = 0; ks < kBK / 16; ++ks) {
+          const uint64_t b_desc = kDx ? smem_desc_sw128(b_addr + ks * 32, 16, 1024)
+                                      : smem_desc_sw128(b_addr + ks * 2048, 8192, 1024);
+#pragma unroll
+          for (int t = 0; t < MT2; ++t) {
+            const uint64_t a_desc = smem_desc_sw128(a_addr + t * kSubTileBytes + ks * 32, 16, 1024);
+            mma_bf16_ss_2cta(tmem_base + t * kTileN, a_desc, b_desc, idesc, (kb | ks) != 0);
+          }
+        }
+        mma_commit_2cta(a_empty(sa));
+        mma_commit_2cta(b_empty(sb));
+      }
+      mma_commit_2cta(acc_full);
+    }
+    __syncwarp();
+  } else {
+    // ===================== W-tile generators (both CTAs, own 128 columns) =====================
+    const int gw = warp - 2;  // 0..15
+    int wrow[4], wcol;
+    uint32_t soff[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (!kDx) {
+        wrow[r] = gw + 16 * r;
+        soff[r] = (uint32_t)((lane >> 4) * 8192 + ((gw >> 3) + 2 * r) * 1024 + (gw & 7) * 128 +
+                             ((((lane & 15) >> 1) ^ (gw & 7)) << 4) + ((lane & 1) << 3));
+      } else {
+        const int n = 8 * gw + 2 * r + (lane >> 4);
+        wrow[r] = nb0 + n;
+        soff[r] = (uint32_t)(n * 128 + ((((lane & 15) >> 1) ^ (n & 7)) << 4) + ((lane & 1) << 3));
+      }
+    }
+    wcol = kDx ? 4 * (lane & 15) : nb0 + 4 * lane;
+    const int64_t ldw = p.w_out;
+    const float* eps_base = kInjected ? p.eps_w + (int64_t)mc * p.w_in * p.w_out : nullptr;
+
+    auto gen_block = [&](int kb, auto full_tag) {
+      constexpr bool kFull = decltype(full_tag)::value;
+      const int s = kb % Cfg::kStagesB, ph = (kb / Cfg::kStagesB) & 1;
+      const int k0 = kb * kBK;
+      float4 mu[4], sg[4], ep[4];
+      int row[4];
+      const int col = kDx ? k0 + wcol : wcol;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        row[r] = kDx ? wrow[r] : k0 + wrow[r];
+        const bool ok = kFull || (row[r] < p.w_in && col < p.w_out);
+        const int64_t idx = (int64_t)row[r] * ldw + col;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kFull || p.w_aligned) {
+          mu[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_mu + idx)) : z;
+          sg[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_sigma + idx)) : z;
+          if (kInjected) ep[r] = ok ? __ldg(reinterpret_cast<const float4*>(eps_base + idx)) : z;
+        } else {  // rows not 16-byte aligned / ragged last group (conv K = Cin*k*k): scalar loads
+          float m4[4], s4[4], e4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool okj = ok && col + j < p.w_out;
+            m4[j] = okj ? __ldg(p.w_mu + idx + j) : 0.f;
+            s4[j] = okj ? __ldg(p.w_sigma + idx + j) : 0.f;
+            e4[j] = (kInjected && okj) ? __ldg(eps_base + idx + j) : 0.f;
+          }
+          mu[r] = make_float4(m4[0], m4[1], m4[2], m4[3]);
+          sg[r] = make_float4(s4[0], s4[1], s4[2], s4[3]);
+          if (kInjected) ep[r] = make_float4(e4[0], e4[1], e4[2], e4[3]);
+        }
+      }
+      mbar_wait(b_empty(s), ph ^ 1);
+      const uint32_t dst = sB + s * kSubTileBytes;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float4 e;
+        if (kInjected) e = ep[r];
+        else e = eps4(p.sw, mc, row[r], col >> 2);
+        const uint32_t lo = pack_bf16x2(fmaf(sg[r].x, e.x, mu[r].x), fmaf(sg[r].y, e.y, mu[r].y));
+        const uint32_t hi = pack_bf16x2(fmaf(sg[r].z, e.z, mu[r].z), fmaf(sg[r].w, e.w, mu[r].w));
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + soff[r]), "r"(lo), "r"(hi) : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(b_full(s), 0);   // signal the leader's barrier
+    };
+    const bool n_full = p.w_aligned && (kDx ? (nb0 + 128 <= p.w_in) : (nb0 + 128 <= p.w_out));
+    const int k_extent = kDx ? p.w_out : p.w_in;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      if (n_full && (kb + 1) * kBK <= k_extent) gen_block(kb, std::true_type{});
+      else gen_block(kb, std::false_type{});
+    }
+    // ===================== epilogue: this CTA's 128 rows of every sub-tile, all 256 columns ==========
+    mbar_wait(acc_full, 0);
+    tc_fence_after_sync();
+    const int q = warp & 3;
+#pragma unroll 1
+    for (int t = 0; t < MT2; ++t) {
+      const int row = m0 + t * 256 + (int)rank * 128 + q * 32 + lane;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col = (gw >> 2) * 64 + cc * 32;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * kTileN + col), v);
+        tmem_ld_wait();
+        if (row < p.rows) {
+          if (p.out_hw == 0) {
+            float* o = p.out + ((int64_t)mc * p.rows + row) * p.ndim + n0 + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (n0 + col + j < p.ndim) {
+                float4 w;
+                w.x = __uint_as_float(v[j + 0]) + bias_s[col + j + 0];
+                w.y = __uint_as_float(v[j + 1]) + bias_s[col + j + 1];
+                w.z = __uint_as_float(v[j + 2]) + bias_s[col + j + 2];
+                w.w = __uint_as_float(v[j + 3]) + bias_s[col + j + 3];
+                *reinterpret_cast<float4*>(o + j) = w;
+              }
+            }
+          } else {
+            const int img = row / p.out_hw, pix = row - img * p.out_hw;
+            float* o = p.out + (((int64_t)mc * (p.rows / p.out_hw) + img) * p.ndim + n0 + col) * p.out_hw + pix;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + col + j < p.ndim) o[(int64_t)j * p.out_hw] = __uint_as_float(v[j]) + bias_s[col + j];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();     // the peer's smem / TMEM must outlive the leader's MMAs
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused weight-gradient kernel: one CTA owns a [128 in-rows x 128 out-cols] tile of the weight and
+// walks over all MC samples.  Per sample, dW[mc] = X[mc]^T . dY[mc] (K = batch) is accumulated in
+// TMEM by tcgen05.mma (both operands MN-major straight from the [batch, features] activations via
+// TMA), the accumulator is double-buffered, and the epilogue warps regenerate eps[mc] for the tile
+// from the Philox counter and fold the tile into register accumulators
+//     acc_mu += dW[mc]        acc_rho += dW[mc] * eps[mc]
+// while the tensor core already works on sample mc+1.  dW [MC,I,O] never exists in HBM.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDwStages = 6;
+constexpr int kDwStageBytes = 2 * kSubTileBytes;  // A [128 i x 64 b] + B [128 o x 64 b], bf16
+constexpr int kDwSmemBytes = kDwStages * kDwStageBytes + 1024 + 1024;
+
+struct TcDwParams {
+  int mc, batch, w_in, w_out;
+  int mc_per_split;        // MC samples per split
+  int kb_splits;           // blockIdx.z = mc_split * kb_splits + kb_split
+  int kb_per_split;        // reduction k-blocks (64 rows each) per split
+  int x_broadcast;         // input has no MC axis
+  int atomic_out;          // several MC splits add into zero-initialised outputs
+  int dy_broadcast;        // the second operand has no MC axis (conv: im2col of an MC-broadcast input)
+  int w_aligned;           // w_out % 4 == 0: 128-bit eps / rho loads and gradient stores
+  const float* w_rho;      // [I, O]
+  const float* eps_w;      // optional injected eps [mc, I, O]
+  Sampler sw;
+  float* dw_mu;
+  float* dw_rho;
+};
+
+template <bool kInjected>
+__global__ void __launch_bounds__(kTcThreads, 1)
+dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+      const TcDwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sStage = smem_base;
+  const uint32_t bar0 = sStage + kDwStages * kDwStageBytes;
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (kDwStages + s); };
+  auto acc_full = [&](int b) { return bar0 + 8u * (2 * kDwStages + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (2 * kDwStages + 2 + b); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * kDwStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o0 = blockIdx.x * 128, i0 = blockIdx.y * 128;
+  const int mc_begin = ((int)blockIdx.z / p.kb_splits) * p.mc_per_split;
+  const int mc_end = min(p.mc, mc_begin + p.mc_per_split);
+  const int kb_begin = ((int)blockIdx.z % p.kb_splits) * p.kb_per_split;
+  const int kb_end = min((p.batch + kBK - 1) / kBK, kb_begin + p.kb_per_split);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDwStages; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), kGenWarps);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_dy);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int mc = mc_begin; mc < mc_end; ++mc) {
+        const int xm = p.x_broadcast ? 0 : mc;
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % kDwStages, ph = (it / kDwStages) & 1;
+          mbar_wait(empty(s), ph ^ 1);
+          mbar_expect_tx(full(s), kDwStageBytes);
+          const uint32_t dst = sStage + s * kDwStageBytes;
+          // MN-major operand sub-tiles: [64 batch rows] x [64 features = 128 B], two per operand
+          tma_load_3d(dst, &tmap_x, full(s), i0, kb * kBK, xm);
+          tma_load_3d(dst + 8192, &tmap_x, full(s), i0 + 64, kb * kBK, xm);
+          const int ym = p.dy_broadcast ? 0 : mc;
+          tma_load_3d(dst + kSubTileBytes, &tmap_dy, full(s), o0, kb * kBK, ym);
+          tma_load_3d(dst + kSubTileBytes + 8192, &tmap_dy, full(s), o0 + 64, kb * kBK, ym);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(128, 128, 1, 1);
+      int it = 0;
+      for (int mc = mc_begin, n = 0; mc < mc_end; ++mc, ++n) {
+        const int buf = n & 1;
+        mbar_wait(acc_empty(buf), ((n >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % kDwStages, ph = (it / kDwStages) & 1;
+          mbar_wait(full(s), ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = sStage + s * kDwStageBytes, b_addr = a_addr + kSubTileBytes;
+#pragma unroll
+          for (int ks = 0; ks < kBK / 16; ++ks) {
+            // 16 batch rows = two 8-row swizzle groups = 2048 B; 64-feature groups 8192 B apart
+            const uint64_t a_desc = smem_desc_sw128(a_addr + ks * 2048, 8192, 1024);
+            const uint64_t b_desc = smem_desc_sw128(b_addr + ks * 2048, 8192, 1024);
+            mma_bf16_ss(tmem_base + buf * 128, a_desc, b_desc, idesc, (kb > kb_begin) || ks != 0);
+          }
+          mma_commit(empty(s));
+        }
+        mma_commit(acc_full(buf));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: eps regeneration + MC reduction =====================
+    const int gw = warp - 2, q = warp & 3, h = gw >> 2;
+    constexpr int kCols = 128 / (kGenWarps / 4);   // weight columns per thread (32)
+    const int row = i0 + q * 32 + lane;          // weight row (in-feature) this thread owns
+    const int col0 = o0 + h * kCols;             // first of its weight columns
+    float acc_mu[kCols], acc_rho[kCols];
+#pragma unroll
+    for (int j = 0; j < kCols; ++j) acc_mu[j] = acc_rho[j] = 0.f;
+    for (int mc = mc_begin, n = 0; mc < mc_end; ++mc, ++n) {
+      const int buf = n & 1;
+      mbar_wait(acc_full(buf), (n >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < kCols / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + h * kCols + c * 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = col0 + c * 16 + g * 4;
+          float4 e;
+          if (kInjected) {
+            e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < p.w_in && col < p.w_out) {
+              const float* ep = p.eps_w + ((int64_t)mc * p.w_in + row) * p.w_out + col;
+              if (p.w_aligned) {
+                e = __ldg(reinterpret_cast<const float4*>(ep));
+              } else {
+                e.x = __ldg(ep);
+                if (col + 1 < p.w_out) e.y = __ldg(ep + 1);
+                if (col + 2 < p.w_out) e.z = __ldg(ep + 2);
+                if (col + 3 < p.w_out) e.w = __ldg(ep + 3);
+              }
+            }
+          } else {
+            e = eps4(p.sw, mc, row, col >> 2);
+          }
+          const int j = c * 16 + g * 4;
+          const float d0 = __uint_as_float(v[g * 4 + 0]), d1 = __uint_as_float(v[g * 4 + 1]),
+                      d2 = __uint_as_float(v[g * 4 + 2]), d3 = __uint_as_float(v[g * 4 + 3]);
+          acc_mu[j + 0] += d0; acc_rho[j + 0] = fmaf(d0, e.x, acc_rho[j + 0]);
+          acc_mu[j + 1] += d1; acc_rho[j + 1] = fmaf(d1, e.y, acc_rho[j + 1]);
+          acc_mu[j + 2] += d2; acc_rho[j + 2] = fmaf(d2, e.z, acc_rho[j + 2]);
+          acc_mu[j + 3] += d3; acc_rho[j + 3] = fmaf(d3, e.w, acc_rho[j + 3]);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+    }
+    if (row < p.w_in) {
+#pragma unroll
+      for (int j = 0; j < kCols; j += 4) {
+        const int col = col0 + j;
+        if (col < p.w_out) {
+          const int64_t idx = (int64_t)row * p.w_out + col;
+          if (!p.w_aligned) {   // ragged / unaligned rows (conv K = Cin*k*k): element-wise tail
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (col + t < p.w_out) {
+                const float gmv = acc_mu[j + t];
+                const float grv = acc_rho[j + t] * sigmoid_f(__ldg(p.w_rho + idx + t));
+                if (p.atomic_out) {
+                  atomicAdd(p.dw_mu + idx + t, gmv);
+                  atomicAdd(p.dw_rho + idx + t, grv);
+                } else {
+                  p.dw_mu[idx + t] = gmv;
+                  p.dw_rho[idx + t] = grv;
+                }
+              }
+            continue;
+          }
+          const float4 r = __ldg(reinterpret_cast<const float4*>(p.w_rho + idx));
+          float4 gm = make_float4(acc_mu[j], acc_mu[j + 1], acc_mu[j + 2], acc_mu[j + 3]);
+          float4 gr = make_float4(acc_rho[j] * sigmoid_f(r.x), acc_rho[j + 1] * sigmoid_f(r.y),
+                                  acc_rho[j + 2] * sigmoid_f(r.z), acc_rho[j + 3] * sigmoid_f(r.w));
+          if (p.atomic_out) {
+            atomicAdd(p.dw_mu + idx + 0, gm.x); atomicAdd(p.dw_mu + idx + 1, gm.y);
+            atomicAdd(p.dw_mu + idx + 2, gm.z); atomicAdd(p.dw_mu + idx + 3, gm.w);
+            atomicAdd(p.dw_rho + idx + 0, gr.x); atomicAdd(p.dw_rho + idx + 1, gr.y);
+            atomicAdd(p.dw_rho + idx + 2, gr.z); atomicAdd(p.dw_rho + idx + 3, gr.w);
+          } else {
+            *reinterpret_cast<float4*>(p.dw_mu + idx) = gm;
+            *reinterpret_cast<float4*>(p.dw_rho + idx) = gr;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols], box [box_rows, 64 cols], SWIZZLE_128B
+static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols,
+                          uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return PL_ERR_CUDA;
+  }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %llu cols %llu)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols);
+    return PL_ERR_CUDA;
+  }
+  return PL_OK;
+}
+
+// 3-D bf16 tensor [mc, rows, cols] (cols innermost), box [1, box_rows, box_cols]: out-of-range rows
+// of one MC sample are zero-filled instead of running into the next sample
+static int make_tmap_bf16_3d(CUtensorMap* m, const void* base, uint64_t mc, uint64_t rows, uint64_t cols,
+                             uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return PL_ERR_CUDA;
+  }
+  const cuuint64_t dims[3] = {cols, rows, mc};
+  const cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
+  const cuuint32_t box[3] = {box_cols, box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+    return PL_ERR_CUDA;
+  }
+  return PL_OK;
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static inline int ew_grid(int64_t n, int per_block) {
+  int64_t g = (n + per_block - 1) / per_block;
+  return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+}
+
+// PL_TC_2CTA=1 selects the cta_group::2 kernels.  Measured on C4 (r01): 2.22 ms vs 1.78 ms per
+// 4096^2 forward for the 1-CTA kernel -- the kernels are bound by the sampler's issue rate, not by
+// shared-memory operand traffic, and pairing two SMs per stage hand-off costs more than it saves.
+// Kept (parity-tested) for when the sampler gets cheaper.
+static int g_force_1cta = -1;
+
+template <bool kDx, bool kInj>
+static int launch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_t st) {
+  if (g_force_1cta < 0) {
+    const char* e = getenv("PL_TC_2CTA");
+    g_force_1cta = (e && e[0] == '1') ? 0 : 1;
+  }
+  if (!g_force_1cta && p.rows > 128 && p.ndim > 128) {
+    const int pair_rows = p.rows > 256 ? 512 : 256;
+    dim3 grid(2u * (unsigned)((p.ndim + 255) / 256), (unsigned)((p.rows + pair_rows - 1) / pair_rows),
+              (unsigned)p.mc);
+    if (pair_rows == 512) {
+      auto kern = sampled_gemm_tc2<2, kDx, kInj>;
+      PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<2>::kSmemBytes));
+      kern<<<grid, kTcThreads, Tc2Cfg<2>::kSmemBytes, st>>>(tm, p);
+    } else {
+      auto kern = sampled_gemm_tc2<1, kDx, kInj>;
+      PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<1>::kSmemBytes));
+      kern<<<grid, kTcThreads, Tc2Cfg<1>::kSmemBytes, st>>>(tm, p);
+    }
+    PL_LAUNCH_CHECK("sampled_gemm_tc2");
+    return PL_OK;
+  }
+  const int mt_rows = p.rows > 256 ? 512 : (p.rows > 128 ? 256 : 128);
+  dim3 grid((unsigned)((p.ndim + kBN - 1) / kBN), (unsigned)((p.rows + mt_rows - 1) / mt_rows),
+            (unsigned)p.mc);
+#define PL_LAUNCH_MT(MT)                                                                            \
+  do {                                                                                              \
+    auto kern = sampled_gemm_tc<MT, kDx, kInj>;                                                     \
+    PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
+                                 TcCfg<MT>::kSmemBytes));                                           \
+    kern<<<grid, kTcThreads, TcCfg<MT>::kSmemBytes, st>>>(tm, p);                                    \
+  } while (0)
+  if (mt_rows == 512) PL_LAUNCH_MT(4);
+  else if (mt_rows == 256) PL_LAUNCH_MT(2);
+  else PL_LAUNCH_MT(1);
+#undef PL_LAUNCH_MT
+  PL_LAUNCH_CHECK("sampled_gemm_tc");
+  return PL_OK;
+}
+
+
+}  // namespace pl

@@ -204,15 +204,18 @@ class _BayesConv2dFn(torch.autograd.Function):
         a = _cabi.Conv2dArgs()
         a.mc, a.batch, a.cin, a.cout, a.h, a.w = mc, batch, cin, cout, h, w
         a.k, a.stride, a.padding, a.dilation = k, stride, padding, dilation
-        a.precision = _cabi.PREC_FP32 if spec.precision != _cabi.PREC_FP32 else spec.precision
+        a.precision = spec.precision
         a.x, a.x_mc_stride = _cabi.ptr(xb), x_stride
         a.w_mu, a.w_rho, a.b_mu, a.b_rho = (_cabi.ptr(t) for t in tens[:4])
         a.seed, a.layer_id, a.mc_global_offset = spec.seed, spec.layer_id, spec.mc_global_offset
         a.eps_w, a.eps_b = _cabi.ptr(tens[4]), _cabi.ptr(tens[5])
         a.y = _cabi.ptr(y)
+        ws = _workspace(lib.pl_conv2d_workspace_bytes(C.byref(a)), x.device)
+        a.workspace, a.workspace_bytes = _cabi.ptr(ws), ws.numel()
         a.stream = _cabi.current_stream(x.device)
         with torch.cuda.device(x.device):
-            _cabi.check(lib.pl_conv2d_fwd(C.byref(a)), "pl_conv2d_fwd")
+            _timed(f"conv_fwd[{mc}x{batch}x{cin}x{h}x{w}->{cout}]",
+                   lambda: _cabi.check(lib.pl_conv2d_fwd(C.byref(a)), "pl_conv2d_fwd"))
         ctx.save_for_backward(xb, *tens)
         ctx.meta = (spec, hyper, x_stride, (mc, batch, cin, cout, h, w), a.precision)
         return y
@@ -244,11 +247,12 @@ class _BayesConv2dFn(torch.autograd.Function):
         a.eps_w, a.eps_b = _cabi.ptr(eps_w), _cabi.ptr(eps_b)
         a.dy, a.dx = _cabi.ptr(dy), _cabi.ptr(dx)
         a.dw_mu, a.dw_rho, a.db_mu, a.db_rho = (_cabi.ptr(t) for t in (dw_mu, dw_rho, db_mu, db_rho))
-        ws = _workspace(4 * mc * cout, dev)
+        ws = _workspace(lib.pl_conv2d_workspace_bytes(C.byref(a)), dev)
         a.workspace, a.workspace_bytes = _cabi.ptr(ws), ws.numel()
         a.stream = _cabi.current_stream(dev)
         with torch.cuda.device(dev):
-            _cabi.check(lib.pl_conv2d_bwd(C.byref(a)), "pl_conv2d_bwd")
+            _timed(f"conv_bwd[{mc}x{batch}x{cin}x{h}x{w}->{cout}]",
+                   lambda: _cabi.check(lib.pl_conv2d_bwd(C.byref(a)), "pl_conv2d_bwd"))
         return dx, dw_mu, dw_rho, db_mu, db_rho, None, None, None, None
 
 

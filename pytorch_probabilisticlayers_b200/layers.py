@@ -364,7 +364,13 @@ class BayesConv2d(_FusedBayesLayer):
         assert x.dim() == 5, f'Input tensor not of shape [num_MC, batch_size in_channels, height, width], but {x.shape=}'
         assert x.shape[0] == self.num_MC, f'Input.shape={x.shape} with [{x.shape[0]=}]!=[{self.num_MC=}]'
         mc = x.shape[0]
-        eps_w, eps_b, spec = self._draw(mc, x.device, False)
+        # tensor cores pay off once the per-sample GEMM has a few full tiles
+        k = self.kernel_size
+        ho = (x.shape[3] + 2 * self.padding - self.dilation * (k - 1) - 1) // self.stride + 1
+        wo = (x.shape[4] + 2 * self.padding - self.dilation * (k - 1) - 1) // self.stride + 1
+        tc_ok = (x.shape[1] * ho * wo >= 512 and self.out_channels >= 32
+                 and self.in_channels * k * k >= 32)
+        eps_w, eps_b, spec = self._draw(mc, x.device, tc_ok)
         out = PF.bayes_conv2d(x, self.weight.loc, self.weight.logscale, self.bias.loc,
                               self.bias.logscale, self.kernel_size, self.stride, self.padding,
                               self.dilation, eps_w, eps_b, spec)

@@ -135,3 +135,69 @@ def test_tc_rejects_unsupported_shapes_loudly(plb):
     auto = plb.BayesLinear(30, 20).cuda()
     auto.precision = "auto"                      # auto falls back to the fp32 kernels by shape
     assert auto(torch.zeros(2, 4, 30, device="cuda")).shape == (2, 4, 20)
+
+
+# ---------------------------------------------------------------------------------------------
+# BayesConv2d on the tensor-core kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["conv_small", "conv_strided", "conv_k5"])
+def test_tc_conv_injected_eps_matches_reference_golden(plb, name):
+    g = load_golden(name)
+    k, s, pad, d = (int(v) for v in g["hyper"])
+    mc = g["x"].shape[0]
+    cout, cin = g["w_mu"].shape[:2]
+    layer = plb.BayesConv2d(cin, cout, k, stride=s, padding=pad, dilation=d, num_MC=mc,
+                            prior_scale=float(g["prior"])).cuda()
+    layer.precision = "bf16"
+    with torch.no_grad():
+        layer.weight.loc.copy_(dev(g["w_mu"]))
+        layer.weight.logscale.copy_(dev(g["w_rho"]))
+        layer.bias.loc.copy_(dev(g["b_mu"]))
+        layer.bias.logscale.copy_(dev(g["b_rho"]))
+    layer.inject_eps(dev(g["eps_w"]), dev(g["eps_b"]))
+    x = dev(g["x"]).requires_grad_(True)
+    out = layer(x)
+    assert out.shape == g["out"].shape
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < BF16_TOL
+    (out * dev(g["gy"])).sum().backward()
+    assert rel_err(x.grad.cpu().numpy(), g["dx"]) < BF16_TOL
+    assert rel_err(layer.weight.loc.grad.cpu().numpy(), g["dw_mu"]) < BF16_TOL
+    assert rel_err(layer.weight.logscale.grad.cpu().numpy(), g["dw_rho"]) < BF16_TOL
+    assert rel_err(layer.bias.loc.grad.cpu().numpy(), g["db_mu"]) < 1e-4
+    assert rel_err(layer.bias.logscale.grad.cpu().numpy(), g["db_rho"]) < 1e-4
+
+
+@pytest.mark.parametrize("mc,b,cin,cout,hw,k,s,p,d,expand", [
+    (2, 4, 8, 40, 12, 3, 1, 1, 1, False),
+    (3, 2, 3, 96, 16, 5, 1, 2, 1, True),     # C3 conv1-like: K = 75 (unaligned rows), MC-broadcast input
+    (2, 3, 16, 136, 9, 3, 2, 1, 1, False),   # stride 2, two Cout tiles
+    (2, 2, 6, 33, 11, 3, 1, 2, 2, False),    # dilation 2
+])
+def test_tc_conv_philox_matches_fp64_oracle(plb, mc, b, cin, cout, hw, k, s, p, d, expand):
+    torch.manual_seed(cout)
+    plb.manual_seed(777 + cin)
+    layer = plb.BayesConv2d(cin, cout, k, stride=s, padding=p, dilation=d, num_MC=mc).cuda()
+    layer.precision = "bf16"
+    with torch.no_grad():
+        layer.weight.logscale.uniform_(-4, -1)
+        layer.bias.logscale.uniform_(-3, 0)
+    if expand:
+        x = torch.randn(b, cin, hw, hw, device="cuda").unsqueeze(0).expand(mc, b, cin, hw, hw)
+    else:
+        x = torch.randn(mc, b, cin, hw, hw, device="cuda", requires_grad=True)
+    out = layer(x)
+    gy = torch.randn_like(out)
+    (out * gy).sum().backward()
+    n = lambda t: t.detach().cpu().numpy()
+    eps_w, eps_b = n(layer.weight.eps), n(layer.bias.eps)
+    want = cf.conv2d_fwd(n(x), n(layer.weight.loc), n(layer.weight.logscale), eps_w,
+                         n(layer.bias.loc), n(layer.bias.logscale), eps_b, s, p, d)
+    assert rel_err(n(out), want) < BF16_TOL
+    bw = cf.conv2d_bwd(n(gy), n(x), n(layer.weight.loc), n(layer.weight.logscale), eps_w,
+                       n(layer.bias.logscale), eps_b, s, p, d)
+    if not expand:
+        assert rel_err(n(x.grad), bw["dx"]) < BF16_TOL
+    assert rel_err(n(layer.weight.loc.grad), bw["dw_mu"]) < BF16_TOL
+    assert rel_err(n(layer.weight.logscale.grad), bw["dw_rho"]) < BF16_TOL
+    assert rel_err(n(layer.bias.loc.grad), bw["db_mu"]) < 1e-4
+    assert rel_err(n(layer.bias.logscale.grad), bw["db_rho"]) < 1e-4
