@@ -35,6 +35,12 @@ WORKLOADS = {
                name="C4 wide Bayesian MLP 4096-4096-4096-1000, MC=64, batch 512"),
     "c2": dict(dims=[784, 1200, 1200, 10], mc=32, batch=256, num_samples=55000, lr=1e-3,
                name="C2 MNIST-shaped Bayesian MLP 784-1200-1200-10, MC=32, batch 256"),
+    # CIFAR-shaped Bayesian ConvNet (experiments/BNN.py:228-253); single GPU only: MC_BatchNorm2D
+    # pools statistics over MC
+    "c3": dict(conv=True, in_dims=(3, 32, 32), dims=[3 * 32 * 32, 10], mc=16, batch=128,
+               num_samples=50000, lr=1e-3, flops=1.8334e12,
+               name="C3 CIFAR-shaped Bayesian ConvNet 3-96-128-256-128 (k5,p2)+BN+pool, 512-200-10, "
+                    "MC=16, batch 128"),
 }
 METRIC = "mc_samples_x_examples_per_sec_per_train_step"
 UNIT = "MC-sample*examples/s"
@@ -70,10 +76,14 @@ def cpu_port_throughput(wl, mc_sample, steps, warmup):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(1234)
-    net = tp.build_mlp(wl["dims"], mc_sample, torch.nn.LeakyReLU)
+    if wl.get("conv"):
+        net = tp.build_convnet(mc_sample, wl["in_dims"])
+        x = torch.randn(wl["batch"], *wl["in_dims"])
+    else:
+        net = tp.build_mlp(wl["dims"], mc_sample, torch.nn.LeakyReLU)
+        x = torch.randn(wl["batch"], wl["dims"][0])
     crit = tp.MCCrossEntropyPort(wl["num_samples"])
     opt = torch.optim.Adam(net.parameters(), wl["lr"])
-    x = torch.randn(wl["batch"], wl["dims"][0])
     y = torch.randint(0, wl["dims"][-1], (wl["batch"],))
     for _ in range(warmup):
         tp.train_step(net, crit, opt, x, y, wl["num_samples"])
@@ -90,7 +100,7 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    mc_sample = 4 if args.workload == "c4" else 8
+    mc_sample = {"c4": 4, "c2": 8, "c3": 2}[args.workload]
     steps = max(1, min(args.steps, 10))
     warmup = max(1, min(args.warmup, 2))
     value, ms, cores = cpu_port_throughput(wl, mc_sample, steps, warmup)
@@ -195,16 +205,30 @@ def run_b200(args, wl):
     dims, mc_total, batch, ns = wl["dims"], wl["mc"], wl["batch"], wl["num_samples"]
     assert mc_total % world == 0
     mc_local = mc_total // world
-    mods = [plb.MC_ExpansionLayer(num_MC=mc_local, input_dim=2)]
-    for li in range(len(dims) - 1):
-        mods.append(plb.BayesLinear(dims[li], dims[li + 1]))
-        if li + 2 < len(dims):
-            mods.append(torch.nn.LeakyReLU())
-    net = torch.nn.Sequential(*mods).to(dev)
+    if wl.get("conv"):
+        assert world == 1, "C3 couples MC samples through MC_BatchNorm2D: single GPU (replicas only)"
+        chans = [wl["in_dims"][0], 96, 128, 256, 128]
+        mods = [plb.MC_ExpansionLayer(num_MC=mc_local, input_dim=4)]
+        for li in range(4):
+            mods += [plb.BayesConv2d(chans[li], chans[li + 1], 5, stride=1, padding=2, num_MC=mc_local),
+                     plb.MC_BatchNorm2D(chans[li + 1]), torch.nn.LeakyReLU(), plb.MC_MaxPool2d(2, 2)]
+        mods += [plb.BayesAdaptiveInit_FlattenAndLinear(200), torch.nn.LeakyReLU(),
+                 plb.BayesLinear(200, dims[-1])]
+        net = torch.nn.Sequential(*mods).to(dev)
+        with torch.no_grad():      # the reference's dry run (experiments/BNN.py:253), on the device
+            net(torch.randn(1, *wl["in_dims"], device=dev))
+    else:
+        mods = [plb.MC_ExpansionLayer(num_MC=mc_local, input_dim=2)]
+        for li in range(len(dims) - 1):
+            mods.append(plb.BayesLinear(dims[li], dims[li + 1]))
+            if li + 2 < len(dims):
+                mods.append(torch.nn.LeakyReLU())
+        net = torch.nn.Sequential(*mods).to(dev)
     trainer = ELBOTrainStep(net, plb.MC_CrossEntropyLoss(ns), ns, lr=wl["lr"])
     assert trainer.set_shard(mc_total) == mc_local
 
-    x_host = torch.randn(batch, dims[0]).pin_memory()
+    x_host = (torch.randn(batch, *wl["in_dims"]) if wl.get("conv")
+              else torch.randn(batch, dims[0])).pin_memory()
     y_host = torch.randint(0, dims[-1], (batch,)).pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
@@ -271,25 +295,21 @@ def run_b200(args, wl):
     per_call = {k: v[1] / v[0] for k, v in prof.items()}                  # ms per call
     per_step = {k: v[1] / prof_steps for k, v in prof.items()}            # ms per step
     top = max(per_step, key=per_step.get)
-    shape = top[top.index("[") + 1:-1]
-    if top.startswith("linear"):
-        m_, b_, i_, o_ = (int(v) for v in shape.split("x"))
-        flops = 2.0 * m_ * b_ * i_ * o_
-        achieved = flops / (per_call[top] * 1e-3) / 1e12
+    kind, amount = PF._WORK.get(top, ("flops", 0.0))
+    if kind == "flops":
+        achieved = amount / (per_call[top] * 1e-3) / 1e12
         peak = pk["tf_sustained"]
         roofline = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": pk["source"] + " bf16 dense sustained",
-                    "ms_per_launch": per_call[top],
-                    "algorithmic_flops_per_launch": flops}
+                    "ms_per_launch": per_call[top], "algorithmic_flops_per_launch": amount,
+                    "note": "C-ABI call = fused tcgen05 kernel + its HBM-bound pre-passes"}
     else:
-        n_ = int(shape)
-        nbytes = (8.0 if top.startswith("kl_fwd") else 24.0) * n_
-        achieved = nbytes / (per_call[top] * 1e-3) / 1e9
+        achieved = amount / (per_call[top] * 1e-3) / 1e9
         roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": pk["hbm"],
                     "unit": "GB/s", "frac": achieved / pk["hbm"], "traffic": None,
                     "peak_source": pk["source"], "ms_per_launch": per_call[top],
-                    "algorithmic_bytes_per_launch": nbytes}
+                    "algorithmic_bytes_per_launch": amount}
     # secondary: the KL reduction against the HBM roofline (north_star target (c)): the kernel
     # launched back to back over the two 4096x4096 layers' (mu, rho) in turn (2 x 134 MB > L2, so
     # every launch streams from HBM), CUDA events around the batch
@@ -327,13 +347,13 @@ def run_b200(args, wl):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        mc_sample = 4 if args.workload == "c4" else 8
+        mc_sample = {"c4": 4, "c2": 8, "c3": 2}[args.workload]
         v, ms, cores = cpu_port_throughput(wl, mc_sample, 3, 1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step_sample": ms,
                "sample": f"MC={mc_sample} of {wl['mc']}, full batch {wl['batch']}, 3 timed steps "
                          f"after 1 warm-up, torch CPU fp32, {cores} threads"}
 
-    flops = step_flops(dims, mc_total, batch)
+    flops = wl.get("flops") or step_flops(dims, mc_total, batch)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -370,7 +390,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c4")
-    ap.add_argument("--precision", choices=["fp32", "bf16", "auto"], default="bf16")
+    ap.add_argument("--precision", choices=["fp32", "bf16", "auto"], default="auto",
+                    help="auto = bf16 tcgen05 kernels wherever the layer shape tiles, fp32 kernels for tiny layers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

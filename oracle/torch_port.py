@@ -115,6 +115,65 @@ class MCExpansionPort(torch.nn.Module):
         return x
 
 
+class MCBatchNorm2DPort(torch.nn.modules.batchnorm._BatchNorm):
+    """src/ProbabilisticLayers.py:736-762 (statistics pooled over MC, B, H, W)"""
+
+    def _check_input_dim(self, input):
+        return
+
+    def forward(self, x):
+        factor = 0.0 if self.momentum is None else self.momentum
+        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked += 1
+            factor = 1.0 / float(self.num_batches_tracked) if self.momentum is None else self.momentum
+        out = x.permute(1, 2, 3, 4, 0)                                                   # :757
+        out = F.batch_norm(out, self.running_mean, self.running_var, self.weight, self.bias,
+                           self.training or not self.track_running_stats, factor, self.eps)
+        return out.permute(4, 0, 1, 2, 3)                                                # :761
+
+
+class MCMaxPool2dPort(torch.nn.Module):
+    """src/ProbabilisticLayers.py:207-236 (fold MC into channels, pool, unfold: 3 copies)"""
+
+    def __init__(self, kernel_size=2, stride=2):
+        super().__init__()
+        self.kernel_size, self.stride = kernel_size, stride
+
+    def forward(self, x):
+        mc, bs, c = x.shape[:3]
+        out = x.permute(1, 0, 2, 3, 4).flatten(1, 2).contiguous()
+        out = F.max_pool2d(out, kernel_size=self.kernel_size, stride=self.stride)
+        out = out.reshape(bs, mc, c, out.shape[-2], out.shape[-1]).contiguous()
+        return out.permute(1, 0, 2, 3, 4).contiguous()
+
+
+class FlattenAndLinearPort(torch.nn.Module):
+    """src/ProbabilisticLayers.py:787-808"""
+
+    def __init__(self, in_features, num_hidden):
+        super().__init__()
+        self.linear = BayesLinearPort(in_features, num_hidden)
+
+    def forward(self, x):
+        return self.linear(x.flatten(2, -1))
+
+
+def build_convnet(num_mc, in_dims=(3, 32, 32), num_hidden=200, num_classes=10):
+    """experiments/BNN.py:228-253 ('cbnn'): 4 x [BayesConv2d(k5,p2) - MC_BatchNorm2D - LeakyReLU -
+    MC_MaxPool2d(2,2)] with channels 3-96-128-256-128, then flatten - BayesLinear - LeakyReLU -
+    BayesLinear."""
+    chans = [in_dims[0], 96, 128, 256, 128]
+    mods = [MCExpansionPort(num_mc, 4)]
+    hw = in_dims[1]
+    for i in range(4):
+        mods += [BayesConv2dPort(chans[i], chans[i + 1], 5, stride=1, padding=2, num_MC=num_mc),
+                 MCBatchNorm2DPort(chans[i + 1]), torch.nn.LeakyReLU(), MCMaxPool2dPort(2, 2)]
+        hw //= 2
+    mods += [FlattenAndLinearPort(chans[-1] * hw * hw, num_hidden), torch.nn.LeakyReLU(),
+             BayesLinearPort(num_hidden, num_classes)]
+    return torch.nn.Sequential(*mods)
+
+
 class MCCrossEntropyPort(torch.nn.Module):
     """src/ProbabilisticLayers.py:22-43"""
 

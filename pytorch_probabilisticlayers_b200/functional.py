@@ -27,6 +27,7 @@ class SampleSpec:
 
 # ---- optional per-call CUDA-event timing (bench.py's roofline leg) -----------------------------
 _PROFILE = None
+_WORK = {}     # tag -> ("flops" | "bytes", algorithmic amount per call), filled while profiling
 
 
 def profile_start():
@@ -43,9 +44,11 @@ def profile_stop():
     return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (prof or {}).items()}
 
 
-def _timed(tag, fn):
+def _timed(tag, fn, work=None):
     if _PROFILE is None:
         return fn()
+    if work is not None:
+        _WORK[tag] = work
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     r = fn()
@@ -121,7 +124,8 @@ class _BayesLinearFn(torch.autograd.Function):
         a.stream = _cabi.current_stream(x.device)
         with torch.cuda.device(x.device):
             _timed(f"linear_fwd[{mc}x{batch}x{fin}x{fout}]",
-                   lambda: _cabi.check(lib.pl_linear_fwd(C.byref(a)), "pl_linear_fwd"))
+                   lambda: _cabi.check(lib.pl_linear_fwd(C.byref(a)), "pl_linear_fwd"),
+                   ("flops", 2.0 * mc * batch * fin * fout))
         ctx.save_for_backward(None if state is not None else xb, w_mu_c, w_rho_c, b_mu_c, b_rho_c,
                               eps_w_c, eps_b_c, state)
         ctx.meta = (spec, param_mode, x_stride, mc, batch, fin, fout, tuple(x.shape))
@@ -174,7 +178,9 @@ class _BayesLinearFn(torch.autograd.Function):
                         continue
                     a.dx, a.dw_mu, a.dw_rho, a.db_mu, a.db_rho = sel
                     _timed(f"linear_bwd_{tag}{shape}",
-                           lambda: _cabi.check(lib.pl_linear_bwd(C.byref(a)), "pl_linear_bwd"))
+                           lambda: _cabi.check(lib.pl_linear_bwd(C.byref(a)), "pl_linear_bwd"),
+                           ("flops", 2.0 * mc * batch * fin * fout) if tag != "db"
+                           else ("bytes", 4.0 * mc * batch * fout))
                 a.dx, a.dw_mu, a.dw_rho, a.db_mu, a.db_rho = outs
         return dx, dw_mu, dw_rho, db_mu, db_rho, None, None, None, None
 
@@ -214,8 +220,9 @@ class _BayesConv2dFn(torch.autograd.Function):
         a.workspace, a.workspace_bytes = _cabi.ptr(ws), ws.numel()
         a.stream = _cabi.current_stream(x.device)
         with torch.cuda.device(x.device):
-            _timed(f"conv_fwd[{mc}x{batch}x{cin}x{h}x{w}->{cout}]",
-                   lambda: _cabi.check(lib.pl_conv2d_fwd(C.byref(a)), "pl_conv2d_fwd"))
+            _timed(f"conv_fwd[{mc}x{batch}x{cin}x{h}x{w}->{cout},k{k}]",
+                   lambda: _cabi.check(lib.pl_conv2d_fwd(C.byref(a)), "pl_conv2d_fwd"),
+                   ("flops", 2.0 * mc * batch * ho * wo * cout * cin * k * k))
         ctx.save_for_backward(xb, *tens)
         ctx.meta = (spec, hyper, x_stride, (mc, batch, cin, cout, h, w), a.precision)
         return y
@@ -251,8 +258,11 @@ class _BayesConv2dFn(torch.autograd.Function):
         a.workspace, a.workspace_bytes = _cabi.ptr(ws), ws.numel()
         a.stream = _cabi.current_stream(dev)
         with torch.cuda.device(dev):
-            _timed(f"conv_bwd[{mc}x{batch}x{cin}x{h}x{w}->{cout}]",
-                   lambda: _cabi.check(lib.pl_conv2d_bwd(C.byref(a)), "pl_conv2d_bwd"))
+            ho = (h + 2 * padding - dilation * (k - 1) - 1) // stride + 1
+            wo = (w + 2 * padding - dilation * (k - 1) - 1) // stride + 1
+            _timed(f"conv_bwd[{mc}x{batch}x{cin}x{h}x{w}->{cout},k{k}]",
+                   lambda: _cabi.check(lib.pl_conv2d_bwd(C.byref(a)), "pl_conv2d_bwd"),
+                   ("flops", 2.0 * mc * batch * ho * wo * cout * cin * k * k * (2 if need_dx else 1)))
         return dx, dw_mu, dw_rho, db_mu, db_rho, None, None, None, None
 
 
@@ -276,7 +286,8 @@ class _KLFn(torch.autograd.Function):
             _timed(f"kl_fwd[{mu_c.numel()}]", lambda: _cabi.check(
                 lib.pl_kl_fwd(_cabi.ptr(mu_c), _cabi.ptr(rho_c), mu_c.numel(), float(prior_scale),
                               _cabi.ptr(pse), _cabi.ptr(out), _cabi.ptr(ws), ws.numel(),
-                              _cabi.current_stream(mu.device)), "pl_kl_fwd"))
+                              _cabi.current_stream(mu.device)), "pl_kl_fwd"),
+                   ("bytes", 8.0 * mu_c.numel()))
         ctx.save_for_backward(mu_c, rho_c, pse)
         ctx.prior_scale = float(prior_scale)
         return out[0], out[1]

@@ -67,8 +67,11 @@ class ELBOTrainStep:
         # fused KL gradient: layers compute kl_div without an autograd graph
         self.kl_layers = [m for m in net.modules()
                           if isinstance(m, (BayesLinear, BayesConv2d)) and isinstance(m, self.kl_kinds)]
-        for m in self.kl_layers:
-            m.kl_autograd = False
+        for m in net.modules():
+            # kl_div of layers outside kl_kinds (conv in the reference's experiments) never reaches
+            # the loss: no graph needed for them either
+            if isinstance(m, (BayesLinear, BayesConv2d)):
+                m.kl_autograd = False
         # per-layer slices of the flat buffer for the overlapped all-reduce
         self.overlap = overlap and self.world > 1
         self._handles = []
@@ -114,7 +117,8 @@ class ELBOTrainStep:
         PF._timed(f"kl_bwd_acc[{w.loc.numel()}]", lambda: _cabi.check(
             lib.pl_kl_bwd(w.loc.data_ptr(), w.logscale.data_ptr(), w.loc.numel(), float(prior),
                           None, None, None, self._inv, w.loc.grad.data_ptr(),
-                          w.logscale.grad.data_ptr(), 1, stream), "pl_kl_bwd"))
+                          w.logscale.grad.data_ptr(), 1, stream), "pl_kl_bwd"),
+                  ("bytes", 24.0 * w.loc.numel()))
 
     def _make_hook(self, state):
         def hook(_param):
