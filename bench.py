@@ -131,7 +131,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                       "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -258,12 +258,14 @@ def run_b200(args, wl):
         ys = y_host.to(dev, non_blocking=True)
         return trainer.step(xs, ys).cpu()        # D2H read of [LL, KL, ACC, loss] every step
 
+    # clocks are sampled from before the warm-up to the end of the timed region (steps are ~10 ms:
+    # nvidia-smi needs the warm-up to spin up)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         stats = step_resident()
     torch.cuda.synchronize()
 
     # ---- headline: device-resident inputs ----
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     l0 = lib.pl_launch_count()
     ms_total = timed(step_resident, args.steps)
     launches = (lib.pl_launch_count() - l0) // 1
@@ -386,7 +388,7 @@ def run_b200(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c4")
