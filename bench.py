@@ -360,7 +360,7 @@ def run_b200(args, wl):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "bf16": "bf16", "auto": "bf16"}[args.precision],
+        "dtype": {"fp32": "f32", "bf16": "bf16", "auto": "bf16", "tf32": "tf32", "auto_tf32": "tf32"}[args.precision],
         "data": "synthetic",
         "config": {"workload": wl["name"], "mc_total": mc_total, "mc_per_gpu": mc_local,
                    "batch": batch, "num_samples": ns, "precision": args.precision,
@@ -392,7 +392,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c4")
-    ap.add_argument("--precision", choices=["fp32", "bf16", "auto"], default="auto",
+    ap.add_argument("--precision", choices=["fp32", "tf32", "bf16", "auto", "auto_tf32"], default="auto",
                     help="auto = bf16 tcgen05 kernels wherever the layer shape tiles, fp32 kernels for tiny layers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

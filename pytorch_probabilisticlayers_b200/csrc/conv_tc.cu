@@ -262,11 +262,11 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     PL_CHECK_ARG((int64_t)g.mc * p.kb_splits <= 65535, "pl_conv2d_bwd: too many reduction splits");
     dim3 grid((unsigned)((g.K + 127) / 128), (unsigned)((g.cout + 127) / 128), (unsigned)(g.mc * p.kb_splits));
     if (a->eps_w) {
-      PL_CUDA(cudaFuncSetAttribute(dw_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes));
-      dw_tc<true><<<grid, kTcThreads, kDwSmemBytes, st>>>(tmx, tmdy, p);
+      PL_CUDA(cudaFuncSetAttribute(dw_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes));
+      dw_tc<true, false><<<grid, kTcThreads, kDwSmemBytes, st>>>(tmx, tmdy, p);
     } else {
-      PL_CUDA(cudaFuncSetAttribute(dw_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes));
-      dw_tc<false><<<grid, kTcThreads, kDwSmemBytes, st>>>(tmx, tmdy, p);
+      PL_CUDA(cudaFuncSetAttribute(dw_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes));
+      dw_tc<false, false><<<grid, kTcThreads, kDwSmemBytes, st>>>(tmx, tmdy, p);
     }
     PL_LAUNCH_CHECK("dw_tc");
   }

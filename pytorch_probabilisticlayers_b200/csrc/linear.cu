@@ -13,12 +13,12 @@ int linear_bwd_tc_launch(const pl_linear_args* a);
 
 extern "C" size_t pl_linear_workspace_bytes(const pl_linear_args* a) {
   if (!a) return 0;
-  if (a->precision == PL_PREC_BF16) return pl::linear_tc_workspace_bytes(a);
+  if (a->precision == PL_PREC_BF16 || a->precision == PL_PREC_TF32) return pl::linear_tc_workspace_bytes(a);
   return pl::linear_simt_workspace_bytes(a);
 }
 
 extern "C" size_t pl_linear_state_bytes(const pl_linear_args* a) {
-  if (!a || a->precision != PL_PREC_BF16) return 0;
+  if (!a || (a->precision != PL_PREC_BF16 && a->precision != PL_PREC_TF32)) return 0;
   return pl::linear_tc_state_bytes(a);
 }
 
@@ -26,7 +26,8 @@ extern "C" int pl_linear_fwd(const pl_linear_args* a) {
   PL_CHECK_ARG(a, "pl_linear_fwd: NULL args");
   switch (a->precision) {
     case PL_PREC_FP32: return pl::linear_fwd_simt_launch(a);
-    case PL_PREC_BF16: return pl::linear_fwd_tc_launch(a);
+    case PL_PREC_BF16:
+    case PL_PREC_TF32: return pl::linear_fwd_tc_launch(a);
     default:
       pl::set_error("pl_linear_fwd: precision %d not implemented", a->precision);
       return PL_ERR_UNSUPPORTED;
@@ -37,7 +38,8 @@ extern "C" int pl_linear_bwd(const pl_linear_args* a) {
   PL_CHECK_ARG(a, "pl_linear_bwd: NULL args");
   switch (a->precision) {
     case PL_PREC_FP32: return pl::linear_bwd_simt_launch(a);
-    case PL_PREC_BF16: return pl::linear_bwd_tc_launch(a);
+    case PL_PREC_BF16:
+    case PL_PREC_TF32: return pl::linear_bwd_tc_launch(a);
     default:
       pl::set_error("pl_linear_bwd: precision %d not implemented", a->precision);
       return PL_ERR_UNSUPPORTED;

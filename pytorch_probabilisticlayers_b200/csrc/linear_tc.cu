@@ -131,8 +131,11 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   const int64_t x_rows = a->x_mc_stride == 0 ? B : MC * B;
   softplus_kernel<<<ew_grid(I * O, 1024), 256, 0, st>>>(a->w_rho, state.sigma, I * O);
   PL_LAUNCH_CHECK("softplus_kernel");
-  cast_bf16_kernel<<<ew_grid(x_rows * I / 8, 1024), 256, 0, st>>>(a->x, state.x_bf16, x_rows * I / 8);
-  PL_LAUNCH_CHECK("cast_bf16_kernel");
+  const bool tf32 = a->precision == PL_PREC_TF32;   // fp32 operands straight from the caller's tensors
+  if (!tf32) {
+    cast_bf16_kernel<<<ew_grid(x_rows * I / 8, 1024), 256, 0, st>>>(a->x, state.x_bf16, x_rows * I / 8);
+    PL_LAUNCH_CHECK("cast_bf16_kernel");
+  }
   if (a->b_mu) {
     sample_bias_kernel<<<ew_grid(MC * ((O + 3) / 4), 256), 256, 0, st>>>(
         a->b_mu, a->b_rho, a->eps_b, make_sampler(a->seed, a->layer_id, true, a->mc_global_offset),
@@ -140,7 +143,8 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
     PL_LAUNCH_CHECK("sample_bias_kernel");
   }
   CUtensorMap tm;
-  rc = make_tmap_bf16(&tm, state.x_bf16, (uint64_t)x_rows, (uint64_t)I, 128, kBK);
+  rc = tf32 ? make_tmap_2d(&tm, a->x, (uint64_t)x_rows, (uint64_t)I, 128, 32, true)
+            : make_tmap_bf16(&tm, state.x_bf16, (uint64_t)x_rows, (uint64_t)I, 128, kBK);
   if (rc != PL_OK) return rc;
   TcGemmParams p;
   p.mc = (int)MC; p.rows = (int)B; p.ndim = (int)O; p.kdim = (int)I;
@@ -152,6 +156,7 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   p.out = a->y;
   p.out_hw = 0;
   p.w_aligned = 1;
+  if (tf32) return a->eps_w ? launch_gemm<false, true, true>(tm, p, st) : launch_gemm<false, false, true>(tm, p, st);
   return a->eps_w ? launch_gemm<false, true>(tm, p, st) : launch_gemm<false, false>(tm, p, st);
 }
 
@@ -159,7 +164,8 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
   PL_CHECK_ARG(a, "pl_linear_bwd: NULL args");
   if (a->mc == 0 || a->batch == 0) return linear_bwd_simt_launch(a);
   const bool have_state = a->fwd_state != nullptr;
-  PL_CHECK_ARG((a->x || have_state) && a->w_mu && a->w_rho && a->dy, "pl_linear_bwd: NULL pointer");
+  const bool tf32 = a->precision == PL_PREC_TF32;
+  PL_CHECK_ARG((a->x || (have_state && !tf32)) && a->w_mu && a->w_rho && a->dy, "pl_linear_bwd: NULL pointer");
   PL_CHECK_ARG((a->db_mu == nullptr) == (a->db_rho == nullptr), "pl_linear_bwd: db_mu/db_rho must both be set or NULL");
   PL_CHECK_ARG(!a->db_mu || a->b_rho, "pl_linear_bwd: bias gradients requested without a bias");
   int rc = tc_shape_ok(a, "pl_linear_bwd");
@@ -176,16 +182,16 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
       softplus_kernel<<<ew_grid(I * O, 1024), 256, 0, st>>>(a->w_rho, state.sigma, I * O);
       PL_LAUNCH_CHECK("softplus_kernel");
     }
-    if (a->dw_mu) {
+    if (a->dw_mu && !tf32) {
       cast_bf16_kernel<<<ew_grid(x_rows * I / 8, 1024), 256, 0, st>>>(a->x, state.x_bf16, x_rows * I / 8);
       PL_LAUNCH_CHECK("cast_bf16_kernel");
     }
   }
-  if (a->dx || a->dw_mu || a->db_mu) {
+  if ((!tf32 && (a->dx || a->dw_mu)) || a->db_mu) {
     // one pass over dY: bf16 operand copy + per-sample column sums for the bias gradients
     dim3 grid((unsigned)((O + 127) / 128), (unsigned)MC);
-    cast_dy_colsum_kernel<<<grid, 256, 0, st>>>(a->dy, w.dy_bf16, a->db_mu ? w.colsum : nullptr,
-                                                (int)B, (int)O);
+    cast_dy_colsum_kernel<<<grid, 256, 0, st>>>(a->dy, tf32 ? nullptr : w.dy_bf16,
+                                                a->db_mu ? w.colsum : nullptr, (int)B, (int)O);
     PL_LAUNCH_CHECK("cast_dy_colsum_kernel");
   }
   if (a->db_mu) {
@@ -196,7 +202,8 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
   }
   if (a->dx) {
     CUtensorMap tm;
-    rc = make_tmap_bf16(&tm, w.dy_bf16, (uint64_t)(MC * B), (uint64_t)O, 128, kBK);
+    rc = tf32 ? make_tmap_2d(&tm, a->dy, (uint64_t)(MC * B), (uint64_t)O, 128, 32, true)
+              : make_tmap_bf16(&tm, w.dy_bf16, (uint64_t)(MC * B), (uint64_t)O, 128, kBK);
     if (rc != PL_OK) return rc;
     TcGemmParams p;
     p.mc = (int)MC; p.rows = (int)B; p.ndim = (int)I; p.kdim = (int)O;
@@ -208,16 +215,23 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
     p.out = a->dx;
     p.out_hw = 0;
     p.w_aligned = 1;
-    rc = a->eps_w ? launch_gemm<true, true>(tm, p, st) : launch_gemm<true, false>(tm, p, st);
+    if (tf32) rc = a->eps_w ? launch_gemm<true, true, true>(tm, p, st) : launch_gemm<true, false, true>(tm, p, st);
+    else rc = a->eps_w ? launch_gemm<true, true>(tm, p, st) : launch_gemm<true, false>(tm, p, st);
     if (rc != PL_OK) return rc;
   }
   if (a->dw_mu) {
     PL_CHECK_ARG(a->dw_rho, "pl_linear_bwd: dw_mu/dw_rho must both be set or NULL");
     CUtensorMap tmx, tmdy;
-    rc = make_tmap_bf16_3d(&tmx, state.x_bf16, a->x_mc_stride == 0 ? 1 : (uint64_t)MC, (uint64_t)B,
-                           (uint64_t)I, kBK, 64);
-    if (rc != PL_OK) return rc;
-    rc = make_tmap_bf16_3d(&tmdy, w.dy_bf16, (uint64_t)MC, (uint64_t)B, (uint64_t)O, kBK, 64);
+    const uint64_t mcx = a->x_mc_stride == 0 ? 1 : (uint64_t)MC;
+    if (tf32) {
+      rc = make_tmap_3d(&tmx, a->x, mcx, (uint64_t)B, (uint64_t)I, 32, 32, true);
+      if (rc != PL_OK) return rc;
+      rc = make_tmap_3d(&tmdy, a->dy, (uint64_t)MC, (uint64_t)B, (uint64_t)O, 32, 32, true);
+    } else {
+      rc = make_tmap_bf16_3d(&tmx, state.x_bf16, mcx, (uint64_t)B, (uint64_t)I, kBK, 64);
+      if (rc != PL_OK) return rc;
+      rc = make_tmap_bf16_3d(&tmdy, w.dy_bf16, (uint64_t)MC, (uint64_t)B, (uint64_t)O, kBK, 64);
+    }
     if (rc != PL_OK) return rc;
     TcDwParams p;
     p.mc = (int)MC; p.batch = (int)B; p.w_in = (int)I; p.w_out = (int)O;
@@ -236,7 +250,7 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
     }
     p.mc_per_split = (int)((MC + splits - 1) / splits);
     p.kb_splits = 1;
-    p.kb_per_split = (int)((B + kBK - 1) / kBK);
+    p.kb_per_split = (int)((B + (tf32 ? 32 : kBK) - 1) / (tf32 ? 32 : kBK));
     splits = (int)((MC + p.mc_per_split - 1) / p.mc_per_split);
     p.atomic_out = splits > 1;
     if (p.atomic_out) {
@@ -244,13 +258,19 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
       PL_CUDA(cudaMemsetAsync(a->dw_rho, 0, sizeof(float) * I * O, st));
     }
     dim3 grid((unsigned)((O + 127) / 128), (unsigned)((I + 127) / 128), (unsigned)splits);
+#define PL_DW_LAUNCH(INJ, TF)                                                                          \
+  do {                                                                                                \
+    PL_CUDA(cudaFuncSetAttribute(dw_tc<INJ, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes)); \
+    dw_tc<INJ, TF><<<grid, kTcThreads, kDwSmemBytes, st>>>(tmx, tmdy, p);                             \
+  } while (0)
     if (a->eps_w) {
-      PL_CUDA(cudaFuncSetAttribute(dw_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes));
-      dw_tc<true><<<grid, kTcThreads, kDwSmemBytes, st>>>(tmx, tmdy, p);
+      if (tf32) PL_DW_LAUNCH(true, true);
+      else PL_DW_LAUNCH(true, false);
     } else {
-      PL_CUDA(cudaFuncSetAttribute(dw_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemBytes));
-      dw_tc<false><<<grid, kTcThreads, kDwSmemBytes, st>>>(tmx, tmdy, p);
+      if (tf32) PL_DW_LAUNCH(false, true);
+      else PL_DW_LAUNCH(false, false);
     }
+#undef PL_DW_LAUNCH
     PL_LAUNCH_CHECK("dw_tc");
   }
   return PL_OK;

@@ -101,6 +101,24 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "r"(z)
       : "memory");
 }
+// D[tmem] (+)= A[smem desc] * B[smem desc]; fp32 words read as tf32, fp32 accumulate
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z), "r"(z), "r"(z),
+      "r"(z)
+      : "memory");
+}
+template <bool kTf32>
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  if (kTf32) mma_tf32_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+  else mma_bf16_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
 // all previously issued MMAs of this thread -> one arrival on `bar` when they retire
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -219,12 +237,36 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo_
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major 32-bit (tf32) operands have exactly one legal swizzled layout: SWIZZLE_128B_BASE32B
+// (layout type 1): 128-byte rows, 32-byte chunks XOR-ed with (row % 4), 4-row groups `sbo` apart,
+// 32-element MN groups `lbo` apart.  TMA produces it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t smem_desc_sw128_base32(uint32_t addr, uint32_t lbo_bytes,
+                                                           uint32_t sbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (1ull << 61);
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, dense:
 // c_format F32 (1) [4,6); a_format BF16 (1) [7,10); b_format BF16 (1) [10,13); a_major [15];
 // b_major [16] (0 = K-major, 1 = MN-major); N>>3 [17,23); M>>4 [24,29).
 __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) |
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// kind::tf32: a/b format TF32 (2), otherwise as idesc_bf16
+__host__ __device__ constexpr uint32_t idesc_tf32(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+template <bool kTf32>
+__host__ __device__ constexpr uint32_t idesc_for(int m, int n, int a_mn, int b_mn) {
+  return kTf32 ? idesc_tf32(m, n, a_mn, b_mn) : idesc_bf16(m, n, a_mn, b_mn);
+}
+// fp32 -> tf32 (round to nearest, ties away) kept in a 32-bit word
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -96,9 +96,10 @@ static __global__ void __launch_bounds__(256) cast_dy_colsum_kernel(const float*
       const int64_t idx = base + (int64_t)b * out + col;
       const float4 v0 = *reinterpret_cast<const float4*>(dy + idx);
       const float4 v1 = *reinterpret_cast<const float4*>(dy + idx + 4);
-      *reinterpret_cast<uint4*>(dst + idx) =
-          make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y),
-                     pack_bf16x2(v1.z, v1.w));
+      if (dst)   // tf32 path: dY is consumed as fp32 by TMA, only the column sums are needed
+        *reinterpret_cast<uint4*>(dst + idx) =
+            make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y),
+                       pack_bf16x2(v1.z, v1.w));
       s[0] += v0.x; s[1] += v0.y; s[2] += v0.z; s[3] += v0.w;
       s[4] += v1.x; s[5] += v1.y; s[6] += v1.z; s[7] += v1.w;
     }
@@ -155,7 +156,7 @@ struct TcCfg {
   static constexpr int kTmemCols = MT * kBN;  // 128, 256 or 512: powers of two
 };
 
-template <int MT, bool kDx, bool kInjected>
+template <int MT, bool kDx, bool kInjected, bool kTf32>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p) {
   using Cfg = TcCfg<MT>;
@@ -180,7 +181,10 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
   const int n0 = blockIdx.x * kBN;
   const int m0 = blockIdx.y * (MT * 128);
   const int mc = blockIdx.z;
-  const int num_kb = (p.kdim + kBK - 1) / kBK;
+  // elements per 128-byte swizzle row = k-block: 64 (bf16) or 32 (tf32: fp32 words); one MMA
+  // consumes 32 bytes of K (16 bf16 / 8 tf32), so a k-block is always 4 MMA k-steps
+  constexpr int kBKe = kTf32 ? 32 : 64;
+  const int num_kb = (p.kdim + kBKe - 1) / kBKe;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStagesA; ++s) {
@@ -215,7 +219,7 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
         mbar_expect_tx(a_full(s), Cfg::kABytes);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
-          tma_load_2d(sA + s * Cfg::kABytes + mt * kSubTileBytes, &tmap_a, a_full(s), kb * kBK,
+          tma_load_2d(sA + s * Cfg::kABytes + mt * kSubTileBytes, &tmap_a, a_full(s), kb * kBKe,
                       row0 + mt * 128);
       }
     }
@@ -223,7 +227,7 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16(128, kBN, /*a MN-major*/ 0, /*b MN-major*/ kDx ? 0 : 1);
+      constexpr uint32_t idesc = idesc_for<kTf32>(128, kBN, /*a MN-major*/ 0, /*b MN-major*/ kDx ? 0 : 1);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int sa = kb % Cfg::kStagesA, pa = (kb / Cfg::kStagesA) & 1;
         const int sb = kb % Cfg::kStagesB, pb = (kb / Cfg::kStagesB) & 1;
@@ -233,16 +237,20 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
         const uint32_t a_addr = sA + sa * Cfg::kABytes;
         const uint32_t b_addr = sB + sb * kSubTileBytes;
 #pragma unroll
-        for (int ks = 0; ks < kBK / 16; ++ks) {
+        for (int ks = 0; ks < 4; ++ks) {
           // A: K-major SW128 (8-row groups 1024 B apart); advancing K by 16 bf16 = 32 B
           // B: forward MN-major SW128 (64-col groups 8192 B apart = LBO, 8-k groups 1024 B = SBO,
           //    16 k = 2 groups = 2048 B); dX K-major SW128 like A
-          const uint64_t b_desc = kDx ? smem_desc_sw128(b_addr + ks * 32, 16, 1024)
-                                      : smem_desc_sw128(b_addr + ks * 2048, 8192, 1024);
+          // (tf32 MN-major: SWIZZLE_128B_BASE32B, 32-col groups 4096 B apart, 4-k groups 512 B apart,
+          //  8 k = 1024 B per MMA)
+          const uint64_t b_desc =
+              kDx ? smem_desc_sw128(b_addr + ks * 32, 16, 1024)
+                  : (kTf32 ? smem_desc_sw128_base32(b_addr + ks * 1024, 4096, 512)
+                           : smem_desc_sw128(b_addr + ks * 2048, 8192, 1024));
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             const uint64_t a_desc = smem_desc_sw128(a_addr + mt * kSubTileBytes + ks * 32, 16, 1024);
-            mma_bf16_ss(tmem_base + mt * kBN, a_desc, b_desc, idesc, (kb | ks) != 0);
+            mma_ss<kTf32>(tmem_base + mt * kBN, a_desc, b_desc, idesc, (kb | ks) != 0);
           }
         }
         mma_commit(a_empty(sa));   // frees the activation stage when these MMAs retire
@@ -256,36 +264,44 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
     // operand element (n, k): forward W[i = k0+k][o = n0+n]; dX W[i = n0+n][o = k0+k].
     // Each thread owns 4 groups of 4 consecutive o per k-block (one Philox call per group).
     const int gw = warp - 2;  // 0..15
-    int wrow[4], wcol;        // weight coordinates of the thread's groups at k-block 0
-    uint32_t soff[4];
+    // groups (4 consecutive o) per thread and k-block: 4 (bf16, 64-k blocks) or 2 (tf32, 32-k blocks)
+    constexpr int kGr = kTf32 ? 2 : 4;
+    int wrow[kGr], wcol;      // weight coordinates of the thread's groups at k-block 0
+    uint32_t soff[kGr];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < kGr; ++r) {
       if (!kDx) {
-        // k = gw + 16 r, n = 4 lane.  MN-major SW128:
-        // [n/64]*8192 + [k/8]*1024 + (k%8)*128 + (((n%64)/8) ^ (k%8))*16 + (n%8)*2
+        // k = gw + 16 r, n = 4 lane.  MN-major SW128 (bf16: 64-col groups, tf32: 32-col groups):
+        // [n/G]*LBO + [k/8]*1024 + (k%8)*128 + ((16-byte chunk of n in its group) ^ (k%8))*16 + ...
         wrow[r] = gw + 16 * r;
-        soff[r] = (uint32_t)((lane >> 4) * 8192 + ((gw >> 3) + 2 * r) * 1024 + (gw & 7) * 128 +
-                             ((((lane & 15) >> 1) ^ (gw & 7)) << 4) + ((lane & 1) << 3));
+        if (kTf32)   // [n/32]*4096 + [k/4]*512 + (k%4)*128 + (((n%32)/8) ^ (k%4))*32 + (n%8)*4
+          soff[r] = (uint32_t)((lane >> 3) * 4096 + ((gw >> 2) + 4 * r) * 512 + (gw & 3) * 128 +
+                               ((((lane & 7) >> 1) ^ (gw & 3)) << 5) + ((lane & 1) << 4));
+        else
+          soff[r] = (uint32_t)((lane >> 4) * 8192 + ((gw >> 3) + 2 * r) * 1024 + (gw & 7) * 128 +
+                               ((((lane & 15) >> 1) ^ (gw & 7)) << 4) + ((lane & 1) << 3));
       } else {
-        // n = 8 gw + 2 r + lane/16, k = 4 (lane%16).  K-major SW128: n*128 + (((k/8) ^ (n%8))*16) + (k%8)*2
-        const int n = 8 * gw + 2 * r + (lane >> 4);
+        // K-major SW128: n*128 + ((16-byte chunk of k) ^ (n%8))*16 + ...
+        // bf16: n = 8 gw + 2 r + lane/16, k = 4 (lane%16);  tf32: n = 8 gw + 4 r + lane/8, k = 4 (lane%8)
+        const int n = kTf32 ? 8 * gw + 4 * r + (lane >> 3) : 8 * gw + 2 * r + (lane >> 4);
         wrow[r] = n0 + n;
-        soff[r] = (uint32_t)(n * 128 + ((((lane & 15) >> 1) ^ (n & 7)) << 4) + ((lane & 1) << 3));
+        if (kTf32) soff[r] = (uint32_t)(n * 128 + (((lane & 7) ^ (n & 7)) << 4));
+        else soff[r] = (uint32_t)(n * 128 + ((((lane & 15) >> 1) ^ (n & 7)) << 4) + ((lane & 1) << 3));
       }
     }
-    wcol = kDx ? 4 * (lane & 15) : n0 + 4 * lane;
+    wcol = kDx ? 4 * (kTf32 ? (lane & 7) : (lane & 15)) : n0 + 4 * lane;
     const int64_t ldw = p.w_out;
     const float* eps_base = kInjected ? p.eps_w + (int64_t)mc * p.w_in * p.w_out : nullptr;
 
     auto gen_block = [&](int kb, auto full_tag) {
       constexpr bool kFull = decltype(full_tag)::value;
       const int s = kb % Cfg::kStagesB, ph = (kb / Cfg::kStagesB) & 1;
-      const int k0 = kb * kBK;
-      float4 mu[4], sg[4], ep[4];
-      int row[4];
+      const int k0 = kb * kBKe;
+      float4 mu[kGr], sg[kGr], ep[kGr];
+      int row[kGr];
       const int col = kDx ? k0 + wcol : wcol;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < kGr; ++r) {
         row[r] = kDx ? wrow[r] : k0 + wrow[r];
         const bool ok = kFull || (row[r] < p.w_in && col < p.w_out);
         const int64_t idx = (int64_t)row[r] * ldw + col;
@@ -311,13 +327,20 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
       mbar_wait(b_empty(s), ph ^ 1);
       const uint32_t dst = sB + s * kSubTileBytes;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < kGr; ++r) {
         float4 e;
         if (kInjected) e = ep[r];
         else e = eps4(p.sw, mc, row[r], col >> 2);
-        const uint32_t lo = pack_bf16x2(fmaf(sg[r].x, e.x, mu[r].x), fmaf(sg[r].y, e.y, mu[r].y));
-        const uint32_t hi = pack_bf16x2(fmaf(sg[r].z, e.z, mu[r].z), fmaf(sg[r].w, e.w, mu[r].w));
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + soff[r]), "r"(lo), "r"(hi) : "memory");
+        const float w0 = fmaf(sg[r].x, e.x, mu[r].x), w1 = fmaf(sg[r].y, e.y, mu[r].y),
+                    w2 = fmaf(sg[r].z, e.z, mu[r].z), w3 = fmaf(sg[r].w, e.w, mu[r].w);
+        if (kTf32) {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + soff[r]), "r"(to_tf32(w0)),
+                       "r"(to_tf32(w1)), "r"(to_tf32(w2)), "r"(to_tf32(w3))
+                       : "memory");
+        } else {
+          const uint32_t lo = pack_bf16x2(w0, w1), hi = pack_bf16x2(w2, w3);
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + soff[r]), "r"(lo), "r"(hi) : "memory");
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -327,7 +350,7 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
     const bool n_full = p.w_aligned && (kDx ? (n0 + kBN <= p.w_in) : (n0 + kBN <= p.w_out));
     const int k_extent = kDx ? p.w_out : p.w_in;
     for (int kb = 0; kb < num_kb; ++kb) {
-      if (n_full && (kb + 1) * kBK <= k_extent) gen_block(kb, std::true_type{});
+      if (n_full && (kb + 1) * kBKe <= k_extent) gen_block(kb, std::true_type{});
       else gen_block(kb, std::false_type{});
     }
     // ===================== epilogue: TMEM -> registers -> HBM =====================
@@ -635,7 +658,7 @@ struct TcDwParams {
   float* dw_rho;
 };
 
-template <bool kInjected>
+template <bool kInjected, bool kTf32>
 __global__ void __launch_bounds__(kTcThreads, 1)
 dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
       const TcDwParams p) {
@@ -656,7 +679,8 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
   const int mc_begin = ((int)blockIdx.z / p.kb_splits) * p.mc_per_split;
   const int mc_end = min(p.mc, mc_begin + p.mc_per_split);
   const int kb_begin = ((int)blockIdx.z % p.kb_splits) * p.kb_per_split;
-  const int kb_end = min((p.batch + kBK - 1) / kBK, kb_begin + p.kb_per_split);
+  constexpr int kBKe = kTf32 ? 32 : 64;   // reduction rows per stage (one 16 KB sub-tile per operand)
+  const int kb_end = min((p.batch + kBKe - 1) / kBKe, kb_begin + p.kb_per_split);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kDwStages; ++s) {
@@ -688,12 +712,15 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
           mbar_wait(empty(s), ph ^ 1);
           mbar_expect_tx(full(s), kDwStageBytes);
           const uint32_t dst = sStage + s * kDwStageBytes;
-          // MN-major operand sub-tiles: [64 batch rows] x [64 features = 128 B], two per operand
-          tma_load_3d(dst, &tmap_x, full(s), i0, kb * kBK, xm);
-          tma_load_3d(dst + 8192, &tmap_x, full(s), i0 + 64, kb * kBK, xm);
+          // MN-major operand sub-tiles of [kBKe batch rows] x [128 B of features]: two 64-feature
+          // boxes (bf16) or four 32-feature boxes (tf32) per operand
           const int ym = p.dy_broadcast ? 0 : mc;
-          tma_load_3d(dst + kSubTileBytes, &tmap_dy, full(s), o0, kb * kBK, ym);
-          tma_load_3d(dst + kSubTileBytes + 8192, &tmap_dy, full(s), o0 + 64, kb * kBK, ym);
+          constexpr int kBoxes = kTf32 ? 4 : 2, kFeat = kTf32 ? 32 : 64, kBoxBytes = kSubTileBytes / kBoxes;
+#pragma unroll
+          for (int g = 0; g < kBoxes; ++g) {
+            tma_load_3d(dst + g * kBoxBytes, &tmap_x, full(s), i0 + g * kFeat, kb * kBKe, xm);
+            tma_load_3d(dst + kSubTileBytes + g * kBoxBytes, &tmap_dy, full(s), o0 + g * kFeat, kb * kBKe, ym);
+          }
         }
       }
     }
@@ -701,7 +728,7 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16(128, 128, 1, 1);
+      constexpr uint32_t idesc = idesc_for<kTf32>(128, 128, 1, 1);
       int it = 0;
       for (int mc = mc_begin, n = 0; mc < mc_end; ++mc, ++n) {
         const int buf = n & 1;
@@ -713,11 +740,15 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
           tc_fence_after_sync();
           const uint32_t a_addr = sStage + s * kDwStageBytes, b_addr = a_addr + kSubTileBytes;
 #pragma unroll
-          for (int ks = 0; ks < kBK / 16; ++ks) {
+          for (int ks = 0; ks < 4; ++ks) {
             // 16 batch rows = two 8-row swizzle groups = 2048 B; 64-feature groups 8192 B apart
-            const uint64_t a_desc = smem_desc_sw128(a_addr + ks * 2048, 8192, 1024);
-            const uint64_t b_desc = smem_desc_sw128(b_addr + ks * 2048, 8192, 1024);
-            mma_bf16_ss(tmem_base + buf * 128, a_desc, b_desc, idesc, (kb > kb_begin) || ks != 0);
+            // (tf32: 8 batch rows = one group = 1024 B per MMA; 32-feature groups 4096 B apart)
+            constexpr uint32_t kStep = kTf32 ? 1024 : 2048;
+            const uint64_t a_desc = kTf32 ? smem_desc_sw128_base32(a_addr + ks * kStep, 4096, 512)
+                                          : smem_desc_sw128(a_addr + ks * kStep, 8192, 1024);
+            const uint64_t b_desc = kTf32 ? smem_desc_sw128_base32(b_addr + ks * kStep, 4096, 512)
+                                          : smem_desc_sw128(b_addr + ks * kStep, 8192, 1024);
+            mma_ss<kTf32>(tmem_base + buf * 128, a_desc, b_desc, idesc, (kb > kb_begin) || ks != 0);
           }
           mma_commit(empty(s));
         }
@@ -841,18 +872,26 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 row-major tensor [rows, cols], box [box_rows, 64 cols], SWIZZLE_128B
+static int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                        uint32_t box_cols, bool f32);
 static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols,
                           uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_2d(m, base, rows, cols, box_rows, box_cols, false);
+}
+// 2-D row-major tensor [rows, cols] of bf16 or fp32, box [box_rows, box_cols] (box_cols * esize = 128 B)
+static int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                        uint32_t box_cols, bool f32) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return PL_ERR_CUDA;
   }
   const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint64_t strides[1] = {cols * (f32 ? 4 : 2)};
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -865,19 +904,29 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 
 // 3-D bf16 tensor [mc, rows, cols] (cols innermost), box [1, box_rows, box_cols]: out-of-range rows
 // of one MC sample are zero-filled instead of running into the next sample
+static int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t mc, uint64_t rows, uint64_t cols,
+                        uint32_t box_rows, uint32_t box_cols, bool f32);
 static int make_tmap_bf16_3d(CUtensorMap* m, const void* base, uint64_t mc, uint64_t rows, uint64_t cols,
                              uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_3d(m, base, mc, rows, cols, box_rows, box_cols, false);
+}
+static int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t mc, uint64_t rows, uint64_t cols,
+                        uint32_t box_rows, uint32_t box_cols, bool f32) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return PL_ERR_CUDA;
   }
+  const uint64_t es = f32 ? 4 : 2;
   const cuuint64_t dims[3] = {cols, rows, mc};
-  const cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
+  const cuuint64_t strides[2] = {cols * es, rows * cols * es};
   const cuuint32_t box[3] = {box_cols, box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  // fp32 here means an MN-major tf32 MMA operand: the 32-byte-atom flavour of the 128-byte swizzle
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                  const_cast<void*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  f32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
@@ -899,13 +948,13 @@ static inline int ew_grid(int64_t n, int per_block) {
 // Kept (parity-tested) for when the sampler gets cheaper.
 static int g_force_1cta = -1;
 
-template <bool kDx, bool kInj>
+template <bool kDx, bool kInj, bool kTf32 = false>
 static int launch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_t st) {
   if (g_force_1cta < 0) {
     const char* e = getenv("PL_TC_2CTA");
     g_force_1cta = (e && e[0] == '1') ? 0 : 1;
   }
-  if (!g_force_1cta && p.rows > 128 && p.ndim > 128) {
+  if (!kTf32 && !g_force_1cta && p.rows > 128 && p.ndim > 128) {
     const int pair_rows = p.rows > 256 ? 512 : 256;
     dim3 grid(2u * (unsigned)((p.ndim + 255) / 256), (unsigned)((p.rows + pair_rows - 1) / pair_rows),
               (unsigned)p.mc);
@@ -926,7 +975,7 @@ static int launch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_
             (unsigned)p.mc);
 #define PL_LAUNCH_MT(MT)                                                                            \
   do {                                                                                              \
-    auto kern = sampled_gemm_tc<MT, kDx, kInj>;                                                     \
+    auto kern = sampled_gemm_tc<MT, kDx, kInj, kTf32>;                                              \
     PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
                                  TcCfg<MT>::kSmemBytes));                                           \
     kern<<<grid, kTcThreads, TcCfg<MT>::kSmemBytes, st>>>(tm, p);                                    \

@@ -126,7 +126,8 @@ class _BayesLinearFn(torch.autograd.Function):
             _timed(f"linear_fwd[{mc}x{batch}x{fin}x{fout}]",
                    lambda: _cabi.check(lib.pl_linear_fwd(C.byref(a)), "pl_linear_fwd"),
                    ("flops", 2.0 * mc * batch * fin * fout))
-        ctx.save_for_backward(None if state is not None else xb, w_mu_c, w_rho_c, b_mu_c, b_rho_c,
+        keep_x = state is None or spec.precision != _cabi.PREC_BF16   # bf16: the state holds x as bf16
+        ctx.save_for_backward(xb if keep_x else None, w_mu_c, w_rho_c, b_mu_c, b_rho_c,
                               eps_w_c, eps_b_c, state)
         ctx.meta = (spec, param_mode, x_stride, mc, batch, fin, fout, tuple(x.shape))
         return y

@@ -46,8 +46,8 @@ def manual_seed(seed: int):
 
 
 def set_precision(precision: str):
-    if precision not in ("fp32", "bf16", "auto"):
-        raise ValueError(f"precision must be 'fp32', 'bf16' or 'auto', got {precision!r}")
+    if precision not in ("fp32", "tf32", "bf16", "auto", "auto_tf32"):
+        raise ValueError(f"precision must be 'fp32', 'tf32', 'bf16', 'auto' or 'auto_tf32', got {precision!r}")
     _STATE["precision"] = precision
 
 
@@ -186,6 +186,8 @@ class _FusedBayesLayer(torch.nn.Module):
         p = self.precision or _STATE["precision"]
         if p == "auto":
             p = "bf16" if shape_ok_for_tc else "fp32"
+        elif p == "auto_tf32":
+            p = "tf32" if shape_ok_for_tc else "fp32"
         return _cabi.PRECISIONS[p]
 
     def _draw(self, mc, device, tc_ok):

@@ -10,6 +10,7 @@ from oracle import closed_form as cf
 pytestmark = pytest.mark.gpu
 
 BF16_TOL = 2e-2
+TF32_TOL = 2e-3      # north_star: rel 2e-3 at TF32 / fp32 accumulate
 
 
 @pytest.fixture(scope="module")
@@ -201,3 +202,66 @@ def test_tc_conv_philox_matches_fp64_oracle(plb, mc, b, cin, cout, hw, k, s, p, 
     assert rel_err(n(layer.weight.logscale.grad), bw["dw_rho"]) < BF16_TOL
     assert rel_err(n(layer.bias.loc.grad), bw["db_mu"]) < 1e-4
     assert rel_err(n(layer.bias.logscale.grad), bw["db_rho"]) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# TF32 tensor-core mode (kind::tf32, fp32 operands straight from the caller's tensors)
+# ---------------------------------------------------------------------------------------------
+def test_tf32_injected_eps_matches_reference_golden(plb):
+    g = load_golden("linear_tile")
+    layer = plb.BayesLinear(128, 128, prior=float(g["prior"])).cuda()
+    layer.precision = "tf32"
+    with torch.no_grad():
+        layer.weight.loc.copy_(dev(g["w_mu"]))
+        layer.weight.logscale.copy_(dev(g["w_rho"]))
+        layer.bias.loc.copy_(dev(g["b_mu"]))
+        layer.bias.logscale.copy_(dev(g["b_rho"]))
+    layer.inject_eps(dev(g["eps_w"]), dev(g["eps_b"]))
+    x = dev(g["x"]).requires_grad_(True)
+    out = layer(x)
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < TF32_TOL
+    (out * dev(g["gy"])).sum().backward()
+    assert rel_err(x.grad.cpu().numpy(), g["dx"]) < TF32_TOL
+    assert rel_err(layer.weight.loc.grad.cpu().numpy(), g["dw_mu"]) < TF32_TOL
+    assert rel_err(layer.weight.logscale.grad.cpu().numpy(), g["dw_rho"]) < TF32_TOL
+    assert rel_err(layer.bias.loc.grad.cpu().numpy(), g["db_mu"]) < 1e-4
+    assert rel_err(layer.bias.logscale.grad.cpu().numpy(), g["db_rho"]) < 1e-4
+
+
+@pytest.mark.parametrize("mc,b,i,o,bias,expand", [
+    (2, 128, 128, 128, True, False),
+    (1, 128, 32, 128, False, False),      # single k-block
+    (3, 512, 256, 384, True, False),      # MT=4
+    (2, 200, 192, 200, True, False),      # ragged rows / N tile
+    (2, 300, 200, 136, True, False),      # K tail (200 % 32 = 8), batch tail (300 % 32 = 12)
+    (4, 512, 512, 256, True, True),       # MC-broadcast input
+])
+def test_tf32_philox_matches_fp64_oracle(plb, mc, b, i, o, bias, expand):
+    torch.manual_seed(mc * 100 + b)
+    plb.manual_seed(31337 + o)
+    layer = plb.BayesLinear(i, o, bias=bias).cuda()
+    layer.precision = "tf32"
+    with torch.no_grad():
+        layer.weight.logscale.uniform_(-5, -1)
+        if bias:
+            layer.bias.logscale.uniform_(-3, 0)
+    if expand:
+        x = torch.randn(b, i, device="cuda").unsqueeze(0).expand(mc, b, i)
+    else:
+        x = torch.randn(mc, b, i, device="cuda", requires_grad=True)
+    gy = torch.randn(mc, b, o, device="cuda")
+    out = layer(x)
+    (out * gy).sum().backward()
+    n = lambda t: t.detach().cpu().numpy()
+    eps_w = n(layer.weight.eps)
+    eps_b = n(layer.bias.eps) if bias else None
+    want = cf.linear_fwd(n(x), n(layer.weight.loc), n(layer.weight.logscale), eps_w,
+                         n(layer.bias.loc) if bias else None,
+                         n(layer.bias.logscale) if bias else None, eps_b)
+    assert rel_err(n(out), want) < TF32_TOL
+    bw = cf.linear_bwd(n(gy), n(x), n(layer.weight.loc), n(layer.weight.logscale), eps_w,
+                       n(layer.bias.logscale) if bias else None, eps_b)
+    if not expand:
+        assert rel_err(n(x.grad), bw["dx"]) < TF32_TOL
+    assert rel_err(n(layer.weight.loc.grad), bw["dw_mu"]) < TF32_TOL
+    assert rel_err(n(layer.weight.logscale.grad), bw["dw_rho"]) < TF32_TOL
