@@ -88,6 +88,17 @@ int pl_kl_bwd(const float* mu, const float* rho, int64_t n, float prior_scale,
               const float* prior_scale_elem, const float* grad_kl, const float* grad_ent,
               float host_scale, float* dmu, float* drho, int32_t accumulate, void* stream);
 
+/* ---- fused optimiser pass (replaces torch.optim.Adam.step, experiments/BNN.py:349, plus the KL
+ *      backward): Adam update of one parameter tensor with the analytic KL gradient added on the fly.
+ * kind 0: plain Adam; 1: p is a posterior mean (grad += kl_scale * p/sp^2); 2: p is a posterior rho
+ * (grad += kl_scale * (s/sp^2 - 1/s) sigmoid(p)).  kl_value (optional device double) += this tensor's
+ * part of the KL VALUE from the pre-update parameters: kind 1: sum 0.5 p^2/sp^2, kind 2:
+ * sum 0.5 s^2/sp^2 - log s; the caller adds n*(log sp - 0.5) per (mean, rho) pair.  step >= 1 is the
+ * 1-based Adam step count.  Arithmetic identical to torch.optim.Adam (no amsgrad / weight decay). */
+int pl_adam_kl_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t kind,
+                    float prior_scale, float kl_scale, float lr, float beta1, float beta2, float eps,
+                    int32_t step, double* kl_value, void* stream);
+
 /* ---- BayesLinear / SIVILayer contraction (replaces VariationalNormal.rsample + torch.baddbmm /
  *      torch.bmm at src/ProbabilisticLayers.py:925-935 and :321-326, and their autograd) ------ */
 typedef struct pl_linear_args {

@@ -22,7 +22,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32}
 
 EXPORTS = (
     "pl_version", "pl_last_error", "pl_launch_count", "pl_device_supported", "pl_eps_dump",
-    "pl_kl_workspace_bytes", "pl_kl_fwd", "pl_kl_bwd",
+    "pl_kl_workspace_bytes", "pl_kl_fwd", "pl_kl_bwd", "pl_adam_kl_step",
     "pl_linear_workspace_bytes", "pl_linear_state_bytes", "pl_linear_fwd", "pl_linear_bwd",
     "pl_conv2d_workspace_bytes", "pl_conv2d_fwd", "pl_conv2d_bwd",
 )
@@ -89,6 +89,10 @@ def lib():
                 l.pl_kl_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                         C.c_int32, C.c_void_p]
+                l.pl_adam_kl_step.restype = C.c_int
+                l.pl_adam_kl_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                              C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
+                                              C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p]
                 l.pl_linear_workspace_bytes.restype = C.c_size_t
                 l.pl_linear_workspace_bytes.argtypes = [C.POINTER(LinearArgs)]
                 l.pl_linear_state_bytes.restype = C.c_size_t

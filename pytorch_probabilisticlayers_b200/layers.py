@@ -176,6 +176,9 @@ class _FusedBayesLayer(torch.nn.Module):
         # False: kl_div is computed without an autograd graph; the caller (train.ELBOTrainStep)
         # streams the analytic KL gradient into .grad with pl_kl_bwd(accumulate=1)
         self.kl_autograd = True
+        # True: forward does not compute kl_div at all (train.ELBOTrainStep's fused optimiser pass
+        # produces both the KL gradient and the KL value); kl_div reads as a zero scalar
+        self.kl_skip = False
 
     def inject_eps(self, eps_w, eps_b=None):
         """Use these eps tensors ([MC,*weight.shape], [MC,*bias.shape]) for the next forward(s);
@@ -312,6 +315,8 @@ class BayesLinear(_FusedBayesLayer):
             pse = self.prior.prior_scale().to(x.device)
             self.kl_div, self.entropy = PF.kl_and_entropy(self.weight.loc, self.weight.logscale,
                                                           1.0, pse)
+        elif self.kl_skip:
+            self.kl_div = self.entropy = torch.zeros((), device=x.device)
         elif self.kl_autograd:
             self.kl_div, self.entropy = PF.kl_and_entropy(self.weight.loc, self.weight.logscale,
                                                           self.prior.scale)
@@ -379,7 +384,9 @@ class BayesConv2d(_FusedBayesLayer):
                               self.bias.logscale, self.kernel_size, self.stride, self.padding,
                               self.dilation, eps_w, eps_b, spec)
         self._remember(mc, eps_w, eps_b, spec)
-        if self.kl_autograd:
+        if self.kl_skip:
+            self.kl_div = torch.zeros((), device=x.device)
+        elif self.kl_autograd:
             self.kl_div, _ = PF.kl_and_entropy(self.weight.loc, self.weight.logscale, self.prior_scale)
         else:
             with torch.no_grad():

@@ -19,6 +19,7 @@ exposed (SURVEY.md hard part H3).
 """
 from __future__ import annotations
 
+import math
 from typing import Iterable, Optional
 
 import torch
@@ -44,7 +45,8 @@ class ELBOTrainStep:
     def __init__(self, net: torch.nn.Module, criterion, num_samples: int, lr: float = 1e-3,
                  kl_kinds: Iterable = (BayesLinear, SIVILayer), with_accuracy: bool = True,
                  group: Optional[dist.ProcessGroup] = None, mc_coupled_loss: bool = False,
-                 overlap: bool = True):
+                 overlap: bool = True, fused_optimizer: bool = True,
+                 betas=(0.9, 0.999), eps: float = 1e-8):
         self.net, self.criterion, self.num_samples = net, criterion, int(num_samples)
         self.kl_kinds = tuple(kl_kinds)
         self.with_accuracy = with_accuracy
@@ -63,7 +65,12 @@ class ELBOTrainStep:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.stats = self.flat[n:n + 4]
-        self.opt = torch.optim.Adam(self.params, lr, fused=dev.type == "cuda")
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        # fused optimiser pass (CUDA): Adam + analytic KL gradient + KL value in one kernel per
+        # tensor (pl_adam_kl_step); replaces torch.optim.Adam and the KL forward/backward kernels
+        self.fused_opt = fused_optimizer and dev.type == "cuda"
+        self.opt = None if self.fused_opt else torch.optim.Adam(self.params, lr, betas=betas, eps=eps,
+                                                                fused=dev.type == "cuda")
         # fused KL gradient: layers compute kl_div without an autograd graph
         self.kl_layers = [m for m in net.modules()
                           if isinstance(m, (BayesLinear, BayesConv2d)) and isinstance(m, self.kl_kinds)]
@@ -72,6 +79,30 @@ class ELBOTrainStep:
             # the loss: no graph needed for them either
             if isinstance(m, (BayesLinear, BayesConv2d)):
                 m.kl_autograd = False
+                if m not in self.kl_layers:
+                    m.kl_skip = True
+        if self.fused_opt:
+            self.adam_m = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.adam_v = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.adam_t = 0
+            self.kl_acc = torch.zeros(1, dtype=torch.float64, device=dev)
+            kinds = {}
+            self.kl_const = 0.0
+            for m in self.kl_layers:
+                gaussian = not (isinstance(m, BayesLinear) and isinstance(m.prior, layers.LaplacePrior))
+                if not gaussian:
+                    continue                      # per-element prior: stays on the autograd path
+                prior = float(m.prior.scale if isinstance(m, BayesLinear) else m.prior_scale)
+                kinds[id(m.weight.loc)] = (1, prior)
+                kinds[id(m.weight.logscale)] = (2, prior)
+                self.kl_const += m.weight.loc.numel() * (math.log(prior) - 0.5)
+                m.kl_skip = True
+            self._adam_plan = []
+            off = 0
+            for p in self.params:
+                kind, prior = kinds.get(id(p), (0, 1.0))
+                self._adam_plan.append((p, off, p.numel(), kind, prior))
+                off += p.numel()
         # per-layer slices of the flat buffer for the overlapped all-reduce
         self.overlap = overlap and self.world > 1
         self._handles = []
@@ -108,7 +139,7 @@ class ELBOTrainStep:
 
     def _kl_backward(self, m):
         """Stream the analytic KL gradient of layer m (scaled 1/(N*num_samples)) into its .grad."""
-        if m.kl_div.requires_grad:               # e.g. Laplace prior: went through autograd
+        if self.fused_opt or m.kl_div.requires_grad:   # fused optimiser pass / autograd handles it
             return
         lib = _cabi.lib()
         w = m.weight
@@ -172,7 +203,30 @@ class ELBOTrainStep:
             for h in self._handles:
                 h.wait()
             self._handles.clear()
-        self.opt.step()
+        if self.fused_opt:
+            self._fused_step()
+        else:
+            self.opt.step()
         out = self.stats.clone()
         out[3] = out[0] + out[1]
         return out
+
+    def _fused_step(self):
+        """Adam + KL gradient + KL value, one streaming kernel per parameter tensor."""
+        lib = _cabi.lib()
+        self.adam_t += 1
+        self.kl_acc.zero_()
+        dev = self.flat.device
+        stream = _cabi.current_stream(dev)
+        kl_scale = 1.0 / self.num_samples       # gradients are already summed over ranks
+        with torch.cuda.device(dev):
+            for p, off, n, kind, prior in self._adam_plan:
+                PF._timed(f"adam_kl[{n}]", lambda: _cabi.check(
+                    lib.pl_adam_kl_step(p.data_ptr(), self.flat[off:off + n].data_ptr(),
+                                        self.adam_m[off:off + n].data_ptr(),
+                                        self.adam_v[off:off + n].data_ptr(), n, kind, prior, kl_scale,
+                                        self.lr, self.betas[0], self.betas[1], self.eps, self.adam_t,
+                                        self.kl_acc.data_ptr(), stream), "pl_adam_kl_step"),
+                          ("bytes", 28.0 * n))
+        # KL value of the pre-update parameters (replica-identical: not part of the all-reduce)
+        self.stats[1] += ((self.kl_acc[0] + self.kl_const) / self.num_samples).float()

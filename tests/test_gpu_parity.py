@@ -411,3 +411,40 @@ def test_error_behaviour(plb):
     # empty batch / empty MC shard do not crash
     out = layer(torch.zeros(3, 0, 4, device="cuda"))
     assert out.shape == (3, 0, 3)
+
+
+# ---------------------------------------------------------------------------------------------
+# the product's train step (ELBOTrainStep: fused Adam + KL pass) against the reference trajectory
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fused", [True, False])
+def test_elbo_train_step_matches_reference_trajectory(plb, fused):
+    from pytorch_probabilisticlayers_b200.train import ELBOTrainStep
+    g = load_golden("train_mlp_ce")
+    dims = [int(d) for d in g["dims"]]
+    mc, ns, steps = int(g["mc"]), int(g["num_samples"]), int(g["steps"])
+    mods = [plb.MC_ExpansionLayer(num_MC=mc, input_dim=2)]
+    for li in range(len(dims) - 1):
+        mods.append(plb.BayesLinear(dims[li], dims[li + 1]))
+        if li + 2 < len(dims):
+            mods.append(torch.nn.LeakyReLU())
+    net = torch.nn.Sequential(*mods).cuda()
+    layers = [m for m in net if isinstance(m, plb.BayesLinear)]
+    with torch.no_grad():
+        for li, l in enumerate(layers):
+            l.weight.loc.copy_(dev(g[f"init_w_mu{li}"]))
+            l.weight.logscale.copy_(dev(g[f"init_w_rho{li}"]))
+            l.bias.loc.copy_(dev(g[f"init_b_mu{li}"]))
+            l.bias.logscale.copy_(dev(g[f"init_b_rho{li}"]))
+    tr = ELBOTrainStep(net, plb.MC_CrossEntropyLoss(ns), ns, lr=float(g["lr"]), fused_optimizer=fused)
+    x, y = dev(g["x"]), dev(g["y"])
+    for s in range(steps):
+        for li, l in enumerate(layers):
+            l.inject_eps(dev(g[f"s{s}_eps_w{li}"]), dev(g[f"s{s}_eps_b{li}"]))
+        ll, kl, acc, loss = tr.step(x, y).tolist()
+        assert abs(ll - float(g[f"s{s}_LL"])) / abs(float(g[f"s{s}_LL"])) < 2e-4, s
+        assert abs(kl - g[f"s{s}_KL"].item()) / abs(g[f"s{s}_KL"].item()) < 1e-5, s
+        assert abs(loss - float(g[f"s{s}_loss"])) / abs(float(g[f"s{s}_loss"])) < 2e-4, s
+    for li, l in enumerate(layers):
+        assert rel_err(l.weight.loc.detach().cpu().numpy(), g[f"final_w_mu{li}"]) < 1e-3
+        assert rel_err(l.weight.logscale.detach().cpu().numpy(), g[f"final_w_rho{li}"]) < 1e-3
+        assert rel_err(l.bias.logscale.detach().cpu().numpy(), g[f"final_b_rho{li}"]) < 1e-3

@@ -1,4 +1,4 @@
-"""Manual probe (not a pytest file): bf16 tensor-core path vs the fp32 path on the same Philox eps."""
+"""Manual GPU probe (run from the repo root: python tools/...): bf16 tensor-core path vs the fp32 path on the same Philox eps."""
 import sys
 import numpy as np
 import torch

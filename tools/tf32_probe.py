@@ -1,4 +1,4 @@
-"""Manual probe (not a pytest file): TF32 tensor-core path vs the fp32 path."""
+"""Manual GPU probe (run from the repo root: python tools/...): TF32 tensor-core path vs the fp32 path."""
 import sys
 import torch
 sys.path.insert(0, ".")
