@@ -176,9 +176,14 @@ typedef struct pl_conv2d_args {
   void* workspace;
   size_t workspace_bytes;
   void* stream;
+  /* optional forward->backward state (pl_conv2d_state_bytes, PL_PREC_BF16 only): pl_conv2d_fwd
+     leaves the bf16 im2col matrix there and pl_conv2d_bwd given the same buffer does not rebuild it */
+  void* fwd_state;
+  size_t fwd_state_bytes;
 } pl_conv2d_args;
 
 size_t pl_conv2d_workspace_bytes(const pl_conv2d_args* a);
+size_t pl_conv2d_state_bytes(const pl_conv2d_args* a);
 int pl_conv2d_fwd(const pl_conv2d_args* a);
 int pl_conv2d_bwd(const pl_conv2d_args* a);
 

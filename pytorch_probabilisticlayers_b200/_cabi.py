@@ -24,7 +24,7 @@ EXPORTS = (
     "pl_version", "pl_last_error", "pl_launch_count", "pl_device_supported", "pl_eps_dump",
     "pl_kl_workspace_bytes", "pl_kl_fwd", "pl_kl_bwd", "pl_adam_kl_step",
     "pl_linear_workspace_bytes", "pl_linear_state_bytes", "pl_linear_fwd", "pl_linear_bwd",
-    "pl_conv2d_workspace_bytes", "pl_conv2d_fwd", "pl_conv2d_bwd",
+    "pl_conv2d_workspace_bytes", "pl_conv2d_state_bytes", "pl_conv2d_fwd", "pl_conv2d_bwd",
 )
 
 
@@ -55,6 +55,7 @@ class Conv2dArgs(C.Structure):
         ("y", C.c_void_p), ("dy", C.c_void_p), ("dx", C.c_void_p),
         ("dw_mu", C.c_void_p), ("dw_rho", C.c_void_p), ("db_mu", C.c_void_p), ("db_rho", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("stream", C.c_void_p),
+        ("fwd_state", C.c_void_p), ("fwd_state_bytes", C.c_size_t),
     ]
 
 
@@ -102,6 +103,8 @@ def lib():
                     getattr(l, name).argtypes = [C.POINTER(LinearArgs)]
                 l.pl_conv2d_workspace_bytes.restype = C.c_size_t
                 l.pl_conv2d_workspace_bytes.argtypes = [C.POINTER(Conv2dArgs)]
+                l.pl_conv2d_state_bytes.restype = C.c_size_t
+                l.pl_conv2d_state_bytes.argtypes = [C.POINTER(Conv2dArgs)]
                 for name in ("pl_conv2d_fwd", "pl_conv2d_bwd"):
                     getattr(l, name).restype = C.c_int
                     getattr(l, name).argtypes = [C.POINTER(Conv2dArgs)]

@@ -326,6 +326,7 @@ static int fill_conv(const pl_conv2d_args* a, ConvParams& p, const char* who) {
 }
 
 size_t conv_tc_workspace_bytes(const pl_conv2d_args* a);
+size_t conv_tc_state_bytes(const pl_conv2d_args* a);
 int conv_fwd_tc_launch(const pl_conv2d_args* a);
 int conv_bwd_tc_launch(const pl_conv2d_args* a);
 
@@ -339,6 +340,11 @@ extern "C" size_t pl_conv2d_workspace_bytes(const pl_conv2d_args* a) {
     return tc > colsum ? tc : colsum;
   }
   return colsum;
+}
+
+extern "C" size_t pl_conv2d_state_bytes(const pl_conv2d_args* a) {
+  if (!a || a->precision != PL_PREC_BF16) return 0;
+  return pl::conv_tc_state_bytes(a);
 }
 
 extern "C" int pl_conv2d_fwd(const pl_conv2d_args* a) {

@@ -59,6 +59,68 @@ __global__ void __launch_bounds__(256) im2col_bf16_kernel(const float* __restric
   }
 }
 
+// Same matrix, one CTA per (image, output row): the k input rows that row needs are staged in shared
+// memory ([Cin][k][W] fp32, zero rows outside the image) so every input element is read from HBM/L2
+// once per output row instead of k*k times, and the 16-byte output chunks are built from smem.
+// grid (ho, mcx*batch), dynamic smem = cin*k*w*4 bytes.
+__global__ void __launch_bounds__(256) im2col_rows_bf16_kernel(const float* __restrict__ x,
+                                                               int64_t x_mc_stride,
+                                                               __nv_bfloat16* __restrict__ A, ConvGeom g) {
+  extern __shared__ float rows[];   // [cin][k][w]
+  const int oh = blockIdx.x, img = blockIdx.y, mc = img / g.batch, b = img - mc * g.batch;
+  const float* xb = x + (int64_t)mc * x_mc_stride + (int64_t)b * g.cin * g.h * g.w;
+  const int ih0 = oh * g.stride - g.pad;
+  const int nrow = g.cin * g.k;
+  for (int t = threadIdx.x; t < nrow * g.w; t += 256) {
+    const int rw = t / g.w, iw = t - rw * g.w, c = rw / g.k, kh = rw - c * g.k;
+    const int ih = ih0 + kh * g.dil;
+    rows[t] = (ih >= 0 && ih < g.h) ? __ldg(xb + ((int64_t)c * g.h + ih) * g.w + iw) : 0.f;
+  }
+  __syncthreads();
+  const int chunks = g.Kp >> 3;
+  const int64_t m0 = ((int64_t)mc * g.batch + b) * g.ho * g.wo + (int64_t)oh * g.wo;   // first pixel row
+  for (int t = threadIdx.x; t < g.wo * chunks; t += 256) {
+    const int ow = t / chunks, kc = t - ow * chunks;
+    const int iw0 = ow * g.stride - g.pad;
+    int kidx = kc << 3;
+    const int kk2 = g.k * g.k;
+    int c = kidx / kk2, r = kidx - c * kk2, kh = r / g.k, kw = r - kh * g.k;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float val = 0.f;
+      if (kidx + j < g.K) {
+        const int iw = iw0 + kw * g.dil;
+        if (iw >= 0 && iw < g.w) val = rows[(c * g.k + kh) * g.w + iw];
+      }
+      v[j] = val;
+      if (++kw == g.k) {
+        kw = 0;
+        if (++kh == g.k) {
+          kh = 0;
+          ++c;
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(A + ((m0 + ow) * chunks + kc) * 8) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                   pack_bf16x2(v[6], v[7]));
+  }
+}
+
+static int launch_im2col(const pl_conv2d_args* a, const ConvGeom& g, __nv_bfloat16* A, cudaStream_t st) {
+  const size_t smem = (size_t)g.cin * g.k * g.w * sizeof(float);
+  if (smem <= 48 * 1024 && (int64_t)g.mcx * g.batch <= 65535) {
+    dim3 grid((unsigned)g.ho, (unsigned)(g.mcx * g.batch));
+    im2col_rows_bf16_kernel<<<grid, 256, smem, st>>>(a->x, a->x_mc_stride, A, g);
+    PL_LAUNCH_CHECK("im2col_rows_bf16_kernel");
+  } else {
+    im2col_bf16_kernel<<<ew_grid((int64_t)g.mcx * g.M * (g.Kp / 8), 256), 256, 0, st>>>(a->x, a->x_mc_stride, A, g);
+    PL_LAUNCH_CHECK("im2col_bf16_kernel");
+  }
+  return PL_OK;
+}
+
 // dy [mc*B, Cout, HW] fp32 -> dYt [mc*B*HW, Coutp] bf16 (pixel-major rows = GEMM operand), zero padded
 // grid (ceil(HW/32), ceil(Coutp/32), mc*B), block (32, 8)
 __global__ void __launch_bounds__(256) dy_pixel_major_kernel(const float* __restrict__ dy,
@@ -82,6 +144,7 @@ __global__ void __launch_bounds__(256) dy_pixel_major_kernel(const float* __rest
 }
 
 // dx[mc][b][c][h][w] = sum_{kh,kw} dA[mc][c*k*k + kh*k + kw][b*HWo + oh*Wo + ow]   (gather, no atomics)
+template <bool kUnit>   // kUnit: stride == 1 and dilation == 1 (no divisibility tests / divisions)
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dA, float* __restrict__ dx,
                                                      ConvGeom g) {
   const int64_t per_mc = (int64_t)g.batch * g.cin * g.h * g.w, total = (int64_t)g.mc * per_mc;
@@ -97,14 +160,14 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ d
     const float* base = dA + ((int64_t)mc * g.K + (int64_t)c * kk2) * g.M + (int64_t)b * hwo;
     float s = 0.f;
     for (int kh = 0; kh < g.k; ++kh) {
-      const int th = ih + g.pad - kh * g.dil;
-      if (th < 0 || th % g.stride) continue;
-      const int oh = th / g.stride;
+      const int th = ih + g.pad - (kUnit ? kh : kh * g.dil);
+      if (th < 0 || (!kUnit && th % g.stride)) continue;
+      const int oh = kUnit ? th : th / g.stride;
       if (oh >= g.ho) continue;
       for (int kw = 0; kw < g.k; ++kw) {
-        const int tw = iw + g.pad - kw * g.dil;
-        if (tw < 0 || tw % g.stride) continue;
-        const int ow = tw / g.stride;
+        const int tw = iw + g.pad - (kUnit ? kw : kw * g.dil);
+        if (tw < 0 || (!kUnit && tw % g.stride)) continue;
+        const int ow = kUnit ? tw : tw / g.stride;
         if (ow >= g.wo) continue;
         s += __ldg(base + (int64_t)(kh * g.k + kw) * g.M + oh * g.wo + ow);
       }
@@ -145,13 +208,17 @@ struct ConvScratch {
   size_t total;
 };
 
-static ConvScratch conv_carve(const ConvGeom& g, void* base, bool backward, bool want_dx) {
+static ConvScratch conv_carve(const ConvGeom& g, void* base, bool backward, bool want_dx, void* state) {
   uint8_t* b = (uint8_t*)(((uintptr_t)base + 255) & ~(uintptr_t)255);
   ConvScratch w;
   size_t off = 0;
   w.sigma = (float*)(b + off); off += align256((size_t)g.cout * g.K * 4);
   w.bias = (float*)(b + off); off += align256((size_t)g.mc * g.cout * 4);
-  w.A = (__nv_bfloat16*)(b + off); off += align256((size_t)g.mcx * g.M * g.Kp * 2);
+  if (state) {   // the im2col matrix lives in the caller's forward->backward state buffer
+    w.A = (__nv_bfloat16*)(((uintptr_t)state + 255) & ~(uintptr_t)255);
+  } else {
+    w.A = (__nv_bfloat16*)(b + off); off += align256((size_t)g.mcx * g.M * g.Kp * 2);
+  }
   w.dyt = (__nv_bfloat16*)(b + off);
   if (backward) off += align256((size_t)g.mc * g.M * g.Coutp * 2);
   w.dA = (float*)(b + off);
@@ -163,7 +230,13 @@ static ConvScratch conv_carve(const ConvGeom& g, void* base, bool backward, bool
 size_t conv_tc_workspace_bytes(const pl_conv2d_args* a) {
   ConvGeom g;
   if (conv_geom(a, g, "pl_conv2d_workspace_bytes") != PL_OK) return 0;
-  return conv_carve(g, nullptr, a->dy != nullptr, a->dx != nullptr).total;
+  return conv_carve(g, nullptr, a->dy != nullptr, a->dx != nullptr, a->fwd_state).total;
+}
+
+size_t conv_tc_state_bytes(const pl_conv2d_args* a) {
+  ConvGeom g;
+  if (conv_geom(a, g, "pl_conv2d_state_bytes") != PL_OK) return 0;
+  return align256((size_t)g.mcx * g.M * g.Kp * 2) + 512;
 }
 
 int conv_fwd_tc_launch(const pl_conv2d_args* a) {
@@ -181,7 +254,11 @@ int conv_fwd_tc_launch(const pl_conv2d_args* a) {
     return PL_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)a->stream;
-  ConvScratch w = conv_carve(g, a->workspace, false, false);
+  if (a->fwd_state && a->fwd_state_bytes < conv_tc_state_bytes(a)) {
+    set_error("pl_conv2d_fwd: fwd_state %zu < %zu bytes", a->fwd_state_bytes, conv_tc_state_bytes(a));
+    return PL_ERR_WORKSPACE;
+  }
+  ConvScratch w = conv_carve(g, a->workspace, false, false, a->fwd_state);
   const int64_t nw = (int64_t)g.cout * g.K;
   softplus_kernel<<<ew_grid(nw, 1024), 256, 0, st>>>(a->w_rho, w.sigma, nw);
   PL_LAUNCH_CHECK("softplus_kernel");
@@ -189,9 +266,8 @@ int conv_fwd_tc_launch(const pl_conv2d_args* a) {
       a->b_mu, a->b_rho, a->eps_b, make_sampler(a->seed, a->layer_id, true, a->mc_global_offset), g.mc,
       g.cout, w.bias);
   PL_LAUNCH_CHECK("sample_bias_kernel");
-  im2col_bf16_kernel<<<ew_grid((int64_t)g.mcx * g.M * (g.Kp / 8), 256), 256, 0, st>>>(a->x, a->x_mc_stride,
-                                                                                       w.A, g);
-  PL_LAUNCH_CHECK("im2col_bf16_kernel");
+  rc = launch_im2col(a, g, w.A, st);
+  if (rc != PL_OK) return rc;
   CUtensorMap tm;
   rc = make_tmap_bf16(&tm, w.A, (uint64_t)g.mcx * g.M, (uint64_t)g.Kp, 128, kBK);
   if (rc != PL_OK) return rc;
@@ -219,7 +295,11 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     return PL_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)a->stream;
-  ConvScratch w = conv_carve(g, a->workspace, true, a->dx != nullptr);
+  if (a->fwd_state && a->fwd_state_bytes < conv_tc_state_bytes(a)) {
+    set_error("pl_conv2d_bwd: fwd_state %zu < %zu bytes", a->fwd_state_bytes, conv_tc_state_bytes(a));
+    return PL_ERR_WORKSPACE;
+  }
+  ConvScratch w = conv_carve(g, a->workspace, true, a->dx != nullptr, a->fwd_state);
   const int hwo = g.ho * g.wo;
   const int64_t nw = (int64_t)g.cout * g.K;
   if (a->dx || a->dw_mu) {
@@ -229,9 +309,10 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     PL_LAUNCH_CHECK("dy_pixel_major_kernel");
   }
   if (a->dw_mu) {
-    im2col_bf16_kernel<<<ew_grid((int64_t)g.mcx * g.M * (g.Kp / 8), 256), 256, 0, st>>>(
-        a->x, a->x_mc_stride, w.A, g);
-    PL_LAUNCH_CHECK("im2col_bf16_kernel");
+    if (!a->fwd_state) {   // stateless call: rebuild the im2col matrix
+      rc = launch_im2col(a, g, w.A, st);
+      if (rc != PL_OK) return rc;
+    }
     CUtensorMap tmx, tmdy;
     rc = make_tmap_bf16_3d(&tmx, w.dyt, (uint64_t)g.mc, (uint64_t)g.M, (uint64_t)g.Coutp, kBK, 64);
     if (rc != PL_OK) return rc;
@@ -289,7 +370,8 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     rc = a->eps_w ? launch_gemm<false, true>(tm, p, st) : launch_gemm<false, false>(tm, p, st);
     if (rc != PL_OK) return rc;
     const int64_t n = (int64_t)g.mc * g.batch * g.cin * g.h * g.w;
-    col2im_kernel<<<ew_grid(n, 256), 256, 0, st>>>(w.dA, a->dx, g);
+    if (g.stride == 1 && g.dil == 1) col2im_kernel<true><<<ew_grid(n, 256), 256, 0, st>>>(w.dA, a->dx, g);
+    else col2im_kernel<false><<<ew_grid(n, 256), 256, 0, st>>>(w.dA, a->dx, g);
     PL_LAUNCH_CHECK("col2im_kernel");
   }
   return PL_OK;

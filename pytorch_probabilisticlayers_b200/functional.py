@@ -217,6 +217,11 @@ class _BayesConv2dFn(torch.autograd.Function):
         a.seed, a.layer_id, a.mc_global_offset = spec.seed, spec.layer_id, spec.mc_global_offset
         a.eps_w, a.eps_b = _cabi.ptr(tens[4]), _cabi.ptr(tens[5])
         a.y = _cabi.ptr(y)
+        state = None
+        nstate = lib.pl_conv2d_state_bytes(C.byref(a))
+        if nstate and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
+            state = torch.empty(int(nstate), dtype=torch.uint8, device=x.device)   # bf16 im2col matrix
+            a.fwd_state, a.fwd_state_bytes = _cabi.ptr(state), state.numel()
         ws = _workspace(lib.pl_conv2d_workspace_bytes(C.byref(a)), x.device)
         a.workspace, a.workspace_bytes = _cabi.ptr(ws), ws.numel()
         a.stream = _cabi.current_stream(x.device)
@@ -224,13 +229,13 @@ class _BayesConv2dFn(torch.autograd.Function):
             _timed(f"conv_fwd[{mc}x{batch}x{cin}x{h}x{w}->{cout},k{k}]",
                    lambda: _cabi.check(lib.pl_conv2d_fwd(C.byref(a)), "pl_conv2d_fwd"),
                    ("flops", 2.0 * mc * batch * ho * wo * cout * cin * k * k))
-        ctx.save_for_backward(xb, *tens)
+        ctx.save_for_backward(xb, *tens, state)
         ctx.meta = (spec, hyper, x_stride, (mc, batch, cin, cout, h, w), a.precision)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        xb, w_mu, w_rho, b_mu, b_rho, eps_w, eps_b = ctx.saved_tensors
+        xb, w_mu, w_rho, b_mu, b_rho, eps_w, eps_b, state = ctx.saved_tensors
         spec, hyper, x_stride, dims, precision = ctx.meta
         mc, batch, cin, cout, h, w = dims
         k, stride, padding, dilation = hyper
@@ -255,6 +260,8 @@ class _BayesConv2dFn(torch.autograd.Function):
         a.eps_w, a.eps_b = _cabi.ptr(eps_w), _cabi.ptr(eps_b)
         a.dy, a.dx = _cabi.ptr(dy), _cabi.ptr(dx)
         a.dw_mu, a.dw_rho, a.db_mu, a.db_rho = (_cabi.ptr(t) for t in (dw_mu, dw_rho, db_mu, db_rho))
+        if state is not None:
+            a.fwd_state, a.fwd_state_bytes = _cabi.ptr(state), state.numel()
         ws = _workspace(lib.pl_conv2d_workspace_bytes(C.byref(a)), dev)
         a.workspace, a.workspace_bytes = _cabi.ptr(ws), ws.numel()
         a.stream = _cabi.current_stream(dev)
