@@ -265,6 +265,53 @@ def init_case(PL):
          conv_w_mu_absmax=npy(c.weight.loc.abs().max()), conv_b_mu_absmax=npy(c.bias.loc.abs().max()))
 
 
+def sivi_train_case(PL, LOSS, name, mc, b, steps, seed):
+    """Config 5 (experiments/SIVILastLayer.py:244-296): Linear(1,50)-LeakyReLU-Linear(50,50)-LeakyReLU-
+    repeat(MC)-SIVILayer(50,1,5), MC_NLL likelihood + SIVI kl_div, Adam lr 1e-2."""
+    torch.manual_seed(seed)
+    fc1, fc2 = torch.nn.Linear(1, 50), torch.nn.Linear(50, 50)
+    sivi = PL.SIVILayer(50, 1, 5)
+    params = list(fc1.parameters()) + list(fc2.parameters()) + list(sivi.parameters())
+    rs = np.random.RandomState(2)
+    xs = np.linspace(-0.35, 0.55, 1000)
+    ys = xs + 0.3 * np.sin(2 * np.pi * xs) + 0.3 * np.sin(4 * np.pi * xs) + rs.normal(0, 0.05, 1000)
+    idx = rs.permutation(1000)[:b]
+    x = torch.from_numpy(xs[idx].reshape(-1, 1)).float()
+    y = torch.from_numpy(ys[idx].reshape(-1, 1)).float()
+    num_samples = 1000
+    crit = LOSS.MC_NLL(num_samples)
+    opt = torch.optim.Adam(params, 1e-2)
+    arrs = dict(x=npy(x), y=npy(y), mc=np.int64(mc), steps=np.int64(steps), num_samples=np.int64(num_samples))
+    for k_, v in fc1.state_dict().items():
+        arrs["fc1__" + k_] = npy(v)
+    for k_, v in fc2.state_dict().items():
+        arrs["fc2__" + k_] = npy(v)
+    for k_, v in sivi.state_dict().items():
+        arrs["sivi__" + k_.replace(".", "__")] = npy(v)
+    for s_ in range(steps):
+        opt.zero_grad()
+        h = torch.nn.functional.leaky_relu(fc2(torch.nn.functional.leaky_relu(fc1(x))))
+        h = h.unsqueeze(0).repeat(mc, 1, 1)                      # SIVILastLayer.py:268
+        torch.manual_seed(seed + 100 + s_)
+        pred = sivi(h)
+        torch.manual_seed(seed + 100 + s_)                       # replay the layer's draws
+        arrs[f"s{s_}_noise"] = npy(torch.randn(mc, 5))
+        arrs[f"s{s_}_eps_w"] = npy(torch.randn(mc, 50, 1))
+        arrs[f"s{s_}_eps_b"] = npy(torch.randn(mc, 1))
+        ll = crit(pred, y) / num_samples
+        kl = sivi.kl_div / num_samples
+        loss = ll + kl
+        loss.backward()
+        arrs[f"s{s_}_pred"] = npy(pred)
+        arrs[f"s{s_}_LL"] = npy(ll)
+        arrs[f"s{s_}_KL"] = npy(kl)
+        arrs[f"s{s_}_loss"] = npy(loss)
+        opt.step()
+    arrs["final_fc1_weight"] = npy(fc1.weight)
+    arrs["final_sivi_last_bias"] = npy(sivi.sivi_net[4].bias)
+    save(name, **arrs)
+
+
 def seeded_init_case(PL):
     """state_dicts of freshly constructed layers under a fixed global seed (drop-in init parity)."""
     arrs = {}
@@ -300,6 +347,7 @@ def main():
     mlp_train_case(PL, LOSS, "train_mlp_ce", [12, 16, 16, 5], mc=4, b=6, act=torch.nn.LeakyReLU,
                    loss_kind="ce", num_samples=100, lr=1e-3, steps=3, seed=32)
     sivi_case(PL, "sivi_small", mc=4, b=3, i=6, seed=41)
+    sivi_train_case(PL, LOSS, "train_c5_sivi", mc=128, b=100, steps=3, seed=51)
     loss_cases(PL, LOSS)
     aux_layer_cases(PL)
     init_case(PL)

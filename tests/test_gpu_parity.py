@@ -448,3 +448,35 @@ def test_elbo_train_step_matches_reference_trajectory(plb, fused):
         assert rel_err(l.weight.loc.detach().cpu().numpy(), g[f"final_w_mu{li}"]) < 1e-3
         assert rel_err(l.weight.logscale.detach().cpu().numpy(), g[f"final_w_rho{li}"]) < 1e-3
         assert rel_err(l.bias.logscale.detach().cpu().numpy(), g[f"final_b_rho{li}"]) < 1e-3
+
+
+def test_sivi_last_layer_training_matches_reference_trajectory(plb):
+    """Config 5 (experiments/SIVILastLayer.py): deterministic feature extractor + SIVILayer(50,1,5),
+    MC=128, batch 100, MC_NLL + SIVI KL, 3 Adam steps with the reference's draws injected."""
+    g = load_golden("train_c5_sivi")
+    mc, ns, steps = int(g["mc"]), int(g["num_samples"]), int(g["steps"])
+    fc1, fc2 = torch.nn.Linear(1, 50).cuda(), torch.nn.Linear(50, 50).cuda()
+    sivi = plb.SIVILayer(50, 1, 5).cuda()
+    fc1.load_state_dict({k[5:]: dev(v) for k, v in g.items() if k.startswith("fc1__")})
+    fc2.load_state_dict({k[5:]: dev(v) for k, v in g.items() if k.startswith("fc2__")})
+    sivi.load_state_dict({k[6:].replace("__", "."): dev(v) for k, v in g.items() if k.startswith("sivi__")})
+    params = list(fc1.parameters()) + list(fc2.parameters()) + list(sivi.parameters())
+    opt = torch.optim.Adam(params, 1e-2)
+    crit = plb.MC_NLL(ns)
+    x, y = dev(g["x"]), dev(g["y"])
+    F = torch.nn.functional
+    for s in range(steps):
+        opt.zero_grad()
+        h = F.leaky_relu(fc2(F.leaky_relu(fc1(x))))
+        h = h.unsqueeze(0).expand(mc, *h.shape)
+        sivi.inject_noise(dev(g[f"s{s}_noise"]), dev(g[f"s{s}_eps_w"]), dev(g[f"s{s}_eps_b"]))
+        pred = sivi(h)
+        ll = crit(pred, y) / ns
+        kl = sivi.kl_div / ns
+        (ll + kl).backward()
+        assert rel_err(pred.detach().cpu().numpy(), g[f"s{s}_pred"]) < 2e-4, s
+        assert abs(ll.item() - float(g[f"s{s}_LL"])) / abs(float(g[f"s{s}_LL"])) < 5e-4, s
+        assert abs(kl.item() - float(g[f"s{s}_KL"])) / abs(float(g[f"s{s}_KL"])) < 1e-4, s
+        opt.step()
+    assert rel_err(fc1.weight.detach().cpu().numpy(), g["final_fc1_weight"]) < 2e-3
+    assert rel_err(sivi.sivi_net[4].bias.detach().cpu().numpy(), g["final_sivi_last_bias"]) < 2e-3
