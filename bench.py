@@ -224,6 +224,11 @@ def run_b200(args, wl):
             if li + 2 < len(dims):
                 mods.append(torch.nn.LeakyReLU())
         net = torch.nn.Sequential(*mods).to(dev)
+        if args.fuse and args.precision in ("auto", "bf16"):
+            # same layers and parameters; the Linear-LeakyReLU-Linear runs hand bf16 activations from
+            # GEMM epilogue to the next TMA load instead of four fp32 passes per hidden layer
+            from pytorch_probabilisticlayers_b200.fused import fuse_bayes_mlp
+            net = fuse_bayes_mlp(net, batch)
     trainer = ELBOTrainStep(net, plb.MC_CrossEntropyLoss(ns), ns, lr=wl["lr"])
     assert trainer.set_shard(mc_total) == mc_local
 
@@ -316,7 +321,7 @@ def run_b200(args, wl):
     # launched back to back over the two 4096x4096 layers' (mu, rho) in turn (2 x 134 MB > L2, so
     # every launch streams from HBM), CUDA events around the batch
     kl_info = None
-    big = [m for m in net if isinstance(m, plb.BayesLinear)]
+    big = [m for m in net.modules() if isinstance(m, plb.BayesLinear)]
     big = [m for m in big if m.weight.loc.numel() == max(b.weight.loc.numel() for b in big)]
     if big:
         reps = 40
@@ -364,6 +369,7 @@ def run_b200(args, wl):
         "data": "synthetic",
         "config": {"workload": wl["name"], "mc_total": mc_total, "mc_per_gpu": mc_local,
                    "batch": batch, "num_samples": ns, "precision": args.precision,
+                   "fused_chain": bool(args.fuse and not wl.get("conv") and args.precision in ("auto", "bf16")),
                    "parallelism": f"mc-shard x{world}" if world > 1 else "single",
                    "l2": "per-step working set (parameters + activations >> 126 MB) exceeds L2; "
                          "no explicit flush"},
@@ -395,6 +401,8 @@ def main():
     ap.add_argument("--precision", choices=["fp32", "tf32", "bf16", "auto", "auto_tf32"], default="auto",
                     help="auto = bf16 tcgen05 kernels wherever the layer shape tiles, fp32 kernels for tiny layers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse", dest="fuse", action="store_false",
+                    help="run BayesLinear / LeakyReLU module by module instead of as a fused chain")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

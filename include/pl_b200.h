@@ -139,6 +139,16 @@ typedef struct pl_linear_args {
      buffer skips recomputing them (and then does not read x).  NULL = stateless. */
   void* fwd_state;
   size_t fwd_state_bytes;
+  /* optional bf16 activation chaining between consecutive layers (PL_PREC_BF16 only): lets a caller
+     that owns a whole BayesLinear -> LeakyReLU -> BayesLinear chain skip the fp32 round trips
+     (y write, activation read/write, cast read/write) between the layers. */
+  const void* x_lp;  /* fwd/bwd: x as bf16 [mc|1, batch, in]; replaces the cast pre-pass (x may be NULL) */
+  void* y_lp;        /* fwd: also write act(y) as bf16 [mc,batch,out]; y may then be NULL */
+  int32_t y_act;     /* 0: none, 1: LeakyReLU(y_act_slope) applied to y and y_lp */
+  float y_act_slope;
+  const void* dy_lp; /* bwd: dY as bf16 [mc,batch,out]; replaces the cast pre-pass (dy may be NULL) */
+  void* dx_lp;       /* bwd: write dX * act'(x) as bf16 [mc,batch,in] (needs x_lp); dx may be NULL */
+  float x_act_slope; /* slope of the LeakyReLU that produced x: act'(x) = x > 0 ? 1 : x_act_slope */
 } pl_linear_args;
 
 size_t pl_linear_workspace_bytes(const pl_linear_args* a);

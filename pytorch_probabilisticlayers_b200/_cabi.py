@@ -40,6 +40,8 @@ class LinearArgs(C.Structure):
         ("dw_mu", C.c_void_p), ("dw_rho", C.c_void_p), ("db_mu", C.c_void_p), ("db_rho", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("stream", C.c_void_p),
         ("fwd_state", C.c_void_p), ("fwd_state_bytes", C.c_size_t),
+        ("x_lp", C.c_void_p), ("y_lp", C.c_void_p), ("y_act", C.c_int32), ("y_act_slope", C.c_float),
+        ("dy_lp", C.c_void_p), ("dx_lp", C.c_void_p), ("x_act_slope", C.c_float),
     ]
 
 

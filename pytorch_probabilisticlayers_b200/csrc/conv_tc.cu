@@ -271,7 +271,7 @@ int conv_fwd_tc_launch(const pl_conv2d_args* a) {
   CUtensorMap tm;
   rc = make_tmap_bf16(&tm, w.A, (uint64_t)g.mcx * g.M, (uint64_t)g.Kp, 128, kBK);
   if (rc != PL_OK) return rc;
-  TcGemmParams p;
+  TcGemmParams p{};
   p.mc = g.mc; p.rows = (int)g.M; p.ndim = g.cout; p.kdim = g.K;
   p.w_in = g.cout; p.w_out = g.K;
   p.a_mc_rows = g.mcx == 1 ? 0 : g.M;
@@ -357,7 +357,7 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     CUtensorMap tm;
     rc = make_tmap_bf16(&tm, w.dyt, (uint64_t)g.mc * g.M, (uint64_t)g.Coutp, 128, kBK);
     if (rc != PL_OK) return rc;
-    TcGemmParams p;
+    TcGemmParams p{};
     p.mc = g.mc; p.rows = (int)g.M; p.ndim = g.K; p.kdim = g.cout;
     p.w_in = g.cout; p.w_out = g.K;
     p.a_mc_rows = g.M;

@@ -115,7 +115,7 @@ static int check_buffers(const pl_linear_args* a, const char* who) {
 int linear_fwd_tc_launch(const pl_linear_args* a) {
   PL_CHECK_ARG(a, "pl_linear_fwd: NULL args");
   if (a->mc == 0 || a->batch == 0) return PL_OK;
-  PL_CHECK_ARG(a->x && a->w_mu && a->w_rho && a->y, "pl_linear_fwd: NULL pointer");
+  PL_CHECK_ARG((a->x || a->x_lp) && a->w_mu && a->w_rho && (a->y || a->y_lp), "pl_linear_fwd: NULL pointer");
   PL_CHECK_ARG((a->b_mu == nullptr) == (a->b_rho == nullptr), "pl_linear_fwd: b_mu and b_rho must both be set or NULL");
   int rc = tc_shape_ok(a, "pl_linear_fwd");
   if (rc != PL_OK) return rc;
@@ -132,7 +132,8 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   softplus_kernel<<<ew_grid(I * O, 1024), 256, 0, st>>>(a->w_rho, state.sigma, I * O);
   PL_LAUNCH_CHECK("softplus_kernel");
   const bool tf32 = a->precision == PL_PREC_TF32;   // fp32 operands straight from the caller's tensors
-  if (!tf32) {
+  PL_CHECK_ARG(!tf32 || !(a->x_lp || a->y_lp), "pl_linear_fwd: bf16 activation chaining needs PL_PREC_BF16");
+  if (!tf32 && !a->x_lp) {
     cast_bf16_kernel<<<ew_grid(x_rows * I / 8, 1024), 256, 0, st>>>(a->x, state.x_bf16, x_rows * I / 8);
     PL_LAUNCH_CHECK("cast_bf16_kernel");
   }
@@ -144,9 +145,10 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   }
   CUtensorMap tm;
   rc = tf32 ? make_tmap_2d(&tm, a->x, (uint64_t)x_rows, (uint64_t)I, 128, 32, true)
-            : make_tmap_bf16(&tm, state.x_bf16, (uint64_t)x_rows, (uint64_t)I, 128, kBK);
+            : make_tmap_bf16(&tm, a->x_lp ? a->x_lp : (const void*)state.x_bf16, (uint64_t)x_rows,
+                             (uint64_t)I, 128, kBK);
   if (rc != PL_OK) return rc;
-  TcGemmParams p;
+  TcGemmParams p{};
   p.mc = (int)MC; p.rows = (int)B; p.ndim = (int)O; p.kdim = (int)I;
   p.w_in = (int)I; p.w_out = (int)O;
   p.a_mc_rows = a->x_mc_stride == 0 ? 0 : B;
@@ -156,6 +158,9 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   p.out = a->y;
   p.out_hw = 0;
   p.w_aligned = 1;
+  p.out_lp = (__nv_bfloat16*)a->y_lp;
+  p.act = a->y_act;
+  p.act_slope = a->y_act_slope;
   if (tf32) return a->eps_w ? launch_gemm<false, true, true>(tm, p, st) : launch_gemm<false, false, true>(tm, p, st);
   return a->eps_w ? launch_gemm<false, true>(tm, p, st) : launch_gemm<false, false>(tm, p, st);
 }
@@ -165,7 +170,10 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
   if (a->mc == 0 || a->batch == 0) return linear_bwd_simt_launch(a);
   const bool have_state = a->fwd_state != nullptr;
   const bool tf32 = a->precision == PL_PREC_TF32;
-  PL_CHECK_ARG((a->x || (have_state && !tf32)) && a->w_mu && a->w_rho && a->dy, "pl_linear_bwd: NULL pointer");
+  PL_CHECK_ARG((a->x || a->x_lp || (have_state && !tf32)) && a->w_mu && a->w_rho && (a->dy || a->dy_lp),
+               "pl_linear_bwd: NULL pointer");
+  PL_CHECK_ARG(!tf32 || !(a->x_lp || a->dy_lp || a->dx_lp), "pl_linear_bwd: bf16 activation chaining needs PL_PREC_BF16");
+  PL_CHECK_ARG(!a->dx_lp || a->x_lp, "pl_linear_bwd: dx_lp needs x_lp (the activation mask source)");
   PL_CHECK_ARG((a->db_mu == nullptr) == (a->db_rho == nullptr), "pl_linear_bwd: db_mu/db_rho must both be set or NULL");
   PL_CHECK_ARG(!a->db_mu || a->b_rho, "pl_linear_bwd: bias gradients requested without a bias");
   int rc = tc_shape_ok(a, "pl_linear_bwd");
@@ -178,16 +186,24 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
   const int64_t I = a->in_features, O = a->out_features, MC = a->mc, B = a->batch;
   const int64_t x_rows = a->x_mc_stride == 0 ? B : MC * B;
   if (!have_state) {
-    if (a->dx) {
+    if (a->dx || a->dx_lp) {
       softplus_kernel<<<ew_grid(I * O, 1024), 256, 0, st>>>(a->w_rho, state.sigma, I * O);
       PL_LAUNCH_CHECK("softplus_kernel");
     }
-    if (a->dw_mu && !tf32) {
+    if (a->dw_mu && !tf32 && !a->x_lp) {
       cast_bf16_kernel<<<ew_grid(x_rows * I / 8, 1024), 256, 0, st>>>(a->x, state.x_bf16, x_rows * I / 8);
       PL_LAUNCH_CHECK("cast_bf16_kernel");
     }
   }
-  if ((!tf32 && (a->dx || a->dw_mu)) || a->db_mu) {
+  const bool want_dx = a->dx || a->dx_lp;
+  const __nv_bfloat16* dy_bf16 = a->dy_lp ? (const __nv_bfloat16*)a->dy_lp : w.dy_bf16;
+  if (a->dy_lp) {
+    if (a->db_mu) {   // bias column sums straight from the bf16 dY
+      dim3 grid((unsigned)((O + 127) / 128), (unsigned)MC);
+      colsum_bf16_kernel<<<grid, 256, 0, st>>>(dy_bf16, w.colsum, (int)B, (int)O);
+      PL_LAUNCH_CHECK("colsum_bf16_kernel");
+    }
+  } else if ((!tf32 && (want_dx || a->dw_mu)) || a->db_mu) {
     // one pass over dY: bf16 operand copy + per-sample column sums for the bias gradients
     dim3 grid((unsigned)((O + 127) / 128), (unsigned)MC);
     cast_dy_colsum_kernel<<<grid, 256, 0, st>>>(a->dy, tf32 ? nullptr : w.dy_bf16,
@@ -200,12 +216,12 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
         (int)MC, (int)O, a->db_mu, a->db_rho);
     PL_LAUNCH_CHECK("bias_grad_tc_kernel");
   }
-  if (a->dx) {
+  if (want_dx) {
     CUtensorMap tm;
     rc = tf32 ? make_tmap_2d(&tm, a->dy, (uint64_t)(MC * B), (uint64_t)O, 128, 32, true)
-              : make_tmap_bf16(&tm, w.dy_bf16, (uint64_t)(MC * B), (uint64_t)O, 128, kBK);
+              : make_tmap_bf16(&tm, dy_bf16, (uint64_t)(MC * B), (uint64_t)O, 128, kBK);
     if (rc != PL_OK) return rc;
-    TcGemmParams p;
+    TcGemmParams p{};
     p.mc = (int)MC; p.rows = (int)B; p.ndim = (int)I; p.kdim = (int)O;
     p.w_in = (int)I; p.w_out = (int)O;
     p.a_mc_rows = B;
@@ -215,6 +231,11 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
     p.out = a->dx;
     p.out_hw = 0;
     p.w_aligned = 1;
+    p.out_lp = (__nv_bfloat16*)a->dx_lp;
+    if (a->dx_lp) {   // chain: dX * act'(x) for the previous layer, mask from this layer's bf16 input
+      p.mask_src = (const __nv_bfloat16*)a->x_lp;
+      p.mask_slope = a->x_act_slope;
+    }
     if (tf32) rc = a->eps_w ? launch_gemm<true, true, true>(tm, p, st) : launch_gemm<true, false, true>(tm, p, st);
     else rc = a->eps_w ? launch_gemm<true, true>(tm, p, st) : launch_gemm<true, false>(tm, p, st);
     if (rc != PL_OK) return rc;
@@ -228,9 +249,10 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
       if (rc != PL_OK) return rc;
       rc = make_tmap_3d(&tmdy, a->dy, (uint64_t)MC, (uint64_t)B, (uint64_t)O, 32, 32, true);
     } else {
-      rc = make_tmap_bf16_3d(&tmx, state.x_bf16, mcx, (uint64_t)B, (uint64_t)I, kBK, 64);
+      rc = make_tmap_bf16_3d(&tmx, a->x_lp ? a->x_lp : (const void*)state.x_bf16, mcx, (uint64_t)B,
+                             (uint64_t)I, kBK, 64);
       if (rc != PL_OK) return rc;
-      rc = make_tmap_bf16_3d(&tmdy, w.dy_bf16, (uint64_t)MC, (uint64_t)B, (uint64_t)O, kBK, 64);
+      rc = make_tmap_bf16_3d(&tmdy, dy_bf16, (uint64_t)MC, (uint64_t)B, (uint64_t)O, kBK, 64);
     }
     if (rc != PL_OK) return rc;
     TcDwParams p;

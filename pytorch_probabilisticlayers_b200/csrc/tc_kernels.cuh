@@ -33,6 +33,12 @@ struct TcGemmParams {
   int out_hw;                   // 0: row-major out; >0: out[(mc*rows/out_hw + row/out_hw)][n][row%out_hw]
                                 //    (conv: rows = pixels of all images, NCHW output)
   int w_aligned;                // weight rows 16-byte aligned (w_out % 4 == 0): 128-bit parameter loads
+  // bf16 activation chaining between consecutive layers (row-major mode only):
+  __nv_bfloat16* out_lp;        // also write the (activated / masked) result as bf16; `out` may be NULL
+  int act;                      // 1: LeakyReLU(act_slope) on the result (forward)
+  float act_slope;
+  const __nv_bfloat16* mask_src;  // dX: multiply by act'(x): x > 0 ? 1 : mask_slope, x = mask_src[row][col]
+  float mask_slope;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -105,6 +111,39 @@ static __global__ void __launch_bounds__(256) cast_dy_colsum_kernel(const float*
     }
   }
   if (colsum == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ry][cg * 8 + j] = s[j];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t += red[r][threadIdx.x];
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c < out) colsum[(int64_t)mc * out + c] = t;
+  }
+}
+
+// column sums of a bf16 dY (activation-chained backward): colsum[mc][o] = sum_b dY[mc][b][o]
+// grid (ceil(O/128), MC), 256 threads = 16 row lanes x 16 column groups of 8
+static __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                 float* __restrict__ colsum, int batch,
+                                                                 int out) {
+  __shared__ float red[16][129];
+  const int mc = blockIdx.y, cg = threadIdx.x & 15, ry = threadIdx.x >> 4;
+  const int col = blockIdx.x * 128 + cg * 8;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < out) {
+    const int64_t base = (int64_t)mc * batch * out;
+    for (int b = ry; b < batch; b += 16) {
+      const uint4 q = *reinterpret_cast<const uint4*>(dy + base + (int64_t)b * out + col);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        s[2 * t] += __uint_as_float(w[t] << 16);
+        s[2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+      }
+    }
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) red[ry][cg * 8 + j] = s[j];
   __syncthreads();
@@ -366,16 +405,36 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
       tmem_ld_wait();
       if (row < p.rows) {
         if (p.out_hw == 0) {
-          float* o = p.out + ((int64_t)mc * p.rows + row) * p.ndim + n0 + col;
+          const int64_t obase = ((int64_t)mc * p.rows + row) * p.ndim + n0 + col;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n0 + col + j < p.ndim) {
-              float4 w;
-              w.x = __uint_as_float(v[j + 0]) + bias_s[col + j + 0];
-              w.y = __uint_as_float(v[j + 1]) + bias_s[col + j + 1];
-              w.z = __uint_as_float(v[j + 2]) + bias_s[col + j + 2];
-              w.w = __uint_as_float(v[j + 3]) + bias_s[col + j + 3];
-              *reinterpret_cast<float4*>(o + j) = w;
+          for (int j = 0; j < 32; j += 8) {
+            if (n0 + col + j < p.ndim) {   // ndim % 8 == 0 on this path
+              float w[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) w[t] = __uint_as_float(v[j + t]) + bias_s[col + j + t];
+              if (p.act) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) w[t] = w[t] > 0.f ? w[t] : p.act_slope * w[t];
+              }
+              if (p.mask_src) {
+                const uint4 mk = __ldg(reinterpret_cast<const uint4*>(p.mask_src + obase + j));
+                const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                  // bf16 sign / zero test on the raw bits: positive and non-zero
+                  const uint32_t h = (t & 1) ? (mw[t >> 1] >> 16) : (mw[t >> 1] & 0xffffu);
+                  const bool pos = (h & 0x8000u) == 0 && (h & 0x7fffu) != 0;
+                  w[t] = pos ? w[t] : p.mask_slope * w[t];
+                }
+              }
+              if (p.out) {
+                *reinterpret_cast<float4*>(p.out + obase + j) = make_float4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<float4*>(p.out + obase + j + 4) = make_float4(w[4], w[5], w[6], w[7]);
+              }
+              if (p.out_lp)
+                *reinterpret_cast<uint4*>(p.out_lp + obase + j) =
+                    make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]),
+                               pack_bf16x2(w[6], w[7]));
             }
           }
         } else {
@@ -954,7 +1013,7 @@ static int launch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_
     const char* e = getenv("PL_TC_2CTA");
     g_force_1cta = (e && e[0] == '1') ? 0 : 1;
   }
-  if (!kTf32 && !g_force_1cta && p.rows > 128 && p.ndim > 128) {
+  if (!kTf32 && !g_force_1cta && p.rows > 128 && p.ndim > 128 && p.out && !p.out_lp && !p.mask_src && !p.act) {
     const int pair_rows = p.rows > 256 ? 512 : 256;
     dim3 grid(2u * (unsigned)((p.ndim + 255) / 256), (unsigned)((p.rows + pair_rows - 1) / pair_rows),
               (unsigned)p.mc);

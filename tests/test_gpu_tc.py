@@ -265,3 +265,52 @@ def test_tf32_philox_matches_fp64_oracle(plb, mc, b, i, o, bias, expand):
         assert rel_err(n(x.grad), bw["dx"]) < TF32_TOL
     assert rel_err(n(layer.weight.loc.grad), bw["dw_mu"]) < TF32_TOL
     assert rel_err(n(layer.weight.logscale.grad), bw["dw_rho"]) < TF32_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# opt-in chain fusion: BayesLinear -> LeakyReLU -> BayesLinear ... with bf16 activation hand-off
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mc,b,dims,expand", [(3, 256, [256, 384, 128, 136], True),
+                                              (2, 200, [192, 256, 200], False)])
+def test_fused_mlp_equals_unfused_bf16_chain(plb, mc, b, dims, expand):
+    from pytorch_probabilisticlayers_b200.fused import FusedBayesMLP, fuse_bayes_mlp
+    torch.manual_seed(11)
+    plb.manual_seed(2718)
+    mods = []
+    for li in range(len(dims) - 1):
+        l = plb.BayesLinear(dims[li], dims[li + 1])
+        l.precision = "bf16"
+        mods.append(l)
+        if li + 2 < len(dims):
+            mods.append(torch.nn.LeakyReLU(0.01))
+    net = torch.nn.Sequential(*mods).cuda()
+    layers = [m for m in net if isinstance(m, plb.BayesLinear)]
+    with torch.no_grad():
+        for l in layers:
+            l.weight.logscale.uniform_(-5, -2)
+    fused = fuse_bayes_mlp(net, b)
+    assert len(fused) == 1 and isinstance(fused[0], FusedBayesMLP)
+    assert fused[0].layers[0] is layers[0]                    # same modules / parameters
+    if expand:
+        x = torch.randn(b, dims[0], device="cuda").unsqueeze(0).expand(mc, b, dims[0])
+    else:
+        x = torch.randn(mc, b, dims[0], device="cuda")
+    gy = torch.randn(mc, b, dims[-1], device="cuda")
+
+    def run(model):
+        for l in layers:
+            l._calls = 0
+            l.zero_grad()
+        out = model(x)
+        (out * gy).sum().backward()
+        return out.detach().clone(), [p.grad.clone() for l in layers for p in l.parameters()], \
+            [l.kl_div.detach().clone() for l in layers]
+
+    out_u, g_u, kl_u = run(net)
+    out_f, g_f, kl_f = run(fused)
+    assert torch.equal(out_f, out_u)                          # identical bf16 operands, same MMAs
+    for k, (a, r) in enumerate(zip(g_f, g_u)):
+        tol = 5e-3 if k % 4 >= 2 else 1e-5                    # bias grads see bf16-rounded dY
+        assert rel_err(a.cpu().numpy(), r.cpu().numpy()) < tol, k
+    for a, r in zip(kl_f, kl_u):
+        assert torch.equal(a, r)
