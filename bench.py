@@ -55,6 +55,15 @@ def step_flops(dims, mc, batch):
     return total
 
 
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernels at the
+# C4 shapes, from the committed `ncu --set full` capture profiles/r01_ncu_full_final_summary.json
+NCU_TRAFFIC_BYTES = {
+    "linear_fwd[64x512x4096x4096]": 1.932e9 + 0.259e9,      # sampled_gemm_tc<4,0,0,0>, bf16 chained output
+    "linear_bwd_dx[64x512x4096x4096]": 2.619e9 + 0.257e9,   # sampled_gemm_tc<4,1,0,0>
+    "linear_bwd_dw[64x512x4096x4096]": 2.273e9 + 0.134e9,   # dw_tc<0,0>
+}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -307,7 +316,7 @@ def run_b200(args, wl):
         achieved = amount / (per_call[top] * 1e-3) / 1e12
         peak = pk["tf_sustained"]
         roofline = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get(top),
                     "peak_source": pk["source"] + " bf16 dense sustained",
                     "ms_per_launch": per_call[top], "algorithmic_flops_per_launch": amount,
                     "note": "C-ABI call = fused tcgen05 kernel + its HBM-bound pre-passes"}
