@@ -314,3 +314,69 @@ def test_fused_mlp_equals_unfused_bf16_chain(plb, mc, b, dims, expand):
         assert rel_err(a.cpu().numpy(), r.cpu().numpy()) < tol, k
     for a, r in zip(kl_f, kl_u):
         assert torch.equal(a, r)
+
+
+def test_tc_backward_mc_shards_sum_to_unsharded_gradients(plb):
+    """Full-width layer (4096 x 1024), bf16 kernels: the gradients of two MC shards add up to the
+    unsharded gradients (the property the one-all-reduce-per-step train step relies on)."""
+    torch.manual_seed(21)
+    plb.manual_seed(1212)
+    layer = plb.BayesLinear(4096, 1024).cuda()
+    layer.precision = "bf16"
+    with torch.no_grad():
+        layer.weight.logscale.uniform_(-6, -3)
+    x = torch.randn(4, 512, 4096, device="cuda")
+    gy = torch.randn(4, 512, 1024, device="cuda")
+
+    def grads(lo, hi):
+        layer._calls = 0
+        layer.zero_grad()
+        plb.set_mc_shard(lo)
+        try:
+            xs = x[lo:hi].clone().requires_grad_(True)
+            (layer(xs) * gy[lo:hi]).sum().backward()
+        finally:
+            plb.set_mc_shard(0)
+        return xs.grad, [p.grad.clone() for p in layer.parameters()]
+
+    dx_full, g_full = grads(0, 4)
+    dx_a, g_a = grads(0, 2)
+    dx_b, g_b = grads(2, 4)
+    assert torch.equal(torch.cat([dx_a, dx_b]), dx_full)            # per-sample work is identical
+    for a, b, f in zip(g_a, g_b, g_full):
+        assert rel_err((a + b).cpu().numpy(), f.cpu().numpy()) < 1e-5
+
+
+def test_train_step_with_fused_chain_matches_module_by_module(plb):
+    from pytorch_probabilisticlayers_b200.fused import fuse_bayes_mlp
+    from pytorch_probabilisticlayers_b200.train import ELBOTrainStep
+    dims, mc, b, ns = [256, 384, 256, 16], 4, 256, 1000
+    results = []
+    for fuse in (False, True):
+        torch.manual_seed(5)
+        plb.manual_seed(99)
+        plb.set_precision("auto")
+        try:
+            mods = [plb.MC_ExpansionLayer(mc, 2)]
+            for li in range(3):
+                mods.append(plb.BayesLinear(dims[li], dims[li + 1]))
+                if li < 2:
+                    mods.append(torch.nn.LeakyReLU())
+            net = torch.nn.Sequential(*mods).cuda()
+            layers = [m for m in net.modules() if isinstance(m, plb.BayesLinear)]
+            for k, l in enumerate(layers):
+                l.layer_id = 1000 + k                                # same eps stream in both runs
+            if fuse:
+                net = fuse_bayes_mlp(net, b)
+            tr = ELBOTrainStep(net, plb.MC_CrossEntropyLoss(ns), ns, lr=1e-3)
+            x = torch.randn(b, dims[0], device="cuda")
+            y = torch.randint(0, dims[-1], (b,), device="cuda")
+            stats = [tr.step(x, y).tolist() for _ in range(3)]
+            results.append((stats, [p.detach().clone() for p in net.parameters()]))
+        finally:
+            plb.set_precision("fp32")
+    (s0, p0), (s1, p1) = results
+    for a, c in zip(s0, s1):
+        assert abs(a[3] - c[3]) / abs(a[3]) < 1e-4                   # loss trajectory
+    for a, c in zip(p0, p1):
+        assert rel_err(c.cpu().numpy(), a.cpu().numpy()) < 2e-3
