@@ -17,7 +17,8 @@
  *
  * eps: either injected (eps_w / eps_b non-NULL: the reference's own torch.randn draws, captured
  * at src/ProbabilisticLayers.py:835) or synthesised on chip from Philox4x32-10 with
- *     key = seed,  counter = (col/4, row, mc_global_offset + mc, 2*layer_id + is_bias)
+ *     key = seed,  counter = (col/8, row, mc_global_offset + mc, 2*layer_id + is_bias)
+ * (one call -> 8 normals: word j is a Box-Muller pair with a 20-bit radius and a 12-bit angle)
  * so that forward and backward regenerate the same numbers for any tiling and GPU count
  * (oracle/philox.py is the CPU restatement).
  */
@@ -66,7 +67,7 @@ int pl_device_supported(void);
 /* ---- eps stream (test bridge; replaces torch.distributions.utils._standard_normal as used at
  *      src/ProbabilisticLayers.py:835) -----------------------------------------------------
  * out: float [num_mc, rows, cols] standard normals (raw == 0) or uint32 [num_mc, rows,
- * 4*ceil(cols/4)] raw Philox words (raw == 1) of stream `stream_id` (2*layer_id + is_bias). */
+ * 4*ceil(cols/8)] raw Philox words (raw == 1) of stream `stream_id` (2*layer_id + is_bias). */
 int pl_eps_dump(uint64_t seed, uint32_t stream_id, uint32_t mc_global_offset, int32_t num_mc,
                 int32_t rows, int32_t cols, void* out, int32_t raw, void* stream);
 

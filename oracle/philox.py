@@ -9,8 +9,9 @@ kernels never store eps, so they need a stateless stream: Philox4x32-10 (Salmon 
 ``normal_`` uses) keyed by the layer seed and indexed by *what* is being sampled:
 
     key     = (seed & 0xffffffff, seed >> 32)
-    counter = (col // 4, row, global_mc_index, stream)         stream = 2*layer_id + is_bias
-    4 x u32 -> 4 normals for columns 4*(col//4) .. +3 of ``row`` (two Box-Muller pairs)
+    counter = (col // 8, row, global_mc_index, stream)         stream = 2*layer_id + is_bias
+    4 x u32 -> 8 normals for columns 8*(col//8) .. +7 of ``row``: word j is one Box-Muller pair
+    (columns 2j, 2j+1) with a 20-bit radius and a 12-bit angle
 
 ``row``/``col`` index the parameter viewed as a 2-D matrix: Linear weight [I,O] -> (i, o);
 conv weight [Cout,Cin,k,k] -> (cout, cin*k*k + kh*k + kw); bias [O] -> (0, o).  The value of
@@ -48,25 +49,27 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1, rounds=10):
     return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
 
 
-def _unit_float(u):
-    """float32 in [1,2) from the top 23 bits of u (what the kernels do with one SHF+LOP3)."""
-    bits = (np.asarray(u, np.uint32) >> np.uint32(9)) | np.uint32(0x3F800000)
-    return bits.view(np.float32).astype(np.float64)
+def _bits_float(bits):
+    """float32 in [1,2) from a uint32 bit pattern 0x3F8xxxxx (what the kernels build with SHF/LOP3)."""
+    return np.asarray(bits, np.uint32).view(np.float32).astype(np.float64)
 
 
-def box_muller(u_radius, u_angle):
-    """(n_cos, n_sin) from two uint32 words, the exact recipe of csrc/philox.cuh:
-         f = 2 - t(u_radius) in (0,1];  r = sqrt(-2 ln f);  theta = 2*pi*t(u_angle) - 3*pi in [-pi,pi)
+def box_muller(w):
+    """(n_cos, n_sin) from ONE uint32 word, the exact recipe of csrc/common.cuh::box_muller:
+         f = 2 - t20 in (0,1] (top 20 bits);  r = sqrt(-2 ln f)
+         theta = 2*pi*t12 - 3*pi (low 12 bits, mid-bin) in (-pi, pi)
     """
-    f = 2.0 - _unit_float(u_radius)
+    w = np.asarray(w, np.uint32)
+    f = 2.0 - _bits_float(((w >> np.uint32(12)) << np.uint32(3)) | np.uint32(0x3F800000))
+    t = _bits_float(((w & np.uint32(0xFFF)) << np.uint32(11)) | np.uint32(0x3F800400))
     r = np.sqrt(-2.0 * np.log(f))
-    theta = 2.0 * np.pi * _unit_float(u_angle) - 3.0 * np.pi
+    theta = 2.0 * np.pi * t - 3.0 * np.pi
     return r * np.cos(theta), r * np.sin(theta)
 
 
 def raw_words(seed, stream, mc0, num_mc, rows, cols):
-    """uint32 [num_mc, rows, 4*ceil(cols/4)]: the raw Philox words in column order."""
-    groups = (cols + 3) // 4
+    """uint32 [num_mc, rows, 4*ceil(cols/8)]: the raw Philox words in column order (one call per 8 cols)."""
+    groups = (cols + 7) // 8
     g = np.arange(groups, dtype=np.uint64)[None, None, :]
     r = np.arange(rows, dtype=np.uint64)[None, :, None]
     m = (np.arange(num_mc, dtype=np.uint64) + np.uint64(mc0))[:, None, None]
@@ -79,10 +82,8 @@ def raw_words(seed, stream, mc0, num_mc, rows, cols):
 def eps_normal(seed, stream, mc0, num_mc, rows, cols):
     """float64 [num_mc, rows, cols] standard normals of the on-chip stream."""
     w = raw_words(seed, stream, mc0, num_mc, rows, cols)
-    w = w.reshape(num_mc, rows, -1, 4)
-    n0, n1 = box_muller(w[..., 0], w[..., 1])
-    n2, n3 = box_muller(w[..., 2], w[..., 3])
-    out = np.stack([n0, n1, n2, n3], -1).reshape(num_mc, rows, -1)
+    n_cos, n_sin = box_muller(w)                       # word j -> columns 2j, 2j+1
+    out = np.stack([n_cos, n_sin], -1).reshape(num_mc, rows, -1)
     return out[:, :, :cols]
 
 

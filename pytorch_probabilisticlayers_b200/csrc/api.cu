@@ -25,9 +25,10 @@ int cuda_fail(cudaError_t e, const char* what) {
   return PL_ERR_CUDA;
 }
 
-// out[mc][row][col] (normals) or out[mc][row][4*groups] (raw words); one thread per 4-group
+// out[mc][row][col] (normals) or out[mc][row][4*ceil(cols/8)] (raw Philox words, one call per 8
+// columns); one thread per 4 columns
 __global__ void eps_dump_kernel(Sampler s, int num_mc, int rows, int cols, void* out, int raw) {
-  const int groups = (cols + 3) / 4;
+  const int groups = 2 * ((cols + 7) / 8);
   const int64_t total = (int64_t)num_mc * rows * groups;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -35,8 +36,9 @@ __global__ void eps_dump_kernel(Sampler s, int num_mc, int rows, int cols, void*
     const int r = (int)((t / groups) % rows);
     const int m = (int)(t / ((int64_t)groups * rows));
     if (raw) {
-      const uint4 w = philox4x32_10(g, r, s.mc_offset + m, s.stream, s.k0, s.k1);
-      uint32_t* o = (uint32_t*)out + ((int64_t)m * rows + r) * (4 * groups) + 4 * g;
+      if (g & 1) continue;   // one Philox call per 8 columns
+      const uint4 w = philox4x32_10(g >> 1, r, s.mc_offset + m, s.stream, s.k0, s.k1);
+      uint32_t* o = (uint32_t*)out + ((int64_t)m * rows + r) * (2 * groups) + 2 * g;
       o[0] = w.x; o[1] = w.y; o[2] = w.z; o[3] = w.w;
     } else {
       const float4 n = eps4(s, m, r, g);
@@ -68,7 +70,7 @@ extern "C" int pl_eps_dump(uint64_t seed, uint32_t stream_id, uint32_t mc_global
   using namespace pl;
   PL_CHECK_ARG(out, "pl_eps_dump: NULL out");
   PL_CHECK_ARG(num_mc >= 0 && rows >= 0 && cols >= 0, "pl_eps_dump: negative size");
-  const int64_t total = (int64_t)num_mc * rows * ((cols + 3) / 4);
+  const int64_t total = (int64_t)num_mc * rows * (2 * ((cols + 7) / 8));
   if (total == 0) return PL_OK;
   Sampler s;
   s.k0 = (uint32_t)(seed & 0xffffffffu);

@@ -77,20 +77,21 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return make_uint4(c0, c1, c2, c3);
 }
 
-// float in [1,2) from the top 23 bits
-__device__ __forceinline__ float unit_float(uint32_t u) {
-  return __uint_as_float((u >> 9) | 0x3F800000u);
-}
-
-// one Box-Muller pair: f = 2 - t(u_r) in (0,1], r = sqrt(-2 ln f), theta = 2pi t(u_a) - 3pi
-__device__ __forceinline__ void box_muller(uint32_t u_r, uint32_t u_a, float& n_cos, float& n_sin) {
-  // MUFU-rate math (lg2 / sqrt / sin / cos .approx): f is a normal number in [2^-23, 1], so no
-  // denormal or slow-path handling is needed
-  const float f = 2.0f - unit_float(u_r);
+// One Box-Muller pair from ONE 32-bit word: radius from the top 20 bits, angle from the low 12.
+//   f = 2 - t20 in (0,1] (2^-20 steps, |eps| <= 5.27), r = sqrt(-2 ln f)
+//   theta = 2 pi t12 - 3 pi in (-pi, pi) on a 4096-point mid-bin grid
+// The angle grid is a midpoint rule over a smooth periodic integrand, so the marginals stay Gaussian
+// to far below fp32 resolution; what is given up is 12 bits of each pair's direction, what is gained
+// is 8 normals per Philox call instead of 4 (the 32x32->64 multiplies of Philox are the slowest part
+// of the sampler on this chip: tools/sampler_bench.cu, profiles/r01_experiments.md).
+// MUFU-rate math (lg2 / sqrt / sin / cos .approx): f is a normal number, no slow paths needed.
+__device__ __forceinline__ void box_muller(uint32_t w, float& n_cos, float& n_sin) {
+  const float f = 2.0f - __uint_as_float(((w >> 12) << 3) | 0x3F800000u);
+  const float t = __uint_as_float(((w & 0xFFFu) << 11) | 0x3F800400u);
   float lg, r, sn, cs;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(f));
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg));
-  const float theta = fmaf(unit_float(u_a), 6.283185307179586f, -9.42477796076938f);
+  const float theta = fmaf(t, 6.283185307179586f, -9.42477796076938f);
   asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(theta));
   asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(theta));
   n_cos = r * cs;
@@ -113,12 +114,23 @@ __host__ __device__ inline Sampler make_sampler(uint64_t seed, uint32_t layer_id
   return s;
 }
 
-// 4 standard normals for columns 4*group .. 4*group+3 of `row` of MC sample `mc` (local index)
-__device__ __forceinline__ float4 eps4(const Sampler& s, uint32_t mc, uint32_t row, uint32_t group) {
-  const uint4 w = philox4x32_10(group, row, s.mc_offset + mc, s.stream, s.k0, s.k1);
+// 8 standard normals for columns 8*group8 .. 8*group8+7 of `row` of MC sample `mc` (local index):
+// Philox counter (group8, row, global mc, stream); word j -> columns 8*group8 + 2j, +2j+1
+__device__ __forceinline__ void eps8(const Sampler& s, uint32_t mc, uint32_t row, uint32_t group8,
+                                     float (&e)[8]) {
+  const uint4 w = philox4x32_10(group8, row, s.mc_offset + mc, s.stream, s.k0, s.k1);
+  box_muller(w.x, e[0], e[1]);
+  box_muller(w.y, e[2], e[3]);
+  box_muller(w.z, e[4], e[5]);
+  box_muller(w.w, e[6], e[7]);
+}
+
+// 4 of them: columns 4*group4 .. +3 (the lower or upper half of an 8-group; fp32 / bias / dump paths)
+__device__ __forceinline__ float4 eps4(const Sampler& s, uint32_t mc, uint32_t row, uint32_t group4) {
+  const uint4 w = philox4x32_10(group4 >> 1, row, s.mc_offset + mc, s.stream, s.k0, s.k1);
   float4 n;
-  box_muller(w.x, w.y, n.x, n.y);
-  box_muller(w.z, w.w, n.z, n.w);
+  box_muller((group4 & 1) ? w.z : w.x, n.x, n.y);
+  box_muller((group4 & 1) ? w.w : w.y, n.z, n.w);
   return n;
 }
 

@@ -325,7 +325,7 @@ def eps_dump(seed, stream_id, mc_global_offset, num_mc, rows, cols, device, raw=
     """The on-chip eps stream, materialised (test bridge for src/ProbabilisticLayers.py:835)."""
     lib = _cabi.lib()
     if raw:
-        out = torch.empty((num_mc, rows, 4 * ((cols + 3) // 4)), dtype=torch.int32, device=device)
+        out = torch.empty((num_mc, rows, 4 * ((cols + 7) // 8)), dtype=torch.int32, device=device)
     else:
         out = torch.empty((num_mc, rows, cols), dtype=torch.float32, device=device)
     with torch.cuda.device(device):
