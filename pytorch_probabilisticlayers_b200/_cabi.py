@@ -13,7 +13,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpl_b200.so")
+# PL_B200_LIB: developer override used by tools/build_probe.sh to time instrumented builds
+LIB_PATH = os.environ.get("PL_B200_LIB") or os.path.join(_HERE, "lib", "libpl_b200.so")
 
 PL_OK = 0
 PREC_FP32, PREC_BF16, PREC_TF32 = 0, 1, 2

@@ -85,9 +85,17 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 // is 8 normals per Philox call instead of 4 (the 32x32->64 multiplies of Philox are the slowest part
 // of the sampler on this chip: tools/sampler_bench.cu, profiles/r01_experiments.md).
 // MUFU-rate math (lg2 / sqrt / sin / cos .approx): f is a normal number, no slow paths needed.
+// a constant the compiler must keep in a register: (x & mask) | bits then folds into ONE 3-input LOP3
+// instead of two immediate-operand LOP3s (the sampler is issue/power bound; 8 such pairs per Philox call)
+__device__ __forceinline__ uint32_t reg_const(uint32_t c) {
+  uint32_t r;
+  asm("mov.b32 %0, %1;" : "=r"(r) : "r"(c));
+  return r;
+}
 __device__ __forceinline__ void box_muller(uint32_t w, float& n_cos, float& n_sin) {
-  const float f = 2.0f - __uint_as_float(((w >> 12) << 3) | 0x3F800000u);
-  const float t = __uint_as_float(((w & 0xFFFu) << 11) | 0x3F800400u);
+  // f: top 20 bits -> mantissa bits [22:3] of a float in [1,2); t: low 12 bits -> mantissa bits [22:11], mid-bin
+  const float f = 2.0f - __uint_as_float(((w >> 9) & reg_const(0x007FFFF8u)) | reg_const(0x3F800000u));
+  const float t = __uint_as_float(((w << 11) & reg_const(0x007FF800u)) | reg_const(0x3F800400u));
   float lg, r, sn, cs;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(f));
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg));

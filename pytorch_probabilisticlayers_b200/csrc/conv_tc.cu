@@ -200,7 +200,7 @@ static int conv_geom(const pl_conv2d_args* a, ConvGeom& g, const char* who) {
 }
 
 struct ConvScratch {
-  float* sigma;            // [cout*K]
+  float* sigma;            // packed {mu|sigma} bf16 groups of the [cout, K] weight matrix
   float* bias;             // [mc*cout] sampled bias (fwd) / column sums (bwd)
   __nv_bfloat16* A;        // [mcx*M*Kp]
   __nv_bfloat16* dyt;      // [mc*M*Coutp]        (bwd)
@@ -212,7 +212,7 @@ static ConvScratch conv_carve(const ConvGeom& g, void* base, bool backward, bool
   uint8_t* b = (uint8_t*)(((uintptr_t)base + 255) & ~(uintptr_t)255);
   ConvScratch w;
   size_t off = 0;
-  w.sigma = (float*)(b + off); off += align256((size_t)g.cout * g.K * 4);
+  w.sigma = (float*)(b + off); off += align256(pack_bytes((size_t)g.cout, (size_t)g.K));
   w.bias = (float*)(b + off); off += align256((size_t)g.mc * g.cout * 4);
   if (state) {   // the im2col matrix lives in the caller's forward->backward state buffer
     w.A = (__nv_bfloat16*)(((uintptr_t)state + 255) & ~(uintptr_t)255);
@@ -260,8 +260,8 @@ int conv_fwd_tc_launch(const pl_conv2d_args* a) {
   }
   ConvScratch w = conv_carve(g, a->workspace, false, false, a->fwd_state);
   const int64_t nw = (int64_t)g.cout * g.K;
-  softplus_kernel<<<ew_grid(nw, 1024), 256, 0, st>>>(a->w_rho, w.sigma, nw);
-  PL_LAUNCH_CHECK("softplus_kernel");
+  rc = prep_params(a->w_mu, a->w_rho, w.sigma, g.cout, g.K, false, st);
+  if (rc != PL_OK) return rc;
   sample_bias_kernel<<<ew_grid((int64_t)g.mc * ((g.cout + 3) / 4), 256), 256, 0, st>>>(
       a->b_mu, a->b_rho, a->eps_b, make_sampler(a->seed, a->layer_id, true, a->mc_global_offset), g.mc,
       g.cout, w.bias);
@@ -275,7 +275,7 @@ int conv_fwd_tc_launch(const pl_conv2d_args* a) {
   p.mc = g.mc; p.rows = (int)g.M; p.ndim = g.cout; p.kdim = g.K;
   p.w_in = g.cout; p.w_out = g.K;
   p.a_mc_rows = g.mcx == 1 ? 0 : g.M;
-  p.w_mu = a->w_mu; p.w_sigma = w.sigma; p.eps_w = a->eps_w;
+  p.w_mu = a->w_mu; p.w_sigma = w.sigma; p.w_pack = (const uint4*)w.sigma; p.eps_w = a->eps_w;
   p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
   p.bias = w.bias;
   p.out = a->y;
@@ -352,8 +352,8 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     PL_LAUNCH_CHECK("dw_tc");
   }
   if (a->dx) {
-    softplus_kernel<<<ew_grid(nw, 1024), 256, 0, st>>>(a->w_rho, w.sigma, nw);
-    PL_LAUNCH_CHECK("softplus_kernel");
+    rc = prep_params(a->w_mu, a->w_rho, w.sigma, g.cout, g.K, false, st);
+    if (rc != PL_OK) return rc;
     CUtensorMap tm;
     rc = make_tmap_bf16(&tm, w.dyt, (uint64_t)g.mc * g.M, (uint64_t)g.Coutp, 128, kBK);
     if (rc != PL_OK) return rc;
@@ -361,7 +361,7 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     p.mc = g.mc; p.rows = (int)g.M; p.ndim = g.K; p.kdim = g.cout;
     p.w_in = g.cout; p.w_out = g.K;
     p.a_mc_rows = g.M;
-    p.w_mu = a->w_mu; p.w_sigma = w.sigma; p.eps_w = a->eps_w;
+    p.w_mu = a->w_mu; p.w_sigma = w.sigma; p.w_pack = (const uint4*)w.sigma; p.eps_w = a->eps_w;
     p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
     p.bias = nullptr;
     p.out = w.dA;                 // [mc][K][M]: K-major so that col2im reads contiguous pixels

@@ -25,7 +25,8 @@
 
 namespace pl {
 
-// forward->backward state: sigma [I*O] f32 | x as bf16 [x_rows*I]
+// forward->backward state: parameters as the kernels read them (bf16: packed {mu|sigma} groups of 8,
+// tf32: sigma [I*O] f32) | x as bf16 [x_rows*I]
 struct TcState {
   float* sigma;
   __nv_bfloat16* x_bf16;
@@ -47,7 +48,7 @@ static TcState carve_state(const pl_linear_args* a, void* base) {
   uint8_t* b = (uint8_t*)(((uintptr_t)base + 255) & ~(uintptr_t)255);
   TcState s;
   size_t off = 0;
-  s.sigma = (float*)(b + off); off += align256(I * O * 4);
+  s.sigma = (float*)(b + off); off += align256(std::max(I * O * 4, pack_bytes(I, O)));
   s.x_bf16 = (__nv_bfloat16*)(b + off); off += align256(x_rows * I * 2);
   s.total = off + 256;
   return s;
@@ -129,9 +130,9 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   const TcState state = a->fwd_state ? carve_state(a, a->fwd_state) : w.st;
   const int64_t I = a->in_features, O = a->out_features, MC = a->mc, B = a->batch;
   const int64_t x_rows = a->x_mc_stride == 0 ? B : MC * B;
-  softplus_kernel<<<ew_grid(I * O, 1024), 256, 0, st>>>(a->w_rho, state.sigma, I * O);
-  PL_LAUNCH_CHECK("softplus_kernel");
   const bool tf32 = a->precision == PL_PREC_TF32;   // fp32 operands straight from the caller's tensors
+  rc = prep_params(a->w_mu, a->w_rho, state.sigma, I, O, tf32, st);
+  if (rc != PL_OK) return rc;
   PL_CHECK_ARG(!tf32 || !(a->x_lp || a->y_lp), "pl_linear_fwd: bf16 activation chaining needs PL_PREC_BF16");
   if (!tf32 && !a->x_lp) {
     cast_bf16_kernel<<<ew_grid(x_rows * I / 8, 1024), 256, 0, st>>>(a->x, state.x_bf16, x_rows * I / 8);
@@ -152,7 +153,7 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   p.mc = (int)MC; p.rows = (int)B; p.ndim = (int)O; p.kdim = (int)I;
   p.w_in = (int)I; p.w_out = (int)O;
   p.a_mc_rows = a->x_mc_stride == 0 ? 0 : B;
-  p.w_mu = a->w_mu; p.w_sigma = state.sigma; p.eps_w = a->eps_w;
+  p.w_mu = a->w_mu; p.w_sigma = state.sigma; p.w_pack = (const uint4*)state.sigma; p.eps_w = a->eps_w;
   p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
   p.bias = a->b_mu ? w.bias : nullptr;
   p.out = a->y;
@@ -187,8 +188,8 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
   const int64_t x_rows = a->x_mc_stride == 0 ? B : MC * B;
   if (!have_state) {
     if (a->dx || a->dx_lp) {
-      softplus_kernel<<<ew_grid(I * O, 1024), 256, 0, st>>>(a->w_rho, state.sigma, I * O);
-      PL_LAUNCH_CHECK("softplus_kernel");
+      rc = prep_params(a->w_mu, a->w_rho, state.sigma, I, O, tf32, st);
+      if (rc != PL_OK) return rc;
     }
     if (a->dw_mu && !tf32 && !a->x_lp) {
       cast_bf16_kernel<<<ew_grid(x_rows * I / 8, 1024), 256, 0, st>>>(a->x, state.x_bf16, x_rows * I / 8);
@@ -225,7 +226,7 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
     p.mc = (int)MC; p.rows = (int)B; p.ndim = (int)I; p.kdim = (int)O;
     p.w_in = (int)I; p.w_out = (int)O;
     p.a_mc_rows = B;
-    p.w_mu = a->w_mu; p.w_sigma = state.sigma; p.eps_w = a->eps_w;
+    p.w_mu = a->w_mu; p.w_sigma = state.sigma; p.w_pack = (const uint4*)state.sigma; p.eps_w = a->eps_w;
     p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
     p.bias = nullptr;
     p.out = a->dx;

@@ -25,7 +25,8 @@ struct TcGemmParams {
   int w_in, w_out;              // weight matrix [I, O]
   int64_t a_mc_rows;            // rows per MC sample in the A tensor map (0 => broadcast input)
   const float* w_mu;            // [I, O]
-  const float* w_sigma;         // softplus(rho), [I, O]
+  const float* w_sigma;         // softplus(rho), [I, O]                              (tf32 kernels)
+  const uint4* w_pack;          // bf16 kernels: [I][ceil(O/8)] x {8 mu bf16 | 8 sigma bf16}, zero padded
   const float* eps_w;           // optional injected eps [mc, I, O]
   Sampler sw;
   const float* bias;            // optional sampled bias [mc, ndim] (forward only)
@@ -49,6 +50,45 @@ static __global__ void __launch_bounds__(256) softplus_kernel(const float* __res
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
     sigma[i] = softplus_f(rho[i]);
 }
+
+// bf16 kernels read the variational parameters as packed bf16: per weight row, per group of 8 columns
+// (= one Philox call), 16 bytes of mu followed by 16 bytes of sigma = softplus(rho).  Halves the
+// L2->SM traffic of the fused kernels (which run at the L2 slice throughput cap with fp32 parameters) and
+// lets the generator finish W = mu + sigma*eps with one packed HFMA2.BF16 per two weights.
+// Columns >= cols of the last group are zero (the operand tile must hold zeros there anyway).
+static __global__ void __launch_bounds__(256) pack_mu_sigma_kernel(const float* __restrict__ mu,
+                                                            const float* __restrict__ rho,
+                                                            uint4* __restrict__ pack, int rows, int cols) {
+  const int groups = (cols + 7) >> 3;
+  const int64_t n = (int64_t)rows * groups;
+  const bool vec = (cols & 3) == 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int r = (int)(i / groups), c = (int)(i - (int64_t)r * groups) * 8;
+    const int64_t idx = (int64_t)r * cols + c;
+    float m[8], sg[8];
+    if (vec && c + 8 <= cols) {
+      const float4 m0 = __ldg(reinterpret_cast<const float4*>(mu + idx)),
+                   m1 = __ldg(reinterpret_cast<const float4*>(mu + idx) + 1),
+                   r0 = __ldg(reinterpret_cast<const float4*>(rho + idx)),
+                   r1 = __ldg(reinterpret_cast<const float4*>(rho + idx) + 1);
+      m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w; m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
+      sg[0] = softplus_f(r0.x); sg[1] = softplus_f(r0.y); sg[2] = softplus_f(r0.z); sg[3] = softplus_f(r0.w);
+      sg[4] = softplus_f(r1.x); sg[5] = softplus_f(r1.y); sg[6] = softplus_f(r1.z); sg[7] = softplus_f(r1.w);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = c + j < cols;
+        m[j] = ok ? __ldg(mu + idx + j) : 0.f;
+        sg[j] = ok ? softplus_f(__ldg(rho + idx + j)) : 0.f;
+      }
+    }
+    pack[2 * i] = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]),
+                             pack_bf16x2(m[6], m[7]));
+    pack[2 * i + 1] = make_uint4(pack_bf16x2(sg[0], sg[1]), pack_bf16x2(sg[2], sg[3]),
+                                 pack_bf16x2(sg[4], sg[5]), pack_bf16x2(sg[6], sg[7]));
+  }
+}
+static inline size_t pack_bytes(size_t rows, size_t cols) { return rows * ((cols + 7) / 8) * 32; }
 
 // fp32 -> bf16, 8 elements per thread per iteration (n % 8 == 0, 16-byte aligned)
 static __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src,
@@ -182,13 +222,218 @@ static __global__ void __launch_bounds__(128) bias_grad_tc_kernel(const float* _
   db_rho[o] = ar * sigmoid_f(b_rho[o]);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// W-tile generator shared by the 1-CTA and 2-CTA kernels.  A k-block of the weight operand is
+// [128 n x kBKe k]; it is cut into groups of 8 consecutive o (the unit of one Philox call, 8 normals):
+// along n for the forward (operand MN-major), along k for dX (operand K-major).  512 generator threads
+// own 2 groups each per k-block in bf16 (64-k blocks) and 1 in tf32 (32-k blocks).  load() issues the
+// mu / sigma (/ injected eps) loads of a k-block, emit() turns them into the swizzled smem operand.
+// ---------------------------------------------------------------------------------------------
+#ifndef PL_STAGES_A4
+#define PL_STAGES_A4 2   // A-ring depth of the MT=4 kernels (64 KB per stage)
+#endif
+#ifndef PL_STAGES_B
+#define PL_STAGES_B 4    // generated-operand ring depth (16 KB per stage)
+#endif
+#ifndef PL_PROBE_W
+#define PL_PROBE_W 0     // tools/build_probe.sh builds instrumented copies with 1 / 2 (never the product)
+#endif
+template <bool kDx, bool kInjected, bool kTf32>
+struct WGen {
+  static constexpr int kGr = kTf32 ? 1 : 2;
+  static constexpr int kBKe = kTf32 ? 32 : 64;
+  int wrow[kGr], wcol;   // weight coordinates of the thread's groups at k-block 0
+  uint32_t soff[kGr];    // byte offset of the group inside the smem operand tile
+  float4 mu[kTf32 ? kGr : 1][2], sg[kTf32 ? kGr : 1][2];   // tf32: fp32 parameters
+  uint4 pk[kTf32 ? 1 : kGr][2];                            // bf16: packed {8 mu | 8 sigma}
+  float4 ep[kInjected ? kGr : 1][2];
+  int row[kGr], col;
+
+  // nb0: first weight index along the operand's n axis handled by this CTA
+  __device__ __forceinline__ void init(int gw, int lane, int nb0) {
+#pragma unroll
+    for (int r = 0; r < kGr; ++r) {
+      if (!kDx) {
+        // group = 8 n at one k.  bf16: k = 2 gw + lane/16 + 32 r, n = 8 (lane%16); MN-major SW128:
+        //   [n/64]*8192 + [k/8]*1024 + (k%8)*128 + (((n%64)/8) ^ (k%8))*16
+        // tf32: k = 2 gw + lane/16, n = 8 (lane%16); SWIZZLE_128B_BASE32B:
+        //   [n/32]*4096 + [k/4]*512 + (k%4)*128 + (((n%32)/8) ^ (k%4))*32   (one 32-byte chunk)
+        const int k = 2 * gw + (lane >> 4) + 32 * r, n8 = lane & 15;
+        wrow[r] = k;
+        if (kTf32)
+          soff[r] = (uint32_t)((n8 >> 2) * 4096 + (k >> 2) * 512 + (k & 3) * 128 + (((n8 & 3) ^ (k & 3)) << 5));
+        else
+          soff[r] = (uint32_t)((n8 >> 3) * 8192 + (k >> 3) * 1024 + (k & 7) * 128 + (((n8 & 7) ^ (k & 7)) << 4));
+      } else {
+        // group = 8 k at one n.  K-major SW128: n*128 + ((16-byte chunk of k) ^ (n%8))*16
+        // bf16: n = 4 gw + lane/8 + 64 r, k = 8 (lane%8) (one chunk);
+        // tf32: n = 8 gw + lane/4, k = 8 (lane%4) (two chunks 2c, 2c+1)
+        const int n = kTf32 ? 8 * gw + (lane >> 2) : 4 * gw + (lane >> 3) + 64 * r;
+        wrow[r] = nb0 + n;
+        soff[r] = (uint32_t)(n * 128);      // chunk term added in emit()
+      }
+    }
+    wcol = kDx ? 8 * (kTf32 ? (lane & 3) : (lane & 7)) : nb0 + 8 * (lane & 15);
+  }
+
+  template <bool kFull>
+  __device__ __forceinline__ void load(const TcGemmParams& p, int mc, int k0) {
+    col = kDx ? k0 + wcol : wcol;
+    const float* eps_base = kInjected ? p.eps_w + (int64_t)mc * p.w_in * p.w_out : nullptr;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int pack_groups = (p.w_out + 7) >> 3;
+#pragma unroll
+    for (int r = 0; r < kGr; ++r) {
+      row[r] = kDx ? wrow[r] : k0 + wrow[r];
+      const bool ok = kFull || (row[r] < p.w_in && col < p.w_out);
+#if PL_PROBE_W == 1      // probe: all parameter loads hit one 64 KB window (L1/L2-resident)
+      const int64_t idx = ((int64_t)row[r] * p.w_out + col) & 0x3FF8;
+#else
+      const int64_t idx = (int64_t)row[r] * p.w_out + col;
+#endif
+      if (!kTf32) {
+        // packed parameters: always two aligned 16-byte loads; the pack is zero beyond w_out
+        const uint4* src = p.w_pack + ((int64_t)row[r] * pack_groups + (col >> 3)) * 2;
+#if PL_PROBE_W == 2      // probe: no parameter loads at all
+        pk[r][0] = make_uint4(0x3dcc3dcc, 0x3dcc3dcc, 0x3dcc3dcc, 0x3dcc3dcc);
+        pk[r][1] = make_uint4(0x3c233c23, 0x3c233c23, 0x3c233c23, 0x3c233c23);
+#else
+        const uint4 zz = make_uint4(0, 0, 0, 0);
+        pk[r][0] = ok ? __ldg(src) : zz;
+        pk[r][1] = ok ? __ldg(src + 1) : zz;
+#endif
+        if (kInjected) {
+          float e8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) e8[j] = (ok && col + j < p.w_out) ? __ldg(eps_base + idx + j) : 0.f;
+          ep[r][0] = make_float4(e8[0], e8[1], e8[2], e8[3]);
+          ep[r][1] = make_float4(e8[4], e8[5], e8[6], e8[7]);
+        }
+        continue;
+      }
+      if (kFull || (p.w_aligned && col + 8 <= p.w_out)) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mu[r][h] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_mu + idx) + h) : z;
+          sg[r][h] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_sigma + idx) + h) : z;
+          if (kInjected) ep[r][h] = ok ? __ldg(reinterpret_cast<const float4*>(eps_base + idx) + h) : z;
+        }
+      } else {   // rows not 16-byte aligned / ragged last group (conv K = Cin*k*k): scalar loads
+        float m8[8], s8[8], e8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool okj = ok && col + j < p.w_out;
+          m8[j] = okj ? __ldg(p.w_mu + idx + j) : 0.f;
+          s8[j] = okj ? __ldg(p.w_sigma + idx + j) : 0.f;
+          e8[j] = (kInjected && okj) ? __ldg(eps_base + idx + j) : 0.f;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mu[r][h] = make_float4(m8[4 * h], m8[4 * h + 1], m8[4 * h + 2], m8[4 * h + 3]);
+          sg[r][h] = make_float4(s8[4 * h], s8[4 * h + 1], s8[4 * h + 2], s8[4 * h + 3]);
+          if (kInjected) ep[r][h] = make_float4(e8[4 * h], e8[4 * h + 1], e8[4 * h + 2], e8[4 * h + 3]);
+        }
+      }
+    }
+  }
+
+  // noise(): eps of the groups loaded last (Philox + Box-Muller; independent of the parameter loads).
+  // bf16 keeps it as 4 packed bf16 pairs per group, tf32 as 8 floats.
+  uint32_t nz[kTf32 ? 1 : kGr][4];
+  float nf[kTf32 ? kGr : 1][8];
+  // The Philox words of a k-block are drawn one iteration ahead (words()) so that, inside one basic block,
+  // the integer-multiply chain of block kb+1 interleaves with the MUFU-bound Box-Muller of block kb.
+  uint4 wd[kInjected ? 1 : kGr];
+  __device__ __forceinline__ void words(const TcGemmParams& p, int mc, int k0) {
+    if (kInjected) return;
+#pragma unroll
+    for (int r = 0; r < kGr; ++r) {
+      const int rown = kDx ? wrow[r] : k0 + wrow[r], coln = kDx ? k0 + wcol : wcol;
+      wd[r] = philox4x32_10((uint32_t)(coln >> 3), (uint32_t)rown, p.sw.mc_offset + (uint32_t)mc, p.sw.stream,
+                            p.sw.k0, p.sw.k1);
+    }
+  }
+  __device__ __forceinline__ void noise() {
+#pragma unroll
+    for (int r = 0; r < kGr; ++r) {
+      float e[8];
+      if (kInjected) {
+        e[0] = ep[r][0].x; e[1] = ep[r][0].y; e[2] = ep[r][0].z; e[3] = ep[r][0].w;
+        e[4] = ep[r][1].x; e[5] = ep[r][1].y; e[6] = ep[r][1].z; e[7] = ep[r][1].w;
+      } else {
+        box_muller(wd[r].x, e[0], e[1]);
+        box_muller(wd[r].y, e[2], e[3]);
+        box_muller(wd[r].z, e[4], e[5]);
+        box_muller(wd[r].w, e[6], e[7]);
+      }
+      if (kTf32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nf[r][j] = e[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nz[r][j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+      }
+    }
+  }
+  // pin: noise and next words are complete before the (volatile) barrier traffic that follows in program order
+  __device__ __forceinline__ void pin() {
+#pragma unroll
+    for (int r = 0; r < kGr; ++r) {
+      if (!kTf32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) asm volatile("" : "+r"(nz[r][j]));
+      }
+      if (!kInjected) asm volatile("" : "+r"(wd[r].x), "+r"(wd[r].y), "+r"(wd[r].z), "+r"(wd[r].w));
+    }
+  }
+
+  __device__ __forceinline__ void store(uint32_t dst, int lane) {
+#pragma unroll
+    for (int r = 0; r < kGr; ++r) {
+      float e[8];
+      if (kTf32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = nf[r][j];
+      }
+      if (!kTf32) {
+        // W = mu + sigma * eps, two weights per HFMA2.BF16 (eps rounded to bf16, one rounding of the result)
+        uint32_t a0 = dst + soff[r];
+        if (kDx) a0 += (uint32_t)(((lane & 7) ^ ((soff[r] >> 7) & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0),
+                     "r"(fma_bf16x2(pk[r][1].x, nz[r][0], pk[r][0].x)),
+                     "r"(fma_bf16x2(pk[r][1].y, nz[r][1], pk[r][0].y)),
+                     "r"(fma_bf16x2(pk[r][1].z, nz[r][2], pk[r][0].z)),
+                     "r"(fma_bf16x2(pk[r][1].w, nz[r][3], pk[r][0].w)) : "memory");
+        continue;
+      }
+      const float w0 = fmaf(sg[r][0].x, e[0], mu[r][0].x), w1 = fmaf(sg[r][0].y, e[1], mu[r][0].y),
+                  w2 = fmaf(sg[r][0].z, e[2], mu[r][0].z), w3 = fmaf(sg[r][0].w, e[3], mu[r][0].w),
+                  w4 = fmaf(sg[r][1].x, e[4], mu[r][1].x), w5 = fmaf(sg[r][1].y, e[5], mu[r][1].y),
+                  w6 = fmaf(sg[r][1].z, e[6], mu[r][1].z), w7 = fmaf(sg[r][1].w, e[7], mu[r][1].w);
+      // tf32: 8 fp32 words = two 16-byte chunks.  forward: both inside one 32-byte chunk of the BASE32B
+      // layout; dX: chunks 2c and 2c+1 of the K-major row, each XOR-swizzled with (n % 8)
+      uint32_t a0 = dst + soff[r], a1 = a0 + 16;
+      if (kDx) {
+        const int n7 = (soff[r] >> 7) & 7, c = 2 * (lane & 3);
+        a0 = dst + soff[r] + (uint32_t)((c ^ n7) << 4);
+        a1 = dst + soff[r] + (uint32_t)(((c + 1) ^ n7) << 4);
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(to_tf32(w0)), "r"(to_tf32(w1)),
+                   "r"(to_tf32(w2)), "r"(to_tf32(w3)) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(to_tf32(w4)), "r"(to_tf32(w5)),
+                   "r"(to_tf32(w6)), "r"(to_tf32(w7)) : "memory");
+    }
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // fused sample + GEMM (forward: kDx = false, B operand MN-major; dX: kDx = true, B operand K-major)
 // ---------------------------------------------------------------------------------------------
 template <int MT>
 struct TcCfg {
-  static constexpr int kStagesA = MT == 4 ? 2 : 4;
-  static constexpr int kStagesB = 4;
+  static constexpr int kStagesA = MT == 4 ? PL_STAGES_A4 : 4;
+  static constexpr int kStagesB = PL_STAGES_B;
   static constexpr int kABytes = MT * kSubTileBytes;
   static constexpr int kSmemBytes = kStagesA * kABytes + kStagesB * kSubTileBytes + 1024 /*bias + barriers*/
                                     + 1024 /*alignment slack*/;
@@ -216,7 +461,7 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
   const uint32_t tmem_slot = acc_full + 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform role index
   const int n0 = blockIdx.x * kBN;
   const int m0 = blockIdx.y * (MT * 128);
   const int mc = blockIdx.z;
@@ -300,98 +545,45 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
     __syncwarp();
   } else {
     // ===================== W-tile generators =====================
-    // operand element (n, k): forward W[i = k0+k][o = n0+n]; dX W[i = n0+n][o = k0+k].
-    // Each thread owns 4 groups of 4 consecutive o per k-block (one Philox call per group).
+    // operand element (n, k): forward W[i = k0+k][o = n0+n]; dX W[i = n0+n][o = k0+k]
     const int gw = warp - 2;  // 0..15
-    // groups (4 consecutive o) per thread and k-block: 4 (bf16, 64-k blocks) or 2 (tf32, 32-k blocks)
-    constexpr int kGr = kTf32 ? 2 : 4;
-    int wrow[kGr], wcol;      // weight coordinates of the thread's groups at k-block 0
-    uint32_t soff[kGr];
-#pragma unroll
-    for (int r = 0; r < kGr; ++r) {
-      if (!kDx) {
-        // k = gw + 16 r, n = 4 lane.  MN-major SW128 (bf16: 64-col groups, tf32: 32-col groups):
-        // [n/G]*LBO + [k/8]*1024 + (k%8)*128 + ((16-byte chunk of n in its group) ^ (k%8))*16 + ...
-        wrow[r] = gw + 16 * r;
-        if (kTf32)   // [n/32]*4096 + [k/4]*512 + (k%4)*128 + (((n%32)/8) ^ (k%4))*32 + (n%8)*4
-          soff[r] = (uint32_t)((lane >> 3) * 4096 + ((gw >> 2) + 4 * r) * 512 + (gw & 3) * 128 +
-                               ((((lane & 7) >> 1) ^ (gw & 3)) << 5) + ((lane & 1) << 4));
-        else
-          soff[r] = (uint32_t)((lane >> 4) * 8192 + ((gw >> 3) + 2 * r) * 1024 + (gw & 7) * 128 +
-                               ((((lane & 15) >> 1) ^ (gw & 7)) << 4) + ((lane & 1) << 3));
-      } else {
-        // K-major SW128: n*128 + ((16-byte chunk of k) ^ (n%8))*16 + ...
-        // bf16: n = 8 gw + 2 r + lane/16, k = 4 (lane%16);  tf32: n = 8 gw + 4 r + lane/8, k = 4 (lane%8)
-        const int n = kTf32 ? 8 * gw + 4 * r + (lane >> 3) : 8 * gw + 2 * r + (lane >> 4);
-        wrow[r] = n0 + n;
-        if (kTf32) soff[r] = (uint32_t)(n * 128 + (((lane & 7) ^ (n & 7)) << 4));
-        else soff[r] = (uint32_t)(n * 128 + ((((lane & 15) >> 1) ^ (n & 7)) << 4) + ((lane & 1) << 3));
-      }
-    }
-    wcol = kDx ? 4 * (kTf32 ? (lane & 7) : (lane & 15)) : n0 + 4 * lane;
-    const int64_t ldw = p.w_out;
-    const float* eps_base = kInjected ? p.eps_w + (int64_t)mc * p.w_in * p.w_out : nullptr;
-
-    auto gen_block = [&](int kb, auto full_tag) {
-      constexpr bool kFull = decltype(full_tag)::value;
-      const int s = kb % Cfg::kStagesB, ph = (kb / Cfg::kStagesB) & 1;
-      const int k0 = kb * kBKe;
-      float4 mu[kGr], sg[kGr], ep[kGr];
-      int row[kGr];
-      const int col = kDx ? k0 + wcol : wcol;
-#pragma unroll
-      for (int r = 0; r < kGr; ++r) {
-        row[r] = kDx ? wrow[r] : k0 + wrow[r];
-        const bool ok = kFull || (row[r] < p.w_in && col < p.w_out);
-        const int64_t idx = (int64_t)row[r] * ldw + col;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kFull || p.w_aligned) {
-          mu[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_mu + idx)) : z;
-          sg[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_sigma + idx)) : z;
-          if (kInjected) ep[r] = ok ? __ldg(reinterpret_cast<const float4*>(eps_base + idx)) : z;
-        } else {  // rows not 16-byte aligned / ragged last group (conv K = Cin*k*k): scalar loads
-          float m4[4], s4[4], e4[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const bool okj = ok && col + j < p.w_out;
-            m4[j] = okj ? __ldg(p.w_mu + idx + j) : 0.f;
-            s4[j] = okj ? __ldg(p.w_sigma + idx + j) : 0.f;
-            e4[j] = (kInjected && okj) ? __ldg(eps_base + idx + j) : 0.f;
-          }
-          mu[r] = make_float4(m4[0], m4[1], m4[2], m4[3]);
-          sg[r] = make_float4(s4[0], s4[1], s4[2], s4[3]);
-          if (kInjected) ep[r] = make_float4(e4[0], e4[1], e4[2], e4[3]);
-        }
-      }
-      mbar_wait(b_empty(s), ph ^ 1);
-      const uint32_t dst = sB + s * kSubTileBytes;
-#pragma unroll
-      for (int r = 0; r < kGr; ++r) {
-        float4 e;
-        if (kInjected) e = ep[r];
-        else e = eps4(p.sw, mc, row[r], col >> 2);
-        const float w0 = fmaf(sg[r].x, e.x, mu[r].x), w1 = fmaf(sg[r].y, e.y, mu[r].y),
-                    w2 = fmaf(sg[r].z, e.z, mu[r].z), w3 = fmaf(sg[r].w, e.w, mu[r].w);
-        if (kTf32) {
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + soff[r]), "r"(to_tf32(w0)),
-                       "r"(to_tf32(w1)), "r"(to_tf32(w2)), "r"(to_tf32(w3))
-                       : "memory");
-        } else {
-          const uint32_t lo = pack_bf16x2(w0, w1), hi = pack_bf16x2(w2, w3);
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + soff[r]), "r"(lo), "r"(hi) : "memory");
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_full(s));
-    };
+    WGen<kDx, kInjected, kTf32> gen;
+    gen.init(gw, lane, n0);
     // tiles fully inside the weight matrix take the predicate-free path
     const bool n_full = p.w_aligned && (kDx ? (n0 + kBN <= p.w_in) : (n0 + kBN <= p.w_out));
     const int k_extent = kDx ? p.w_out : p.w_in;
+    auto load_block = [&](int kb) {
+#if PL_PROBE_W != 3     // probe 3: barrier hand-shakes only (MMA + TMA pipeline floor)
+      if (n_full && (kb + 1) * kBKe <= k_extent) gen.template load<true>(p, mc, kb * kBKe);
+      else gen.template load<false>(p, mc, kb * kBKe);
+#endif
+    };
+    gen.words(p, mc, 0);
+    load_block(0);
     for (int kb = 0; kb < num_kb; ++kb) {
-      if (n_full && (kb + 1) * kBKe <= k_extent) gen_block(kb, std::true_type{});
-      else gen_block(kb, std::false_type{});
+      const int s = kb % Cfg::kStagesB, ph = (kb / Cfg::kStagesB) & 1;
+#if PL_PROBE_W != 3
+      gen.noise();                            // Box-Muller of this block ...
+      gen.words(p, mc, (kb + 1) * kBKe);      // ... interleaved with the Philox chain of the next one
+      gen.pin();
+#endif
+      // The previous k-block is published only now.  fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC:
+      // it waits for every outstanding memory operation of the warp, so it sits where the st.shared of the
+      // previous block and the parameter loads of this one (issued a whole noise() ago) have completed.
+      if (kb > 0) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_full((kb - 1) % Cfg::kStagesB));
+      }
+      mbar_wait(b_empty(s), ph ^ 1);
+#if PL_PROBE_W != 3
+      gen.store(sB + s * kSubTileBytes, lane);
+#endif
+      if (kb + 1 < num_kb) load_block(kb + 1);
     }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(b_full((num_kb - 1) % Cfg::kStagesB));
     // ===================== epilogue: TMEM -> registers -> HBM =====================
     mbar_wait(acc_full, 0);
     tc_fence_after_sync();
@@ -495,7 +687,7 @@ sampled_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams 
   const uint32_t tmem_slot = acc_full + 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform role index
   const uint32_t rank = cluster_ctarank();        // 0 = leader
   const int n0 = (blockIdx.x >> 1) * kTileN;      // pair tile: 256 output columns
   const int nb0 = n0 + (int)rank * 128;           // the 128 columns this CTA synthesises
@@ -574,76 +766,33 @@ sampled_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams 
   } else {
     // ===================== W-tile generators (both CTAs, own 128 columns) =====================
     const int gw = warp - 2;  // 0..15
-    int wrow[4], wcol;
-    uint32_t soff[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (!kDx) {
-        wrow[r] = gw + 16 * r;
-        soff[r] = (uint32_t)((lane >> 4) * 8192 + ((gw >> 3) + 2 * r) * 1024 + (gw & 7) * 128 +
-                             ((((lane & 15) >> 1) ^ (gw & 7)) << 4) + ((lane & 1) << 3));
-      } else {
-        const int n = 8 * gw + 2 * r + (lane >> 4);
-        wrow[r] = nb0 + n;
-        soff[r] = (uint32_t)(n * 128 + ((((lane & 15) >> 1) ^ (n & 7)) << 4) + ((lane & 1) << 3));
-      }
-    }
-    wcol = kDx ? 4 * (lane & 15) : nb0 + 4 * lane;
-    const int64_t ldw = p.w_out;
-    const float* eps_base = kInjected ? p.eps_w + (int64_t)mc * p.w_in * p.w_out : nullptr;
-
-    auto gen_block = [&](int kb, auto full_tag) {
-      constexpr bool kFull = decltype(full_tag)::value;
-      const int s = kb % Cfg::kStagesB, ph = (kb / Cfg::kStagesB) & 1;
-      const int k0 = kb * kBK;
-      float4 mu[4], sg[4], ep[4];
-      int row[4];
-      const int col = kDx ? k0 + wcol : wcol;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        row[r] = kDx ? wrow[r] : k0 + wrow[r];
-        const bool ok = kFull || (row[r] < p.w_in && col < p.w_out);
-        const int64_t idx = (int64_t)row[r] * ldw + col;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kFull || p.w_aligned) {
-          mu[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_mu + idx)) : z;
-          sg[r] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_sigma + idx)) : z;
-          if (kInjected) ep[r] = ok ? __ldg(reinterpret_cast<const float4*>(eps_base + idx)) : z;
-        } else {  // rows not 16-byte aligned / ragged last group (conv K = Cin*k*k): scalar loads
-          float m4[4], s4[4], e4[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const bool okj = ok && col + j < p.w_out;
-            m4[j] = okj ? __ldg(p.w_mu + idx + j) : 0.f;
-            s4[j] = okj ? __ldg(p.w_sigma + idx + j) : 0.f;
-            e4[j] = (kInjected && okj) ? __ldg(eps_base + idx + j) : 0.f;
-          }
-          mu[r] = make_float4(m4[0], m4[1], m4[2], m4[3]);
-          sg[r] = make_float4(s4[0], s4[1], s4[2], s4[3]);
-          if (kInjected) ep[r] = make_float4(e4[0], e4[1], e4[2], e4[3]);
-        }
-      }
-      mbar_wait(b_empty(s), ph ^ 1);
-      const uint32_t dst = sB + s * kSubTileBytes;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        float4 e;
-        if (kInjected) e = ep[r];
-        else e = eps4(p.sw, mc, row[r], col >> 2);
-        const uint32_t lo = pack_bf16x2(fmaf(sg[r].x, e.x, mu[r].x), fmaf(sg[r].y, e.y, mu[r].y));
-        const uint32_t hi = pack_bf16x2(fmaf(sg[r].z, e.z, mu[r].z), fmaf(sg[r].w, e.w, mu[r].w));
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + soff[r]), "r"(lo), "r"(hi) : "memory");
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(b_full(s), 0);   // signal the leader's barrier
-    };
+    WGen<kDx, kInjected, false> gen;
+    gen.init(gw, lane, nb0);
     const bool n_full = p.w_aligned && (kDx ? (nb0 + 128 <= p.w_in) : (nb0 + 128 <= p.w_out));
     const int k_extent = kDx ? p.w_out : p.w_in;
+    auto load_block = [&](int kb) {
+      if (n_full && (kb + 1) * kBK <= k_extent) gen.template load<true>(p, mc, kb * kBK);
+      else gen.template load<false>(p, mc, kb * kBK);
+    };
+    gen.words(p, mc, 0);
+    load_block(0);
     for (int kb = 0; kb < num_kb; ++kb) {
-      if (n_full && (kb + 1) * kBK <= k_extent) gen_block(kb, std::true_type{});
-      else gen_block(kb, std::false_type{});
+      const int s = kb % Cfg::kStagesB, ph = (kb / Cfg::kStagesB) & 1;
+      gen.noise();
+      gen.words(p, mc, (kb + 1) * kBK);
+      gen.pin();
+      if (kb > 0) {   // deferred publish of the previous k-block (see the 1-CTA kernel)
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(b_full((kb - 1) % Cfg::kStagesB), 0);   // the leader's barrier
+      }
+      mbar_wait(b_empty(s), ph ^ 1);
+      gen.store(sB + s * kSubTileBytes, lane);
+      if (kb + 1 < num_kb) load_block(kb + 1);
     }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(b_full((num_kb - 1) % Cfg::kStagesB), 0);
     // ===================== epilogue: this CTA's 128 rows of every sub-tile, all 256 columns ==========
     mbar_wait(acc_full, 0);
     tc_fence_after_sync();
@@ -733,7 +882,7 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
   const uint32_t tmem_slot = bar0 + 8u * (2 * kDwStages + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform role index
   const int o0 = blockIdx.x * 128, i0 = blockIdx.y * 128;
   const int mc_begin = ((int)blockIdx.z / p.kb_splits) * p.mc_per_split;
   const int mc_end = min(p.mc, mc_begin + p.mc_per_split);
@@ -834,32 +983,25 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
         tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + h * kCols + c * 16), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col = col0 + c * 16 + g * 4;
-          float4 e;
+        for (int g = 0; g < 2; ++g) {
+          const int col = col0 + c * 16 + g * 8;
+          float e[8];
           if (kInjected) {
-            e = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < p.w_in && col < p.w_out) {
-              const float* ep = p.eps_w + ((int64_t)mc * p.w_in + row) * p.w_out + col;
-              if (p.w_aligned) {
-                e = __ldg(reinterpret_cast<const float4*>(ep));
-              } else {
-                e.x = __ldg(ep);
-                if (col + 1 < p.w_out) e.y = __ldg(ep + 1);
-                if (col + 2 < p.w_out) e.z = __ldg(ep + 2);
-                if (col + 3 < p.w_out) e.w = __ldg(ep + 3);
-              }
-            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+              e[t] = (row < p.w_in && col + t < p.w_out)
+                         ? __ldg(p.eps_w + ((int64_t)mc * p.w_in + row) * p.w_out + col + t)
+                         : 0.f;
           } else {
-            e = eps4(p.sw, mc, row, col >> 2);
+            eps8(p.sw, mc, row, col >> 3, e);
           }
-          const int j = c * 16 + g * 4;
-          const float d0 = __uint_as_float(v[g * 4 + 0]), d1 = __uint_as_float(v[g * 4 + 1]),
-                      d2 = __uint_as_float(v[g * 4 + 2]), d3 = __uint_as_float(v[g * 4 + 3]);
-          acc_mu[j + 0] += d0; acc_rho[j + 0] = fmaf(d0, e.x, acc_rho[j + 0]);
-          acc_mu[j + 1] += d1; acc_rho[j + 1] = fmaf(d1, e.y, acc_rho[j + 1]);
-          acc_mu[j + 2] += d2; acc_rho[j + 2] = fmaf(d2, e.z, acc_rho[j + 2]);
-          acc_mu[j + 3] += d3; acc_rho[j + 3] = fmaf(d3, e.w, acc_rho[j + 3]);
+          const int j = c * 16 + g * 8;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float d = __uint_as_float(v[g * 8 + t]);
+            acc_mu[j + t] += d;
+            acc_rho[j + t] = fmaf(d, e[t], acc_rho[j + t]);
+          }
         }
       }
       tc_fence_before_sync();
@@ -999,6 +1141,20 @@ static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static inline int ew_grid(int64_t n, int per_block) {
   int64_t g = (n + per_block - 1) / per_block;
   return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+}
+
+// parameters in the form the fused kernels read: bf16 -> packed {mu|sigma} groups (pack_bytes), tf32 -> sigma f32
+static inline int prep_params(const float* mu, const float* rho, float* buf, int64_t rows, int64_t cols,
+                              bool tf32, cudaStream_t st) {
+  if (tf32) {
+    softplus_kernel<<<ew_grid(rows * cols, 1024), 256, 0, st>>>(rho, buf, rows * cols);
+    PL_LAUNCH_CHECK("softplus_kernel");
+  } else {
+    pack_mu_sigma_kernel<<<ew_grid(rows * ((cols + 7) / 8), 512), 256, 0, st>>>(mu, rho, (uint4*)buf, (int)rows,
+                                                                                  (int)cols);
+    PL_LAUNCH_CHECK("pack_mu_sigma_kernel");
+  }
+  return PL_OK;
 }
 
 // PL_TC_2CTA=1 selects the cta_group::2 kernels.  Measured on C4 (r01): 2.22 ms vs 1.78 ms per
