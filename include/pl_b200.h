@@ -100,6 +100,29 @@ int pl_adam_kl_step(float* p, const float* g, float* m, float* v, int64_t n, int
                     float prior_scale, float kl_scale, float lr, float beta1, float beta2, float eps,
                     int32_t step, double* kl_value, void* stream);
 
+/* ---- MC-first cross entropy + accuracy + gradient (replaces MC_CrossEntropyLoss.forward,
+ *      src/ProbabilisticLayers.py:32-43, MC_Accuracy, :46-90, and the autograd backward of both) ----
+ * pred [mc, batch, classes] fp32 logits, target [batch] int64 class ids shared by all MC samples.
+ * out[0] = sum over (mc, batch) of -log softmax(pred)[target]   (the caller scales: the reference's value
+ *          is out[0] / (mc*batch) * num_samples), out[1] = number of rows whose argmax equals the target
+ *          (lowest index wins ties, as torch.argmax).
+ * dpred (optional) [mc, batch, classes] = (softmax(pred) - onehot(target)) * grad_scale, i.e. the gradient of
+ *          grad_scale * out[0]; rows with a target outside [0, classes) contribute no loss and no -onehot.
+ * One launch, deterministic; workspace zero on first use and left zero (self-resetting ticket). */
+typedef struct pl_ce_args {
+  int32_t mc, batch, classes;
+  float grad_scale;
+  const float* pred;
+  const int64_t* target;
+  float* dpred;
+  float* out;
+  void* workspace;
+  size_t workspace_bytes;
+  void* stream;
+} pl_ce_args;
+size_t pl_mc_cross_entropy_workspace_bytes(void);
+int pl_mc_cross_entropy(const pl_ce_args* a);
+
 /* ---- BayesLinear / SIVILayer contraction (replaces VariationalNormal.rsample + torch.baddbmm /
  *      torch.bmm at src/ProbabilisticLayers.py:925-935 and :321-326, and their autograd) ------ */
 typedef struct pl_linear_args {

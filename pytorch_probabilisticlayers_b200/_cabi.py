@@ -24,6 +24,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32}
 EXPORTS = (
     "pl_version", "pl_last_error", "pl_launch_count", "pl_device_supported", "pl_eps_dump",
     "pl_kl_workspace_bytes", "pl_kl_fwd", "pl_kl_bwd", "pl_adam_kl_step",
+    "pl_mc_cross_entropy_workspace_bytes", "pl_mc_cross_entropy",
     "pl_linear_workspace_bytes", "pl_linear_state_bytes", "pl_linear_fwd", "pl_linear_bwd",
     "pl_conv2d_workspace_bytes", "pl_conv2d_state_bytes", "pl_conv2d_fwd", "pl_conv2d_bwd",
 )
@@ -62,6 +63,14 @@ class Conv2dArgs(C.Structure):
     ]
 
 
+class CeArgs(C.Structure):
+    _fields_ = [
+        ("mc", C.c_int32), ("batch", C.c_int32), ("classes", C.c_int32), ("grad_scale", C.c_float),
+        ("pred", C.c_void_p), ("target", C.c_void_p), ("dpred", C.c_void_p), ("out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("stream", C.c_void_p),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -97,6 +106,9 @@ def lib():
                 l.pl_adam_kl_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                               C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
                                               C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p]
+                l.pl_mc_cross_entropy_workspace_bytes.restype = C.c_size_t
+                l.pl_mc_cross_entropy.restype = C.c_int
+                l.pl_mc_cross_entropy.argtypes = [C.POINTER(CeArgs)]
                 l.pl_linear_workspace_bytes.restype = C.c_size_t
                 l.pl_linear_workspace_bytes.argtypes = [C.POINTER(LinearArgs)]
                 l.pl_linear_state_bytes.restype = C.c_size_t

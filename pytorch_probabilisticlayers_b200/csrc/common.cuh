@@ -142,6 +142,8 @@ __device__ __forceinline__ float4 eps4(const Sampler& s, uint32_t mc, uint32_t r
   return n;
 }
 
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

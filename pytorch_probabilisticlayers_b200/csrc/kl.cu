@@ -276,7 +276,6 @@ kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ rho,
   }
 }
 
-static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static inline int kl_grid(int64_t n) {
   const int64_t want = ceil_div64(n, (int64_t)kKlThreads * 4);

@@ -71,6 +71,71 @@ def _kl_workspace(device):
     return ws
 
 
+_CE_WS = {}
+
+
+def _ce_workspace(device):
+    """Zero-initialised, self-resetting ticket workspace of pl_mc_cross_entropy, one per (device, stream)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _CE_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_cabi.lib().pl_mc_cross_entropy_workspace_bytes()), dtype=torch.uint8, device=device)
+        _CE_WS[key] = ws
+    return ws
+
+
+def mc_cross_entropy_raw(pred, target, grad_scale=None):
+    """One pass over the [MC,B,C] logits: returns (out, dpred) with out = device tensor
+    [sum of -log p[target], number of argmax hits] and dpred = (softmax - onehot) * grad_scale
+    (None when grad_scale is None).  Reference: src/ProbabilisticLayers.py:32-43, :46-90."""
+    _cabi.require_cuda_f32(pred, "pred")
+    if pred.dim() != 3 or target.dim() != 1 or target.shape[0] != pred.shape[1]:
+        raise ValueError(f"pred must be [MC,B,C] and target [B], got {tuple(pred.shape)} and {tuple(target.shape)}")
+    lib = _cabi.lib()
+    pc = pred.contiguous()
+    tc = target.to(device=pred.device, dtype=torch.int64).contiguous()
+    mc, batch, classes = pc.shape
+    out = torch.empty(2, dtype=torch.float32, device=pred.device)
+    dpred = torch.empty_like(pc) if grad_scale is not None else None
+    ws = _ce_workspace(pred.device)
+    a = _cabi.CeArgs()
+    a.mc, a.batch, a.classes = mc, batch, classes
+    a.grad_scale = float(grad_scale) if grad_scale is not None else 0.0
+    a.pred, a.target, a.dpred, a.out = _cabi.ptr(pc), _cabi.ptr(tc), _cabi.ptr(dpred), _cabi.ptr(out)
+    a.workspace, a.workspace_bytes = _cabi.ptr(ws), ws.numel()
+    a.stream = _cabi.current_stream(pred.device)
+    with torch.cuda.device(pred.device):
+        _timed(f"mc_cross_entropy[{mc}x{batch}x{classes}]",
+               lambda: _cabi.check(lib.pl_mc_cross_entropy(C.byref(a)), "pl_mc_cross_entropy"),
+               ("bytes", 4.0 * pc.numel() * (2 if dpred is not None else 1)))
+    return out, dpred
+
+
+class _MCCrossEntropyFn(torch.autograd.Function):
+    """loss = num_samples * mean over (MC,B) of CE; the gradient is produced by the same kernel pass."""
+
+    @staticmethod
+    def forward(ctx, pred, target, num_samples):
+        rows = pred.shape[0] * pred.shape[1]
+        scale = float(num_samples) / max(rows, 1)
+        out, dpred = mc_cross_entropy_raw(pred, target, scale if ctx.needs_input_grad[0] else None)
+        ctx.save_for_backward(dpred)
+        ctx.mark_non_differentiable(out)
+        return out[0] * scale, out
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_out):
+        (dpred,) = ctx.saved_tensors
+        return dpred * g_loss, None, None
+
+
+def mc_cross_entropy(pred, target, num_samples):
+    """Returns (loss, out) with out[1] = number of correct argmax predictions (for MC_Accuracy without a
+    second pass over the logits)."""
+    return _MCCrossEntropyFn.apply(pred, target, num_samples)
+
+
 def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 

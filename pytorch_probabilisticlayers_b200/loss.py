@@ -1,8 +1,11 @@
 """Likelihood halves of the ELBO and the accuracy metric, MC-first
 (reference: src/ProbabilisticLayers_Loss.py:27-120, duplicated at src/ProbabilisticLayers.py:22-117).
 
-These are tiny compared with the layers: they stay torch ops
-on the device; MC_Accuracy returns a device tensor instead of forcing a ``.item()`` host sync.
+On CUDA MC_CrossEntropyLoss runs as ONE pass over the logits (csrc/ce.cu: online log-sum-exp, target
+pick, argmax and the gradient in the same sweep); the number of argmax hits
+of the last call is kept on ``.last_correct`` so ELBOTrainStep gets the accuracy without re-reading the
+logits.  MC_Accuracy returns a device tensor instead of forcing a ``.item()`` host sync.  MC_NLL and the
+CPU path of the cross entropy stay torch ops.
 """
 import math
 
@@ -24,6 +27,11 @@ class MC_CrossEntropyLoss(torch.nn.Module):
         assert target.dim() == 1, f'Targets should be of shape [BS] with each correct label but is only of shape {target.shape}'
         MC, BS, C = pred.shape
         assert target.shape == torch.Size([BS]), f"{target.shape=}"
+        if pred.is_cuda and pred.dtype == torch.float32:
+            from .functional import mc_cross_entropy
+            loss, out = mc_cross_entropy(pred, target, self.num_samples)
+            self.last_correct = out[1]
+            return loss
         # mean over MC*BS of the per-sample CE == CE against the MC-tiled targets, without
         # materialising target.repeat(MC)
         logp = F.log_softmax(pred, dim=-1)

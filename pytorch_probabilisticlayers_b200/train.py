@@ -28,7 +28,8 @@ import torch.distributed as dist
 from . import _cabi, layers
 from . import functional as PF
 from .layers import BayesConv2d, BayesLinear, SIVILayer
-from .loss import MC_Accuracy
+from .functional import mc_cross_entropy_raw
+from .loss import MC_Accuracy, MC_CrossEntropyLoss
 
 
 def collect_kl_div(net, kinds=(BayesLinear, SIVILayer)):
@@ -174,7 +175,15 @@ class ELBOTrainStep:
         self.flat.zero_()
         pred = self.net(x)
         inv = 1.0 / (self.num_samples * self.world)
-        ll = self.criterion(pred, y) * inv
+        # cross entropy on CUDA: value, accuracy and d(loss)/d(pred) from one pass over the logits (csrc/ce.cu)
+        fused_ce = isinstance(self.criterion, MC_CrossEntropyLoss) and pred.is_cuda and pred.dtype == torch.float32
+        if fused_ce:
+            rows = max(pred.shape[0] * pred.shape[1], 1)
+            scale = self.criterion.num_samples / rows * inv
+            ce_out, dpred = mc_cross_entropy_raw(pred.detach(), y, scale)
+            ll = ce_out[0] * scale
+        else:
+            ll = self.criterion(pred, y) * inv
         kl_graph = None      # KL terms that still need autograd (SIVI hyper-net, Laplace prior)
         kl_value = torch.zeros((), device=pred.device)
         for m in self.net.modules():
@@ -182,13 +191,23 @@ class ELBOTrainStep:
                 if m.kl_div.requires_grad:
                     kl_graph = m.kl_div if kl_graph is None else kl_graph + m.kl_div
                 kl_value = kl_value + m.kl_div.detach()
-        loss = ll if kl_graph is None else ll + kl_graph * inv
         with torch.no_grad():               # before backward: the tail slice is reduced last
             self.stats[0] = ll.detach()
             self.stats[1] = kl_value * inv
             if self.with_accuracy:
-                self.stats[2] = MC_Accuracy(pred.detach(), y)[0] / self.world
-        loss.backward()                     # overlap mode: hooks launch per-layer KL grad + all-reduce
+                if fused_ce:
+                    self.stats[2] = ce_out[1] / (rows * self.world)
+                else:
+                    self.stats[2] = MC_Accuracy(pred.detach(), y)[0] / self.world
+        # overlap mode: hooks launch per-layer KL grad + all-reduce during the backward
+        if fused_ce:
+            if kl_graph is None:
+                pred.backward(dpred)
+            else:
+                torch.autograd.backward([pred, kl_graph * inv], [dpred, None])
+        else:
+            loss = ll if kl_graph is None else ll + kl_graph * inv
+            loss.backward()
         if not self.overlap:
             for m in self.kl_layers:
                 self._kl_backward(m)

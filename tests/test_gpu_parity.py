@@ -348,6 +348,36 @@ def test_aux_layers_and_losses_match_reference(plb):
     assert rel_err(pr.grad.cpu().numpy(), l["nll_dpred"]) < 5e-5
 
 
+@pytest.mark.parametrize("mc,b,c", [(3, 5, 10), (2, 7, 7), (4, 16, 33), (2, 64, 1000), (1, 3, 4100), (8, 300, 12)])
+def test_fused_cross_entropy_matches_fp64_oracle(plb, mc, b, c):
+    """pl_mc_cross_entropy: loss, accuracy count and gradient from one pass, against the fp64 restatement of
+    MC_CrossEntropyLoss / MC_Accuracy (src/ProbabilisticLayers.py:32-90); deterministic across launches."""
+    from pytorch_probabilisticlayers_b200 import functional as PF
+    rng = np.random.default_rng(mc * 100 + c)
+    pred = (rng.standard_normal((mc, b, c)) * 3).astype(np.float32)
+    target = rng.integers(0, c, size=b)
+    pred[0, 0, :] = 0.25                       # an all-ties row: argmax must be index 0
+    ns = 1234
+    want_loss, want_d = cf.mc_cross_entropy(pred, target, ns)
+    want_hits = float((pred.argmax(-1) == target[None, :]).sum())
+    scale = ns / (mc * b)
+    out, d = PF.mc_cross_entropy_raw(dev(pred), torch.from_numpy(target).cuda(), scale)
+    out2, d2 = PF.mc_cross_entropy_raw(dev(pred), torch.from_numpy(target).cuda(), scale)
+    assert torch.equal(out, out2) and torch.equal(d, d2)
+    assert abs(out[0].item() * scale - want_loss) / abs(want_loss) < 1e-5
+    assert out[1].item() == want_hits
+    assert rel_err(d.cpu().numpy(), want_d) < 1e-5
+    # module path with autograd and a non-unit upstream gradient
+    p = dev(pred).requires_grad_(True)
+    crit = plb.MC_CrossEntropyLoss(ns)
+    (crit(p, torch.from_numpy(target).cuda()) * 0.5).backward()
+    assert rel_err(p.grad.cpu().numpy(), 0.5 * want_d) < 1e-5
+    assert crit.last_correct.item() == want_hits
+    # value only (no gradient requested)
+    out3, d3 = PF.mc_cross_entropy_raw(dev(pred), torch.from_numpy(target).cuda(), None)
+    assert d3 is None and torch.equal(out3, out)
+
+
 # ---------------------------------------------------------------------------------------------
 # end-to-end: the reference's train loop, step by step, eps injected
 # ---------------------------------------------------------------------------------------------
