@@ -214,19 +214,20 @@ def run_b200(args, wl):
     dims, mc_total, batch, ns = wl["dims"], wl["mc"], wl["batch"], wl["num_samples"]
     assert mc_total % world == 0
     mc_local = mc_total // world
-    if wl.get("conv"):
-        assert world == 1, "C3 couples MC samples through MC_BatchNorm2D: single GPU (replicas only)"
-        chans = [wl["in_dims"][0], 96, 128, 256, 128]
-        mods = [plb.MC_ExpansionLayer(num_MC=mc_local, input_dim=4)]
-        for li in range(4):
-            mods += [plb.BayesConv2d(chans[li], chans[li + 1], 5, stride=1, padding=2, num_MC=mc_local),
-                     plb.MC_BatchNorm2D(chans[li + 1]), torch.nn.LeakyReLU(), plb.MC_MaxPool2d(2, 2)]
-        mods += [plb.BayesAdaptiveInit_FlattenAndLinear(200), torch.nn.LeakyReLU(),
-                 plb.BayesLinear(200, dims[-1])]
-        net = torch.nn.Sequential(*mods).to(dev)
-        with torch.no_grad():      # the reference's dry run (experiments/BNN.py:253), on the device
-            net(torch.randn(1, *wl["in_dims"], device=dev))
-    else:
+    def build_net(mc_local):
+        if wl.get("conv"):
+            assert world == 1, "C3 couples MC samples through MC_BatchNorm2D: single GPU (replicas only)"
+            chans = [wl["in_dims"][0], 96, 128, 256, 128]
+            mods = [plb.MC_ExpansionLayer(num_MC=mc_local, input_dim=4)]
+            for li in range(4):
+                mods += [plb.BayesConv2d(chans[li], chans[li + 1], 5, stride=1, padding=2, num_MC=mc_local),
+                         plb.MC_BatchNorm2D(chans[li + 1]), torch.nn.LeakyReLU(), plb.MC_MaxPool2d(2, 2)]
+            mods += [plb.BayesAdaptiveInit_FlattenAndLinear(200), torch.nn.LeakyReLU(),
+                     plb.BayesLinear(200, dims[-1])]
+            net = torch.nn.Sequential(*mods).to(dev)
+            with torch.no_grad():      # the reference's dry run (experiments/BNN.py:253), on the device
+                net(torch.randn(1, *wl["in_dims"], device=dev))
+            return net
         mods = [plb.MC_ExpansionLayer(num_MC=mc_local, input_dim=2)]
         for li in range(len(dims) - 1):
             mods.append(plb.BayesLinear(dims[li], dims[li + 1]))
@@ -238,6 +239,9 @@ def run_b200(args, wl):
             # GEMM epilogue to the next TMA load instead of four fp32 passes per hidden layer
             from pytorch_probabilisticlayers_b200.fused import fuse_bayes_mlp
             net = fuse_bayes_mlp(net, batch)
+        return net
+
+    net = build_net(mc_local)
     trainer = ELBOTrainStep(net, plb.MC_CrossEntropyLoss(ns), ns, lr=wl["lr"])
     assert trainer.set_shard(mc_total) == mc_local
 
@@ -251,12 +255,16 @@ def run_b200(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = {}
+
     def timed(fn, steps):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        t0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        host_ms[fn.__name__] = (time.perf_counter() - t0) * 1e3 / steps   # host time to ENQUEUE a step
         b.record()
         barrier()
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
@@ -301,6 +309,26 @@ def run_b200(args, wl):
         step_resident()
     prof = PF.profile_stop()
     final_stats = stats.tolist()
+
+    # ---- N > 1 only, report-only: the same step with the per-GPU share held at the full MC (weak scaling:
+    # total MC = MC x N); the headline above is the strong-scaling figure BASELINE.json's config names ----
+    weak = None
+    if world > 1 and not wl.get("conv"):
+        del trainer, net
+        torch.cuda.empty_cache()
+        net_w = build_net(mc_total)
+        trainer_w = ELBOTrainStep(net_w, plb.MC_CrossEntropyLoss(ns), ns, lr=wl["lr"])
+        assert trainer_w.set_shard(mc_total * world) == mc_total
+
+        def step_weak():
+            return trainer_w.step(x_dev, y_dev)
+        for _ in range(3):
+            step_weak()
+        ms_w = timed(step_weak, args.steps) / args.steps
+        weak = {"mc_total": mc_total * world, "mc_per_gpu": mc_total, "ms_per_step": ms_w,
+                "value": mc_total * world * batch / (ms_w * 1e-3), "unit": UNIT,
+                "note": "report-only: per-GPU MC fixed at the config's MC, total MC grows with N"}
+        net = net_w            # same layer shapes: the KL micro-benchmark below only needs the parameters
 
     if rank != 0:
         if world > 1:
@@ -386,12 +414,14 @@ def run_b200(args, wl):
                 "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
                 "d2h_bytes_per_step": 16},
         "gpu_launches": int(launches),
+        "host_enqueue_ms_per_step": round(host_ms.get("step_resident", 0.0), 3),
         "clocks": clock_info,
         "roofline": roofline,
         "kl_roofline": kl_info,
         "step_tflops": flops / (ms_step * 1e-3) / 1e12 * (1.0 / world),
         "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
         "cpu_baseline": cpu,
+        "weak_scaling": weak,
         "final_stats": {"LL": final_stats[0], "KL": final_stats[1], "ACC": final_stats[2],
                         "loss": final_stats[3]},
     }
@@ -409,11 +439,16 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c4")
     ap.add_argument("--precision", choices=["fp32", "tf32", "bf16", "auto", "auto_tf32"], default="auto",
                     help="auto = bf16 tcgen05 kernels wherever the layer shape tiles, fp32 kernels for tiny layers")
+    ap.add_argument("--mc", type=int, default=0,
+                    help="developer option: override the workload's MC (e.g. 8 = the per-GPU share at N=8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fuse", dest="fuse", action="store_false",
                     help="run BayesLinear / LeakyReLU module by module instead of as a fused chain")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.mc:
+        wl["mc"] = args.mc
+        wl["name"] = wl.get("name", args.workload) + f" [MC overridden to {args.mc}]"
     if args.impl == "reference":
         run_reference(args, wl)
     else:
