@@ -20,6 +20,7 @@ constexpr int kPad = 4;
 struct LinearParams {
   int mc, batch, in, out;
   int per_mc;  // PL_PARAM_PER_MC_SIGMA
+  int dw_mc_per_split, dw_atomic;  // dW kernel: MC samples per blockIdx.z, partial sums combined by atomics
   const float* x;
   int64_t x_mc_stride;
   const float* w_mu;
@@ -185,7 +186,9 @@ __global__ void __launch_bounds__(kThreads) linear_dx_simt(LinearParams p) {
 // ---------------------------------------------------------------------------------------------
 // dW: per (in-tile, out-tile) CTA, loop over MC; dW[mc] = X[mc]^T dY[mc] lives in registers,
 // eps is regenerated from the counter, d_mu / d_rho are accumulated over MC on chip.
-//                                               grid (ceil(O/64), ceil(I/64))
+//                                               grid (ceil(O/64), ceil(I/64), mc_splits)
+// Thin layers (e.g. 1200 -> 10: 19 tiles) leave most SMs idle, so blockIdx.z splits the MC range and the
+// partial sums are combined with atomics into zero-initialised outputs (p.dw_atomic).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) linear_dw_simt(LinearParams p) {
   __shared__ __align__(16) float As[kK][kT + kPad];  // [b][in row]
@@ -194,7 +197,8 @@ __global__ void __launch_bounds__(kThreads) linear_dw_simt(LinearParams p) {
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
   const int kk = t >> 4, c4 = (t & 15) * 4;
   float acc_mu[4][4] = {}, acc_rho[4][4] = {};
-  for (int mc = 0; mc < p.mc; ++mc) {
+  const int mc_begin = blockIdx.z * p.dw_mc_per_split, mc_end = min(p.mc, mc_begin + p.dw_mc_per_split);
+  for (int mc = mc_begin; mc < mc_end; ++mc) {
     const float* xp = p.x + (int64_t)mc * p.x_mc_stride;
     const float* dyp = p.dy + (int64_t)mc * p.batch * p.out;
     float acc[4][4] = {};
@@ -244,8 +248,14 @@ __global__ void __launch_bounds__(kThreads) linear_dw_simt(LinearParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (oc + j < p.out) {
-        p.dw_mu[base + j] = acc_mu[i][j];
-        p.dw_rho[base + j] = acc_rho[i][j] * sigmoid_f(__ldg(p.w_rho + base + j));
+        const float gr = acc_rho[i][j] * sigmoid_f(__ldg(p.w_rho + base + j));
+        if (p.dw_atomic) {
+          atomicAdd(p.dw_mu + base + j, acc_mu[i][j]);
+          atomicAdd(p.dw_rho + base + j, gr);
+        } else {
+          p.dw_mu[base + j] = acc_mu[i][j];
+          p.dw_rho[base + j] = gr;
+        }
       }
   }
 }
@@ -361,7 +371,17 @@ int linear_bwd_simt_launch(const pl_linear_args* a) {
     PL_LAUNCH_CHECK("linear_dx_simt");
   }
   if (a->dw_mu && p.in > 0 && p.out > 0) {
-    dim3 grid((unsigned)ceil_div64(p.out, kT), (unsigned)ceil_div64(p.in, kT));
+    const int64_t tiles = ceil_div64(p.out, kT) * ceil_div64(p.in, kT);
+    int splits = 1;
+    if (tiles < 148 && p.mc > 1) splits = (int)std::min<int64_t>(p.mc, (2 * 148 + tiles - 1) / tiles);
+    p.dw_mc_per_split = (p.mc + splits - 1) / splits;
+    splits = (p.mc + p.dw_mc_per_split - 1) / p.dw_mc_per_split;
+    p.dw_atomic = (splits > 1 && !p.per_mc) ? 1 : 0;
+    if (p.dw_atomic) {
+      PL_CUDA(cudaMemsetAsync(a->dw_mu, 0, sizeof(float) * (size_t)p.in * p.out, st));
+      PL_CUDA(cudaMemsetAsync(a->dw_rho, 0, sizeof(float) * (size_t)p.in * p.out, st));
+    }
+    dim3 grid((unsigned)ceil_div64(p.out, kT), (unsigned)ceil_div64(p.in, kT), (unsigned)splits);
     linear_dw_simt<<<grid, kThreads, 0, st>>>(p);
     PL_LAUNCH_CHECK("linear_dw_simt");
   }
