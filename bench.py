@@ -58,9 +58,10 @@ def step_flops(dims, mc, batch):
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernels at the
 # C4 shapes, from the committed `ncu --set full` capture profiles/r01_ncu_full_final_summary.json
 NCU_TRAFFIC_BYTES = {
-    "linear_fwd[64x512x4096x4096]": 1.932e9 + 0.259e9,      # sampled_gemm_tc<4,0,0,0>, bf16 chained output
-    "linear_bwd_dx[64x512x4096x4096]": 2.619e9 + 0.257e9,   # sampled_gemm_tc<4,1,0,0>
-    "linear_bwd_dw[64x512x4096x4096]": 2.273e9 + 0.134e9,   # dw_tc<0,0>
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r01_ncu_full_*_v3_summary.json)
+    "linear_fwd[64x512x4096x4096]": 1.293e9 + 0.510e9,      # sampled_gemm_tc<4,0,0,0>, packed bf16 parameters, fp32 output
+    "linear_bwd_dx[64x512x4096x4096]": 2.619e9 + 0.257e9,   # sampled_gemm_tc<4,1,0,0> (v1 capture)
+    "linear_bwd_dw[64x512x4096x4096]": 2.281e9 + 0.130e9,   # dw_tc<0,0>
 }
 
 
