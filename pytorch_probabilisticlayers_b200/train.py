@@ -158,9 +158,9 @@ class ELBOTrainStep:
             if state["left"] == 0:
                 state["left"] = state["n"]
                 self._kl_backward(state["layer"])
-                self._handles.append(dist.all_reduce(self.flat[state["lo"]:state["hi"]],
-                                                     op=dist.ReduceOp.SUM, group=self.group,
-                                                     async_op=True))
+                self._handles.append((dist.all_reduce(self.flat[state["lo"]:state["hi"]],
+                                                      op=dist.ReduceOp.SUM, group=self.group,
+                                                      async_op=True), state["lo"], state["hi"]))
         return hook
 
     def set_shard(self, total_mc: int):
@@ -217,13 +217,14 @@ class ELBOTrainStep:
             for m in self._uncovered:
                 self._kl_backward(m)
             for lo, hi in self._rest:
-                self._handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM,
-                                                     group=self.group, async_op=True))
-            for h in self._handles:
-                h.wait()
-            self._handles.clear()
+                self._handles.append((dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM,
+                                                      group=self.group, async_op=True), lo, hi))
+            if not self.fused_opt:
+                for h, _, _ in self._handles:
+                    h.wait()
+                self._handles.clear()
         if self.fused_opt:
-            self._fused_step()
+            self._fused_step()      # waits slice by slice: a layer's optimiser pass runs under the later slices' reduce
         else:
             self.opt.step()
         out = self.stats.clone()
@@ -238,8 +239,21 @@ class ELBOTrainStep:
         dev = self.flat.device
         stream = _cabi.current_stream(dev)
         kl_scale = 1.0 / self.num_samples       # gradients are already summed over ranks
+        # all-reduce slices complete in launch order; update each tensor as soon as ITS slice has arrived
+        pending, waited = self._handles, 0
+
+        def slice_of(off):
+            for i, (_, lo, hi) in enumerate(pending):
+                if lo <= off < hi:
+                    return i
+            return -1
+        plan = sorted(self._adam_plan, key=lambda e: slice_of(e[1])) if pending else self._adam_plan
         with torch.cuda.device(dev):
-            for p, off, n, kind, prior in self._adam_plan:
+            for p, off, n, kind, prior in plan:
+                k = slice_of(off) if pending else -1
+                while waited <= k:
+                    pending[waited][0].wait()
+                    waited += 1
                 PF._timed(f"adam_kl[{n}]", lambda: _cabi.check(
                     lib.pl_adam_kl_step(p.data_ptr(), self.flat[off:off + n].data_ptr(),
                                         self.adam_m[off:off + n].data_ptr(),
@@ -247,5 +261,9 @@ class ELBOTrainStep:
                                         self.lr, self.betas[0], self.betas[1], self.eps, self.adam_t,
                                         self.kl_acc.data_ptr(), stream), "pl_adam_kl_step"),
                           ("bytes", 28.0 * n))
+        while waited < len(pending):            # the tail slice carries the LL / ACC statistics
+            pending[waited][0].wait()
+            waited += 1
+        pending.clear()
         # KL value of the pre-update parameters (replica-identical: not part of the all-reduce)
         self.stats[1] += ((self.kl_acc[0] + self.kl_const) / self.num_samples).float()
