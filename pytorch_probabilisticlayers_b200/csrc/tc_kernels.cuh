@@ -585,10 +585,22 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
     __syncwarp();
     if (lane == 0) mbar_arrive(b_full((num_kb - 1) % Cfg::kStagesB));
     // ===================== epilogue: TMEM -> registers -> HBM =====================
-    mbar_wait(acc_full, 0);
-    tc_fence_after_sync();
     const int q = warp & 3;        // TMEM lane quadrant this warp may access
     const int col = (gw >> 2) * 32;  // which 32-column quarter of the tile
+    // chained dX: the activation mask (this lane's 64 bytes of bf16 x) is fetched before the accumulator is
+    // waited for, so its L2 round trip hides behind the last MMAs / the TMEM load instead of following them
+    uint4 mk[4];
+    auto fetch_mask = [&](int mt) {
+      const int row = m0 + mt * 128 + q * 32 + lane;
+      const __nv_bfloat16* src = p.mask_src + ((int64_t)mc * p.rows + row) * p.ndim + n0 + col;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        mk[c] = (row < p.rows && n0 + col + 8 * c < p.ndim) ? __ldg(reinterpret_cast<const uint4*>(src) + c)
+                                                            : make_uint4(0, 0, 0, 0);
+    };
+    if (p.mask_src) fetch_mask(0);
+    mbar_wait(acc_full, 0);
+    tc_fence_after_sync();
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
       const int row = m0 + mt * 128 + q * 32 + lane;
@@ -609,8 +621,8 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
                 for (int t = 0; t < 8; ++t) w[t] = w[t] > 0.f ? w[t] : p.act_slope * w[t];
               }
               if (p.mask_src) {
-                const uint4 mk = __ldg(reinterpret_cast<const uint4*>(p.mask_src + obase + j));
-                const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+                const uint4 mkj = mk[j >> 3];
+                const uint32_t mw[4] = {mkj.x, mkj.y, mkj.z, mkj.w};
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                   // bf16 sign / zero test on the raw bits: positive and non-zero
@@ -638,6 +650,7 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
             if (n0 + col + j < p.ndim) o[(int64_t)j * p.out_hw] = __uint_as_float(v[j]) + bias_s[col + j];
         }
       }
+      if (p.mask_src && mt + 1 < MT) fetch_mask(mt + 1);   // in flight during the next TMEM load
     }
   }
   tc_fence_before_sync();
