@@ -158,14 +158,14 @@ class FlattenAndLinearPort(torch.nn.Module):
         return self.linear(x.flatten(2, -1))
 
 
-def build_convnet(num_mc, in_dims=(3, 32, 32), num_hidden=200, num_classes=10):
+def build_convnet(num_mc, in_dims=(3, 32, 32), num_hidden=200, num_classes=10, chans=None):
     """experiments/BNN.py:228-253 ('cbnn'): 4 x [BayesConv2d(k5,p2) - MC_BatchNorm2D - LeakyReLU -
     MC_MaxPool2d(2,2)] with channels 3-96-128-256-128, then flatten - BayesLinear - LeakyReLU -
-    BayesLinear."""
-    chans = [in_dims[0], 96, 128, 256, 128]
+    BayesLinear.  ``chans`` overrides the channel list (toy-sized golden trajectory)."""
+    chans = [in_dims[0], 96, 128, 256, 128] if chans is None else list(chans)
     mods = [MCExpansionPort(num_mc, 4)]
     hw = in_dims[1]
-    for i in range(4):
+    for i in range(len(chans) - 1):
         mods += [BayesConv2dPort(chans[i], chans[i + 1], 5, stride=1, padding=2, num_MC=num_mc),
                  MCBatchNorm2DPort(chans[i + 1]), torch.nn.LeakyReLU(), MCMaxPool2dPort(2, 2)]
         hw //= 2

@@ -327,6 +327,95 @@ def seeded_init_case(PL):
     save("seeded_init", **arrs)
 
 
+def convnet_train_case(PL, name, mc, b, hw, chans, hidden, classes, num_samples, lr, steps, seed):
+    """The reference's 'cbnn' block structure (experiments/BNN.py:228-253) at toy size, trained exactly as
+    BNN.training_step assembles the ELBO (:287-313): BayesConv2d(k5,p2) -> MC_BatchNorm2D -> LeakyReLU ->
+    MC_MaxPool2d per block, then BayesAdaptiveInit_FlattenAndLinear -> LeakyReLU -> BayesLinear; KL is collected
+    from BayesLinear layers only (collect_kl_div, :269-276: conv KL never reaches the loss)."""
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    mods = [PL.MC_ExpansionLayer(num_MC=mc, input_dim=4)]
+    for ci in range(len(chans) - 1):
+        mods += [PL.BayesConv2d(chans[ci], chans[ci + 1], kernel_size=5, padding=2, stride=1, num_MC=mc),
+                 PL.MC_BatchNorm2D(chans[ci + 1]), torch.nn.LeakyReLU(), PL.MC_MaxPool2d(kernel_size=2, stride=2)]
+    mods += [PL.BayesAdaptiveInit_FlattenAndLinear(hidden), torch.nn.LeakyReLU(), PL.BayesLinear(hidden, classes)]
+    net = torch.nn.Sequential(*mods)
+    net(torch.randn(1, chans[0], hw, hw))                      # the reference's dry run creates the flatten layer
+    convs = [m for m in net if isinstance(m, PL.BayesConv2d)]
+    lins = [net[-3].linear, net[-1]]
+    for l in convs + lins:
+        randomise_logscale(l, g)
+    x = torch.randn(b, chans[0], hw, hw, generator=g)
+    y = torch.randint(0, classes, (b,), generator=g)
+    crit = PL.MC_CrossEntropyLoss(num_samples)
+    opt = torch.optim.Adam(net.parameters(), lr)
+    arrs = dict(x=npy(x), y=npy(y), chans=np.array(chans), hw=np.int64(hw), hidden=np.int64(hidden),
+                classes=np.int64(classes), mc=np.int64(mc), num_samples=np.int64(num_samples),
+                lr=np.float64(lr), steps=np.int64(steps))
+    for li, l in enumerate(convs + lins):
+        arrs[f"init_w_mu{li}"] = npy(l.weight.loc)
+        arrs[f"init_w_rho{li}"] = npy(l.weight.logscale)
+        arrs[f"init_b_mu{li}"] = npy(l.bias.loc)
+        arrs[f"init_b_rho{li}"] = npy(l.bias.logscale)
+    net.train()
+    for s in range(steps):
+        opt.zero_grad()
+        torch.manual_seed(seed + 100 + s)
+        pred = net(x)
+        ll = crit(pred, y) / num_samples
+        kl = sum(l.kl_div for l in lins) / num_samples
+        loss = ll + kl
+        loss.backward()
+        arrs[f"s{s}_pred"] = npy(pred)
+        arrs[f"s{s}_loss"] = npy(loss)
+        for li, l in enumerate(convs + lins):
+            arrs[f"s{s}_eps_w{li}"] = npy(l.weight.eps)
+            arrs[f"s{s}_eps_b{li}"] = npy(l.bias.eps)
+            if s == 0:
+                arrs[f"s0_g_w_mu{li}"] = npy(l.weight.loc.grad)
+                arrs[f"s0_g_w_rho{li}"] = npy(l.weight.logscale.grad)
+        opt.step()
+    for li, l in enumerate(convs + lins):
+        arrs[f"final_w_mu{li}"] = npy(l.weight.loc)
+        arrs[f"final_w_rho{li}"] = npy(l.weight.logscale)
+    bns = [m for m in net if isinstance(m, PL.MC_BatchNorm2D)]
+    for bi, bn in enumerate(bns):
+        arrs[f"final_bn_mean{bi}"] = npy(bn.running_mean)
+        arrs[f"final_bn_var{bi}"] = npy(bn.running_var)
+        arrs[f"final_bn_w{bi}"] = npy(bn.weight)
+        arrs[f"final_bn_b{bi}"] = npy(bn.bias)
+    save(name, **arrs)
+
+
+def laplace_case(PL, name, mc, b, i, o, steps, seed, prior="laplace"):
+    """BayesLinear(prior='laplace' | 'laplace_clamp') (src/ProbabilisticLayers.py:131-159, :867-870): the prior
+    scale is an EMA of 1/grad^2 of weight.loc, updated by a tensor hook during backward; KL against the
+    per-element prior.  `steps` SGD-free steps (gradients only, parameters fixed) so the EMA is what is pinned."""
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    layer = PL.BayesLinear(i, o, prior=prior)
+    randomise_logscale(layer, g)
+    x = torch.randn(mc, b, i, generator=g)
+    gy = torch.randn(mc, b, o, generator=g)
+    arrs = dict(x=npy(x), gy=npy(gy), w_mu=npy(layer.weight.loc), w_rho=npy(layer.weight.logscale),
+                b_mu=npy(layer.bias.loc), b_rho=npy(layer.bias.logscale), steps=np.int64(steps))
+    for s in range(steps):
+        layer.zero_grad()
+        torch.manual_seed(seed + 10 + s)
+        out = layer(x)
+        loss = (out * gy).sum() + 0.01 * layer.kl_div
+        arrs[f"s{s}_prior_scale_in"] = npy(layer.prior.dist().scale * torch.ones_like(layer.weight.loc))
+        arrs[f"s{s}_kl"] = npy(layer.kl_div)
+        loss.backward()
+        arrs[f"s{s}_eps_w"] = npy(layer.weight.eps)
+        arrs[f"s{s}_eps_b"] = npy(layer.bias.eps)
+        arrs[f"s{s}_out"] = npy(out)
+        arrs[f"s{s}_g_w_mu"] = npy(layer.weight.loc.grad)
+        arrs[f"s{s}_g_w_rho"] = npy(layer.weight.logscale.grad)
+        arrs[f"s{s}_ema"] = npy(layer.prior.scale)
+    save(name, **arrs)
+
+
 def main():
     torch.set_num_threads(4)
     PL, LOSS = load_reference()
@@ -348,6 +437,10 @@ def main():
                    loss_kind="ce", num_samples=100, lr=1e-3, steps=3, seed=32)
     sivi_case(PL, "sivi_small", mc=4, b=3, i=6, seed=41)
     sivi_train_case(PL, LOSS, "train_c5_sivi", mc=128, b=100, steps=3, seed=51)
+    convnet_train_case(PL, "train_c3_convnet", mc=3, b=4, hw=8, chans=[3, 6, 8], hidden=10, classes=5,
+                       num_samples=200, lr=1e-3, steps=3, seed=71)
+    laplace_case(PL, "laplace_prior", mc=3, b=5, i=6, o=4, steps=3, seed=61)
+    laplace_case(PL, "laplace_prior_clamp", mc=2, b=4, i=5, o=8, steps=2, seed=62, prior="laplace_clamp")
     loss_cases(PL, LOSS)
     aux_layer_cases(PL)
     init_case(PL)

@@ -378,6 +378,31 @@ def test_fused_cross_entropy_matches_fp64_oracle(plb, mc, b, c):
     assert d3 is None and torch.equal(out3, out)
 
 
+@pytest.mark.parametrize("name,prior", [("laplace_prior", "laplace"), ("laplace_prior_clamp", "laplace_clamp")])
+def test_laplace_prior_matches_reference(plb, name, prior):
+    """BayesLinear(prior='laplace' | 'laplace_clamp'): KL against the per-element prior (pl_kl_fwd / pl_kl_bwd with
+    the prior-scale operand) and the EMA the gradient hook maintains, step by step against the reference."""
+    g = load_golden(name)
+    i, o = g["w_mu"].shape
+    layer = plb.BayesLinear(i, o, prior=prior).cuda()
+    with torch.no_grad():
+        layer.weight.loc.copy_(dev(g["w_mu"]))
+        layer.weight.logscale.copy_(dev(g["w_rho"]))
+        layer.bias.loc.copy_(dev(g["b_mu"]))
+        layer.bias.logscale.copy_(dev(g["b_rho"]))
+    x, gy = dev(g["x"]), dev(g["gy"])
+    for s in range(int(g["steps"])):
+        layer.zero_grad()
+        layer.inject_eps(dev(g[f"s{s}_eps_w"]), dev(g[f"s{s}_eps_b"]))
+        out = layer(x)
+        assert rel_err(out.detach().cpu().numpy(), g[f"s{s}_out"]) < 2e-5
+        assert abs(layer.kl_div.item() - float(g[f"s{s}_kl"])) / abs(float(g[f"s{s}_kl"])) < 1e-5
+        ((out * gy).sum() + 0.01 * layer.kl_div).backward()
+        assert rel_err(layer.weight.loc.grad.cpu().numpy(), g[f"s{s}_g_w_mu"]) < 1e-4
+        assert rel_err(layer.weight.logscale.grad.cpu().numpy(), g[f"s{s}_g_w_rho"]) < 1e-4
+        assert rel_err(layer.prior.scale.cpu().numpy(), g[f"s{s}_ema"]) < 1e-3
+
+
 # ---------------------------------------------------------------------------------------------
 # end-to-end: the reference's train loop, step by step, eps injected
 # ---------------------------------------------------------------------------------------------
@@ -424,6 +449,57 @@ def test_training_trajectory_matches_reference(plb, name, act, loss):
     for li, l in enumerate(layers):
         assert rel_err(l.weight.loc.detach().cpu().numpy(), g[f"final_w_mu{li}"]) < 1e-3
         assert rel_err(l.weight.logscale.detach().cpu().numpy(), g[f"final_w_rho{li}"]) < 1e-3
+
+
+def test_convnet_training_trajectory_matches_reference(plb):
+    """The reference's 'cbnn' block structure (experiments/BNN.py:228-253) at toy size, three Adam steps with the
+    reference's own eps injected: BayesConv2d / MC_BatchNorm2D / MC_MaxPool2d / flatten+linear end to end."""
+    g = load_golden("train_c3_convnet")
+    chans, hw, mc, ns = [int(c) for c in g["chans"]], int(g["hw"]), int(g["mc"]), int(g["num_samples"])
+    mods = [plb.MC_ExpansionLayer(num_MC=mc, input_dim=4)]
+    for ci in range(len(chans) - 1):
+        mods += [plb.BayesConv2d(chans[ci], chans[ci + 1], kernel_size=5, padding=2, stride=1, num_MC=mc),
+                 plb.MC_BatchNorm2D(chans[ci + 1]), torch.nn.LeakyReLU(), plb.MC_MaxPool2d(kernel_size=2, stride=2)]
+    mods += [plb.BayesAdaptiveInit_FlattenAndLinear(int(g["hidden"])), torch.nn.LeakyReLU(),
+             plb.BayesLinear(int(g["hidden"]), int(g["classes"]))]
+    net = torch.nn.Sequential(*mods).cuda()
+    with torch.no_grad():
+        net(torch.randn(1, chans[0], hw, hw, device="cuda"))       # dry run creates the flatten layer
+    convs = [m for m in net if isinstance(m, plb.BayesConv2d)]
+    lins = [net[-3].linear, net[-1]]
+    layers = convs + lins
+    bns = [m for m in net if isinstance(m, plb.MC_BatchNorm2D)]
+    with torch.no_grad():
+        for li, l in enumerate(layers):
+            l.weight.loc.copy_(dev(g[f"init_w_mu{li}"]))
+            l.weight.logscale.copy_(dev(g[f"init_w_rho{li}"]))
+            l.bias.loc.copy_(dev(g[f"init_b_mu{li}"]))
+            l.bias.logscale.copy_(dev(g[f"init_b_rho{li}"]))
+        for bn in bns:                                              # the dry run moved the running statistics
+            bn.reset_running_stats()
+    # the reference's dry run also updated ITS running stats once (momentum 0.1) before training
+    crit = plb.MC_CrossEntropyLoss(ns)
+    opt = torch.optim.Adam(net.parameters(), float(g["lr"]))
+    x, y = dev(g["x"]), dev(g["y"])
+    net.train()
+    for s in range(int(g["steps"])):
+        for li, l in enumerate(layers):
+            l.inject_eps(dev(g[f"s{s}_eps_w{li}"]), dev(g[f"s{s}_eps_b{li}"]))
+        opt.zero_grad()
+        pred = net(x)
+        total = crit(pred, y) / ns + sum(l.kl_div for l in lins) / ns
+        total.backward()
+        assert rel_err(pred.detach().cpu().numpy(), g[f"s{s}_pred"]) < 5e-4, s
+        assert abs(total.item() - float(g[f"s{s}_loss"])) / abs(float(g[f"s{s}_loss"])) < 2e-4, s
+        if s == 0:
+            for li, l in enumerate(layers):
+                assert rel_err(l.weight.loc.grad.cpu().numpy(), g[f"s0_g_w_mu{li}"]) < 1e-3, li
+                assert rel_err(l.weight.logscale.grad.cpu().numpy(), g[f"s0_g_w_rho{li}"]) < 1e-3, li
+        opt.step()
+    for li, l in enumerate(layers):
+        assert rel_err(l.weight.loc.detach().cpu().numpy(), g[f"final_w_mu{li}"]) < 2e-3, li
+    for bi, bn in enumerate(bns):
+        assert rel_err(bn.weight.detach().cpu().numpy(), g[f"final_bn_w{bi}"]) < 1e-3
 
 
 # ---------------------------------------------------------------------------------------------

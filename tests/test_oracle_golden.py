@@ -193,3 +193,56 @@ def test_torch_port_train_step_reproduces_reference_trajectory(name, act, loss):
         assert abs(r["loss"] - float(g[f"s{s}_loss"])) / abs(float(g[f"s{s}_loss"])) < 1e-5, s
     for li, l in enumerate(layers):
         assert np.allclose(l.weight.loc.detach().numpy(), g[f"final_w_mu{li}"], rtol=1e-4, atol=1e-6)
+
+
+def test_torch_port_convnet_reproduces_reference_trajectory():
+    """The 'cbnn' block structure at toy size: conv -> MC batch norm -> LeakyReLU -> pool (x2) -> flatten/linear ->
+    linear, three Adam steps; KL from the BayesLinear layers only (experiments/BNN.py:269-276)."""
+    import torch
+    from oracle import torch_port as tp
+    g = load_golden("train_c3_convnet")
+    chans, hw, mc, ns = [int(c) for c in g["chans"]], int(g["hw"]), int(g["mc"]), int(g["num_samples"])
+    net = tp.build_convnet(mc, (chans[0], hw, hw), int(g["hidden"]), int(g["classes"]), chans=chans)
+    layers = [m for m in net if isinstance(m, tp.BayesConv2dPort)] + [net[-3].linear, net[-1]]
+    with torch.no_grad():
+        for li, l in enumerate(layers):
+            l.weight.loc.copy_(torch.from_numpy(g[f"init_w_mu{li}"]))
+            l.weight.logscale.copy_(torch.from_numpy(g[f"init_w_rho{li}"]))
+            l.bias.loc.copy_(torch.from_numpy(g[f"init_b_mu{li}"]))
+            l.bias.logscale.copy_(torch.from_numpy(g[f"init_b_rho{li}"]))
+    crit = tp.MCCrossEntropyPort(ns)
+    opt = torch.optim.Adam(net.parameters(), float(g["lr"]))
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    for s in range(int(g["steps"])):
+        torch.manual_seed(71 + 100 + s)
+        r = tp.train_step(net, crit, opt, x, y, ns)
+        assert abs(r["loss"] - float(g[f"s{s}_loss"])) / abs(float(g[f"s{s}_loss"])) < 1e-5, s
+    for li, l in enumerate(layers):
+        assert np.allclose(l.weight.loc.detach().numpy(), g[f"final_w_mu{li}"], rtol=1e-4, atol=1e-6)
+    bns = [m for m in net if isinstance(m, tp.MCBatchNorm2DPort)]
+    for bi, bn in enumerate(bns):     # (running statistics also carry the reference's random dry-run batch: not compared)
+        assert np.allclose(bn.weight.detach().numpy(), g[f"final_bn_w{bi}"], rtol=1e-5, atol=1e-7)
+        assert np.allclose(bn.bias.detach().numpy(), g[f"final_bn_b{bi}"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,clamp", [("laplace_prior", False), ("laplace_prior_clamp", True)])
+def test_laplace_prior_kl_and_ema_restatement(name, clamp):
+    """LaplacePrior (src/ProbabilisticLayers.py:131-159): per-element prior scale sqrt(EMA)+1e-8 (or clamped at
+    1), EMA of 1/grad^2 of weight.loc with bias correction, KL against it -- the oracle's closed forms against
+    the reference's own values."""
+    g = load_golden(name)
+    ema = np.ones_like(g["w_mu"], dtype=np.float64)
+    for s in range(int(g["steps"])):
+        ps = np.maximum(np.sqrt(ema), 1.0) if clamp else np.sqrt(ema) + 1e-8
+        assert rel_err(ps, g[f"s{s}_prior_scale_in"]) < 1e-6
+        kl, _ = cf.kl_fwd(g["w_mu"], g["w_rho"], ps)
+        assert abs(kl - float(g[f"s{s}_kl"])) / abs(float(g[f"s{s}_kl"])) < 1e-5
+        # total gradient of weight.loc = data term + 0.01 * dKL/dmu, which is what the tensor hook sees
+        data = cf.linear_bwd(g["gy"], g["x"], g["w_mu"], g["w_rho"], g[f"s{s}_eps_w"], g["b_rho"], g[f"s{s}_eps_b"])
+        dmu_kl, drho_kl = cf.kl_bwd(g["w_mu"], g["w_rho"], ps)
+        gmu = data["dw_mu"] + 0.01 * dmu_kl
+        assert rel_err(gmu, g[f"s{s}_g_w_mu"]) < 1e-4
+        assert rel_err(data["dw_rho"] + 0.01 * drho_kl, g[f"s{s}_g_w_rho"]) < 1e-4
+        corr = 1.0 - 0.99 ** (s + 1)
+        ema = 0.99 * ema + 0.01 * (1.0 / g[f"s{s}_g_w_mu"].astype(np.float64) ** 2) / (corr + 1e-8)
+        assert rel_err(ema, g[f"s{s}_ema"]) < 1e-4
