@@ -228,6 +228,10 @@ def run_b200(args, wl):
             net = torch.nn.Sequential(*mods).to(dev)
             with torch.no_grad():      # the reference's dry run (experiments/BNN.py:253), on the device
                 net(torch.randn(1, *wl["in_dims"], device=dev))
+            if args.fuse:
+                # same modules and parameters; each batch-norm / LeakyReLU / max-pool triple runs as one pass
+                from pytorch_probabilisticlayers_b200.bnpool import fuse_bn_act_pool
+                net = fuse_bn_act_pool(net)
             return net
         mods = [plb.MC_ExpansionLayer(num_MC=mc_local, input_dim=2)]
         for li in range(len(dims) - 1):

@@ -123,6 +123,41 @@ typedef struct pl_ce_args {
 size_t pl_mc_cross_entropy_workspace_bytes(void);
 int pl_mc_cross_entropy(const pl_ce_args* a);
 
+/* ---- MC_BatchNorm2D -> LeakyReLU -> MC_MaxPool2d(2, 2) fused (replaces, per conv block of the reference's
+ *      'cbnn' net, experiments/BNN.py:232-247: MC_BatchNorm2D.forward, src/ProbabilisticLayers.py:736-762,
+ *      LeakyReLU, MC_MaxPool2d.forward, :207-236, and their autograd) -----------------------------------
+ * x: [n, channels, h, w] fp32 contiguous with n = MC*B (statistics are pooled over MC, B, H, W jointly, as
+ * the reference's permute + F.batch_norm does), h and w even.
+ * pl_bn_stats: sums[2*c] = sum x, sums[2*c+1] = sum x^2 over (n, hw) for each channel (fp64, zeroed by the call).
+ * The caller derives mean / rstd = 1/sqrt(var + eps) (biased variance) and the running-statistics update.
+ * fwd: y[n,c,h/2,w/2] = max over each 2x2 window of leaky_relu(gamma*(x-mean)*rstd + beta, slope);
+ *      idx = which window element won (0..3, row-major, first maximum).
+ * bwd: dx (optional), dgamma, dbeta (optional) from dy; batch_stats != 0: the statistics came from x itself
+ *      (training: the mean(dz) and xhat*mean(dz*xhat) terms are included); 0: running statistics. */
+typedef struct pl_bnpool_args {
+  int32_t n, channels, h, w;
+  float slope;
+  int32_t batch_stats;
+  const float* x;
+  const float* gamma;
+  const float* beta;
+  const float* mean;
+  const float* rstd;
+  float* y;
+  uint8_t* idx;
+  const float* dy;
+  float* dx;
+  float* dgamma;
+  float* dbeta;
+  void* workspace;
+  size_t workspace_bytes;
+  void* stream;
+} pl_bnpool_args;
+int pl_bn_stats(const float* x, int32_t n, int32_t channels, int32_t hw, double* sums, void* stream);
+size_t pl_bn_act_pool_workspace_bytes(int32_t channels);
+int pl_bn_act_pool_fwd(const pl_bnpool_args* a);
+int pl_bn_act_pool_bwd(const pl_bnpool_args* a);
+
 /* ---- BayesLinear / SIVILayer contraction (replaces VariationalNormal.rsample + torch.baddbmm /
  *      torch.bmm at src/ProbabilisticLayers.py:925-935 and :321-326, and their autograd) ------ */
 typedef struct pl_linear_args {

@@ -25,6 +25,7 @@ EXPORTS = (
     "pl_version", "pl_last_error", "pl_launch_count", "pl_device_supported", "pl_eps_dump",
     "pl_kl_workspace_bytes", "pl_kl_fwd", "pl_kl_bwd", "pl_adam_kl_step",
     "pl_mc_cross_entropy_workspace_bytes", "pl_mc_cross_entropy",
+    "pl_bn_stats", "pl_bn_act_pool_workspace_bytes", "pl_bn_act_pool_fwd", "pl_bn_act_pool_bwd",
     "pl_linear_workspace_bytes", "pl_linear_state_bytes", "pl_linear_fwd", "pl_linear_bwd",
     "pl_conv2d_workspace_bytes", "pl_conv2d_state_bytes", "pl_conv2d_fwd", "pl_conv2d_bwd",
 )
@@ -71,6 +72,17 @@ class CeArgs(C.Structure):
     ]
 
 
+class BnPoolArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("channels", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("slope", C.c_float), ("batch_stats", C.c_int32),
+        ("x", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("mean", C.c_void_p),
+        ("rstd", C.c_void_p), ("y", C.c_void_p), ("idx", C.c_void_p), ("dy", C.c_void_p),
+        ("dx", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("stream", C.c_void_p),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -109,6 +121,13 @@ def lib():
                 l.pl_mc_cross_entropy_workspace_bytes.restype = C.c_size_t
                 l.pl_mc_cross_entropy.restype = C.c_int
                 l.pl_mc_cross_entropy.argtypes = [C.POINTER(CeArgs)]
+                l.pl_bn_stats.restype = C.c_int
+                l.pl_bn_stats.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+                l.pl_bn_act_pool_workspace_bytes.restype = C.c_size_t
+                l.pl_bn_act_pool_workspace_bytes.argtypes = [C.c_int32]
+                for name in ("pl_bn_act_pool_fwd", "pl_bn_act_pool_bwd"):
+                    getattr(l, name).restype = C.c_int
+                    getattr(l, name).argtypes = [C.POINTER(BnPoolArgs)]
                 l.pl_linear_workspace_bytes.restype = C.c_size_t
                 l.pl_linear_workspace_bytes.argtypes = [C.POINTER(LinearArgs)]
                 l.pl_linear_state_bytes.restype = C.c_size_t

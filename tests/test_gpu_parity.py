@@ -451,7 +451,38 @@ def test_training_trajectory_matches_reference(plb, name, act, loss):
         assert rel_err(l.weight.logscale.detach().cpu().numpy(), g[f"final_w_rho{li}"]) < 1e-3
 
 
-def test_convnet_training_trajectory_matches_reference(plb):
+@pytest.mark.parametrize("mc,b,c,h,w,train", [(3, 4, 6, 8, 12, True), (2, 3, 5, 4, 4, True), (1, 2, 96, 32, 32, True),
+                                              (2, 2, 7, 6, 10, False)])
+def test_fused_bn_act_pool_equals_module_chain(plb, mc, b, c, h, w, train):
+    """bnpool.FusedBNActPool against MC_BatchNorm2D -> LeakyReLU -> MC_MaxPool2d(2,2) (the reference's three
+    modules, src/ProbabilisticLayers.py:736-762, :207-236): outputs, gradients of x / weight / bias and the
+    running statistics, in training and in eval mode."""
+    from pytorch_probabilisticlayers_b200.bnpool import FusedBNActPool
+    torch.manual_seed(mc * 100 + c)
+    x0 = torch.randn(mc, b, c, h, w, device="cuda") * 1.7 + 0.3
+    gy = torch.randn(mc, b, c, h // 2, w // 2, device="cuda")
+    res = {}
+    for kind in ("chain", "fused"):
+        bn = plb.MC_BatchNorm2D(c).cuda()
+        with torch.no_grad():
+            bn.weight.copy_(torch.linspace(0.5, 1.5, c))
+            bn.bias.copy_(torch.linspace(-0.3, 0.4, c))
+            bn.running_mean.copy_(torch.linspace(-0.2, 0.2, c))
+            bn.running_var.copy_(torch.linspace(0.8, 1.6, c))
+        bn.train(train)
+        x = x0.clone().requires_grad_(True)
+        if kind == "chain":
+            y = plb.MC_MaxPool2d(2, 2)(torch.nn.functional.leaky_relu(bn(x), 0.01))
+        else:
+            y = FusedBNActPool(bn, 0.01)(x)
+        (y * gy).sum().backward()
+        res[kind] = [t.detach().cpu().numpy() for t in (y, x.grad, bn.weight.grad, bn.bias.grad, bn.running_mean,
+                                                        bn.running_var)]
+    for a, r, tol in zip(res["fused"], res["chain"], (2e-6, 2e-4, 2e-4, 2e-4, 1e-5, 1e-5)):
+        assert rel_err(a, r) < tol
+
+
+def test_convnet_training_trajectory_matches_reference(plb, fuse_blocks=False):
     """The reference's 'cbnn' block structure (experiments/BNN.py:228-253) at toy size, three Adam steps with the
     reference's own eps injected: BayesConv2d / MC_BatchNorm2D / MC_MaxPool2d / flatten+linear end to end."""
     g = load_golden("train_c3_convnet")
@@ -469,6 +500,10 @@ def test_convnet_training_trajectory_matches_reference(plb):
     lins = [net[-3].linear, net[-1]]
     layers = convs + lins
     bns = [m for m in net if isinstance(m, plb.MC_BatchNorm2D)]
+    if fuse_blocks:
+        from pytorch_probabilisticlayers_b200.bnpool import FusedBNActPool, fuse_bn_act_pool
+        net = fuse_bn_act_pool(net)
+        assert sum(isinstance(m, FusedBNActPool) for m in net) == len(bns)
     with torch.no_grad():
         for li, l in enumerate(layers):
             l.weight.loc.copy_(dev(g[f"init_w_mu{li}"]))
@@ -500,6 +535,10 @@ def test_convnet_training_trajectory_matches_reference(plb):
         assert rel_err(l.weight.loc.detach().cpu().numpy(), g[f"final_w_mu{li}"]) < 2e-3, li
     for bi, bn in enumerate(bns):
         assert rel_err(bn.weight.detach().cpu().numpy(), g[f"final_bn_w{bi}"]) < 1e-3
+
+
+def test_convnet_trajectory_with_fused_bn_act_pool_blocks(plb):
+    test_convnet_training_trajectory_matches_reference(plb, fuse_blocks=True)
 
 
 # ---------------------------------------------------------------------------------------------

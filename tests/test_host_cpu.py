@@ -55,7 +55,7 @@ def test_struct_layout_matches_header():
     src = textwrap.dedent("""
         #include <stdio.h>
         #include "pl_b200.h"
-        int main(void){ printf("%zu %zu %zu\\n", sizeof(pl_linear_args), sizeof(pl_conv2d_args), sizeof(pl_ce_args)); return 0; }
+        int main(void){ printf("%zu %zu %zu %zu\\n", sizeof(pl_linear_args), sizeof(pl_conv2d_args), sizeof(pl_ce_args), sizeof(pl_bnpool_args)); return 0; }
     """)
     with tempfile.TemporaryDirectory() as d:
         cfile = os.path.join(d, "s.c")
@@ -66,6 +66,7 @@ def test_struct_layout_matches_header():
     assert int(out[0]) == C.sizeof(_cabi.LinearArgs)
     assert int(out[1]) == C.sizeof(_cabi.Conv2dArgs)
     assert int(out[2]) == C.sizeof(_cabi.CeArgs)
+    assert int(out[3]) == C.sizeof(_cabi.BnPoolArgs)
 
 
 def test_seeded_construction_matches_reference_state_dict():
