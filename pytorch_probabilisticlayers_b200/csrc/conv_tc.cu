@@ -144,8 +144,10 @@ __global__ void __launch_bounds__(256) dy_pixel_major_kernel(const float* __rest
 }
 
 // dx[mc][b][c][h][w] = sum_{kh,kw} dA[mc][c*k*k + kh*k + kw][b*HWo + oh*Wo + ow]   (gather, no atomics)
+// dA is bf16: it is written once by the GEMM epilogue and read once here, and its k*k overlapping contributions
+// per input pixel are summed in fp32 (halves the largest transient of the conv backward: 5 GB at C3's layer 2)
 template <bool kUnit>   // kUnit: stride == 1 and dilation == 1 (no divisibility tests / divisions)
-__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dA, float* __restrict__ dx,
+__global__ void __launch_bounds__(256) col2im_kernel(const __nv_bfloat16* __restrict__ dA, float* __restrict__ dx,
                                                      ConvGeom g) {
   const int64_t per_mc = (int64_t)g.batch * g.cin * g.h * g.w, total = (int64_t)g.mc * per_mc;
   const int kk2 = g.k * g.k, hwo = g.ho * g.wo;
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ d
     const int c = (int)(r % g.cin);
     r /= g.cin;
     const int b = (int)(r % g.batch), mc = (int)(r / g.batch);
-    const float* base = dA + ((int64_t)mc * g.K + (int64_t)c * kk2) * g.M + (int64_t)b * hwo;
+    const __nv_bfloat16* base = dA + ((int64_t)mc * g.K + (int64_t)c * kk2) * g.M + (int64_t)b * hwo;
     float s = 0.f;
     for (int kh = 0; kh < g.k; ++kh) {
       const int th = ih + g.pad - (kUnit ? kh : kh * g.dil);
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ d
         if (tw < 0 || (!kUnit && tw % g.stride)) continue;
         const int ow = kUnit ? tw : tw / g.stride;
         if (ow >= g.wo) continue;
-        s += __ldg(base + (int64_t)(kh * g.k + kw) * g.M + oh * g.wo + ow);
+        s += __bfloat162float(base[(int64_t)(kh * g.k + kw) * g.M + oh * g.wo + ow]);
       }
     }
     dx[t] = s;
@@ -204,7 +206,7 @@ struct ConvScratch {
   float* bias;             // [mc*cout] sampled bias (fwd) / column sums (bwd)
   __nv_bfloat16* A;        // [mcx*M*Kp]
   __nv_bfloat16* dyt;      // [mc*M*Coutp]        (bwd)
-  float* dA;               // [mc*K*M]            (bwd, when dx is wanted)
+  __nv_bfloat16* dA;       // [mc*K*M] bf16       (bwd, when dx is wanted)
   size_t total;
 };
 
@@ -221,8 +223,8 @@ static ConvScratch conv_carve(const ConvGeom& g, void* base, bool backward, bool
   }
   w.dyt = (__nv_bfloat16*)(b + off);
   if (backward) off += align256((size_t)g.mc * g.M * g.Coutp * 2);
-  w.dA = (float*)(b + off);
-  if (backward && want_dx) off += align256((size_t)g.mc * g.K * g.M * 4);
+  w.dA = (__nv_bfloat16*)(b + off);
+  if (backward && want_dx) off += align256((size_t)g.mc * g.K * g.M * 2);
   w.total = off + 256;
   return w;
 }
@@ -364,7 +366,8 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     p.w_mu = a->w_mu; p.w_sigma = w.sigma; p.w_pack = (const uint4*)w.sigma; p.eps_w = a->eps_w;
     p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
     p.bias = nullptr;
-    p.out = w.dA;                 // [mc][K][M]: K-major so that col2im reads contiguous pixels
+    p.out = nullptr;
+    p.out_lp = w.dA;              // bf16 [mc][K][M]: K-major so that col2im reads contiguous pixels
     p.out_hw = (int)g.M;
     p.w_aligned = (g.K % 4) == 0;
     rc = a->eps_w ? launch_gemm<false, true>(tm, p, st) : launch_gemm<false, false>(tm, p, st);

@@ -644,10 +644,19 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
         } else {
           // channel-major output: consecutive lanes (rows = pixels) are contiguous in memory
           const int img = row / p.out_hw, pix = row - img * p.out_hw;
-          float* o = p.out + (((int64_t)mc * (p.rows / p.out_hw) + img) * p.ndim + n0 + col) * p.out_hw + pix;
+          const int64_t ooff = (((int64_t)mc * (p.rows / p.out_hw) + img) * p.ndim + n0 + col) * p.out_hw + pix;
+          if (p.out_lp) {   // bf16 (the conv backward's dA intermediate)
+            __nv_bfloat16* o = p.out_lp + ooff;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + col + j < p.ndim) o[(int64_t)j * p.out_hw] = __uint_as_float(v[j]) + bias_s[col + j];
+            for (int j = 0; j < 32; ++j)
+              if (n0 + col + j < p.ndim)
+                o[(int64_t)j * p.out_hw] = __float2bfloat16(__uint_as_float(v[j]) + bias_s[col + j]);
+          } else {
+            float* o = p.out + ooff;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + col + j < p.ndim) o[(int64_t)j * p.out_hw] = __uint_as_float(v[j]) + bias_s[col + j];
+          }
         }
       }
       if (p.mask_src && mt + 1 < MT) fetch_mask(mt + 1);   // in flight during the next TMEM load
