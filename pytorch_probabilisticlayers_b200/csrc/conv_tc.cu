@@ -59,60 +59,90 @@ __global__ void __launch_bounds__(256) im2col_bf16_kernel(const float* __restric
   }
 }
 
-// Same matrix, one CTA per (image, output row): the k input rows that row needs are staged in shared
-// memory ([Cin][k][W] fp32, zero rows outside the image) so every input element is read from HBM/L2
-// once per output row instead of k*k times, and the 16-byte output chunks are built from smem.
-// grid (ho, mcx*batch), dynamic smem = cin*k*w*4 bytes.
+// Same matrix, one CTA per (image, output row).  The k input rows that output row needs are staged in shared
+// memory WITH their zero padding ([Cin*k + 1][ws] fp32, ws = w + 2*pad; the extra row is all zero and serves the
+// K..Kp tail), next to a table off[kidx] = (c*k + kh)*ws + kw*dil (uint16).  An output chunk of 8 consecutive
+// kidx is then one 16-byte table read, eight shared-memory loads at off + ow*stride, four packs and one 16-byte
+// store: ~40 instructions instead of ~430 (the first version recomputed (c, kh, kw) and bounds per element and
+// was issue bound: 2.1 ms for C3's layer 2, profiles/r01_experiments.md).
+// grid (ho, mcx*batch), dynamic smem = (Cin*k + 1)*ws*4 + Kp*2 bytes.
+// kK: compile-time kernel size (divisions by k and k*k become multiply-shift); 0 = run-time k.  All index
+// arithmetic is per (warp, row) or per (warp, output pixel), never per element.
+template <int kK>
 __global__ void __launch_bounds__(256) im2col_rows_bf16_kernel(const float* __restrict__ x,
                                                                int64_t x_mc_stride,
                                                                __nv_bfloat16* __restrict__ A, ConvGeom g) {
-  extern __shared__ float rows[];   // [cin][k][w]
+  extern __shared__ __align__(16) uint8_t im2col_smem[];
+  const int k = kK ? kK : g.k;
+  const int ws = g.w + 2 * g.pad;
+  const int nrow = g.cin * k;
+  uint16_t* off = reinterpret_cast<uint16_t*>(im2col_smem);                 // [Kp]
+  float* rows = reinterpret_cast<float*>(im2col_smem + (((size_t)g.Kp * 2 + 15) & ~(size_t)15));   // [nrow + 1][ws]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int oh = blockIdx.x, img = blockIdx.y, mc = img / g.batch, b = img - mc * g.batch;
   const float* xb = x + (int64_t)mc * x_mc_stride + (int64_t)b * g.cin * g.h * g.w;
   const int ih0 = oh * g.stride - g.pad;
-  const int nrow = g.cin * g.k;
-  for (int t = threadIdx.x; t < nrow * g.w; t += 256) {
-    const int rw = t / g.w, iw = t - rw * g.w, c = rw / g.k, kh = rw - c * g.k;
-    const int ih = ih0 + kh * g.dil;
-    rows[t] = (ih >= 0 && ih < g.h) ? __ldg(xb + ((int64_t)c * g.h + ih) * g.w + iw) : 0.f;
+  // staged rows: a warp pass covers 32 / cw rows of cw (8, 16 or 32) columns each, so narrow planes keep the lanes busy
+  const int cw = ws <= 8 ? 8 : (ws <= 16 ? 16 : 32), rpp = 32 / cw;
+  const int sub = lane / cw, col0 = lane - sub * cw;
+  for (int rw = warp * rpp + sub; rw <= nrow; rw += 8 * rpp) {   // row nrow = zeros
+    const int c = rw / k, kh = rw - c * k, ih = ih0 + kh * g.dil;
+    const bool row_ok = rw < nrow && ih >= 0 && ih < g.h;
+    const float* src = xb + ((int64_t)c * g.h + ih) * g.w - g.pad;
+    for (int col = col0; col < ws; col += cw)
+      rows[rw * ws + col] = (row_ok && col >= g.pad && col < g.w + g.pad) ? __ldg(src + col) : 0.f;
+  }
+  const int kk2 = k * k;
+  for (int kidx = threadIdx.x; kidx < g.Kp; kidx += 256) {
+    int o = nrow * ws;                                   // the zero row
+    if (kidx < g.K) {
+      const int c = kidx / kk2, r = kidx - c * kk2, kh = r / k, kw = r - kh * k;
+      o = (c * k + kh) * ws + kw * g.dil;
+    }
+    off[kidx] = (uint16_t)o;
   }
   __syncthreads();
   const int chunks = g.Kp >> 3;
   const int64_t m0 = ((int64_t)mc * g.batch + b) * g.ho * g.wo + (int64_t)oh * g.wo;   // first pixel row
-  for (int t = threadIdx.x; t < g.wo * chunks; t += 256) {
-    const int ow = t / chunks, kc = t - ow * chunks;
-    const int iw0 = ow * g.stride - g.pad;
-    int kidx = kc << 3;
-    const int kk2 = g.k * g.k;
-    int c = kidx / kk2, r = kidx - c * kk2, kh = r / g.k, kw = r - kh * g.k;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float val = 0.f;
-      if (kidx + j < g.K) {
-        const int iw = iw0 + kw * g.dil;
-        if (iw >= 0 && iw < g.w) val = rows[(c * g.k + kh) * g.w + iw];
-      }
-      v[j] = val;
-      if (++kw == g.k) {
-        kw = 0;
-        if (++kh == g.k) {
-          kh = 0;
-          ++c;
-        }
-      }
+  for (int ow = warp; ow < g.wo; ow += 8) {
+    const float* base = rows + ow * g.stride;
+    __nv_bfloat16* dst = A + (m0 + ow) * (int64_t)g.Kp;
+    for (int kc = lane; kc < chunks; kc += 32) {
+      const uint4 o8 = *reinterpret_cast<const uint4*>(off + (kc << 3));
+      const float v0 = base[o8.x & 0xffffu], v1 = base[o8.x >> 16], v2 = base[o8.y & 0xffffu], v3 = base[o8.y >> 16];
+      const float v4 = base[o8.z & 0xffffu], v5 = base[o8.z >> 16], v6 = base[o8.w & 0xffffu], v7 = base[o8.w >> 16];
+      *reinterpret_cast<uint4*>(dst + (kc << 3)) =
+          make_uint4(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3), pack_bf16x2(v4, v5), pack_bf16x2(v6, v7));
     }
-    *reinterpret_cast<uint4*>(A + ((m0 + ow) * chunks + kc) * 8) =
-        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                   pack_bf16x2(v[6], v[7]));
   }
 }
 
+static size_t im2col_rows_smem(const ConvGeom& g) {
+  return (((size_t)g.Kp * 2 + 15) & ~(size_t)15) + (size_t)(g.cin * g.k + 1) * (g.w + 2 * g.pad) * sizeof(float);
+}
+
 static int launch_im2col(const pl_conv2d_args* a, const ConvGeom& g, __nv_bfloat16* A, cudaStream_t st) {
-  const size_t smem = (size_t)g.cin * g.k * g.w * sizeof(float);
-  if (smem <= 48 * 1024 && (int64_t)g.mcx * g.batch <= 65535) {
+  const size_t smem = im2col_rows_smem(g);
+  // the row kernel needs the staged rows + table in shared memory, uint16 offsets, and the standard output width
+  const bool rows_ok = smem <= 200 * 1024 && (int64_t)g.mcx * g.batch <= 65535 &&
+                       (size_t)(g.cin * g.k + 2) * (g.w + 2 * g.pad) < 65536 &&
+                       (g.wo - 1) * g.stride + (g.k - 1) * g.dil < g.w + 2 * g.pad;
+  if (rows_ok) {
     dim3 grid((unsigned)g.ho, (unsigned)(g.mcx * g.batch));
-    im2col_rows_bf16_kernel<<<grid, 256, smem, st>>>(a->x, a->x_mc_stride, A, g);
+#define PL_IM2COL(KK)                                                                                      \
+  do {                                                                                                    \
+    static size_t attr_set = 0;                                                                           \
+    if (smem > 48 * 1024 && smem > attr_set) {                                                            \
+      PL_CUDA(cudaFuncSetAttribute(im2col_rows_bf16_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   (int)smem));                                                           \
+      attr_set = smem;                                                                                    \
+    }                                                                                                     \
+    im2col_rows_bf16_kernel<KK><<<grid, 256, smem, st>>>(a->x, a->x_mc_stride, A, g);                     \
+  } while (0)
+    if (g.k == 5) PL_IM2COL(5);
+    else if (g.k == 3) PL_IM2COL(3);
+    else PL_IM2COL(0);
+#undef PL_IM2COL
     PL_LAUNCH_CHECK("im2col_rows_bf16_kernel");
   } else {
     im2col_bf16_kernel<<<ew_grid((int64_t)g.mcx * g.M * (g.Kp / 8), 256), 256, 0, st>>>(a->x, a->x_mc_stride, A, g);
