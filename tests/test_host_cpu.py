@@ -114,3 +114,23 @@ def test_dropin_import_paths():
         generate_nonstationary_data)
     import pytorch_probabilisticlayers_b200 as p
     assert BayesLinear is p.BayesLinear
+
+
+def test_fused_bn_act_pool_module_on_cpu_equals_the_three_modules():
+    """bnpool.FusedBNActPool keeps the batch-norm object and, where the CUDA pass does not apply (CPU tensors, odd
+    planes), runs the reference's three modules unchanged; fuse_bn_act_pool rewrites only matching triples."""
+    import torch
+    import pytorch_probabilisticlayers_b200 as plb
+    from pytorch_probabilisticlayers_b200.bnpool import FusedBNActPool, fuse_bn_act_pool
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(plb.MC_BatchNorm2D(4), torch.nn.LeakyReLU(0.02), plb.MC_MaxPool2d(2, 2),
+                              plb.MC_BatchNorm2D(4), torch.nn.ReLU(), plb.MC_MaxPool2d(2, 2))
+    fused = fuse_bn_act_pool(net)
+    assert isinstance(fused[0], FusedBNActPool) and fused[0].bn is net[0] and fused[0].negative_slope == 0.02
+    assert len(fused) == 4 and fused[1] is net[3]            # BN -> ReLU -> pool is left alone
+    x = torch.randn(2, 3, 4, 6, 6)
+    ref_bn = plb.MC_BatchNorm2D(4)
+    want = plb.MC_MaxPool2d(2, 2)(torch.nn.functional.leaky_relu(ref_bn(x), 0.02))
+    got = fused[0](x)
+    assert torch.allclose(got, want, atol=1e-6)
+    assert torch.allclose(net[0].running_var, ref_bn.running_var)
