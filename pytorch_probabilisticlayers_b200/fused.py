@@ -84,6 +84,7 @@ class _FusedMLPFn(torch.autograd.Function):
         stream = _cabi.current_stream(dev)
         grads = [None] * (4 * nl)
         dy_lp = None
+        dx0 = None                                      # gradient of the chain's input, when something upstream needs it
         with torch.cuda.device(dev):
             for li in reversed(range(nl)):
                 w_mu, w_rho, b_mu, b_rho = params[4 * li:4 * li + 4]
@@ -111,6 +112,9 @@ class _FusedMLPFn(torch.autograd.Function):
                 if li > 0:                              # dX * act'(x) as the bf16 dY of layer li-1
                     dx_lp = torch.empty((mc, batch, fin), dtype=torch.bfloat16, device=dev)
                     a.dx_lp, a.x_act_slope = _cabi.ptr(dx_lp), slope
+                elif ctx.needs_input_grad[0]:           # the chain is not the first thing in the net
+                    dx0 = torch.empty((mc, batch, fin), dtype=torch.float32, device=dev)
+                    a.dx = _cabi.ptr(dx0)
                 ws = PF._workspace(lib.pl_linear_workspace_bytes(C.byref(a)), dev)
                 a.workspace, a.workspace_bytes = _cabi.ptr(ws), ws.numel()
                 a.stream = stream
@@ -119,19 +123,19 @@ class _FusedMLPFn(torch.autograd.Function):
                 if PF._PROFILE is None:
                     _cabi.check(lib.pl_linear_bwd(C.byref(a)), "pl_linear_bwd")
                 else:                                   # one call per output group, timed separately
-                    outs = (a.dx_lp, a.dw_mu, a.dw_rho, a.db_mu, a.db_rho)
-                    for tag, keep in (("dx", (0,)), ("dw", (1, 2)), ("db", (3, 4))):
+                    outs = (a.dx_lp, a.dw_mu, a.dw_rho, a.db_mu, a.db_rho, a.dx)
+                    for tag, keep in (("dx", (0, 5)), ("dw", (1, 2)), ("db", (3, 4))):
                         sel = [o if i in keep else None for i, o in enumerate(outs)]
                         if all(v is None for v in sel):
                             continue
-                        a.dx_lp, a.dw_mu, a.dw_rho, a.db_mu, a.db_rho = sel
+                        a.dx_lp, a.dw_mu, a.dw_rho, a.db_mu, a.db_rho, a.dx = sel
                         PF._timed(f"linear_bwd_{tag}{shape}",
                                   lambda: _cabi.check(lib.pl_linear_bwd(C.byref(a)), "pl_linear_bwd"),
                                   ("flops", flops) if tag != "db" else ("bytes", 2.0 * mc * batch * fout))
-                    a.dx_lp, a.dw_mu, a.dw_rho, a.db_mu, a.db_rho = outs
+                    a.dx_lp, a.dw_mu, a.dw_rho, a.db_mu, a.db_rho, a.dx = outs
                 grads[4 * li:4 * li + 4] = [dw_mu, dw_rho, db_mu, db_rho]
                 dy_lp = dx_lp
-        return (None, None, None, *grads)
+        return (dx0, None, None, *grads)
 
 
 class FusedBayesMLP(torch.nn.Module):
@@ -188,8 +192,12 @@ def fuse_bayes_mlp(net: torch.nn.Sequential, batch: int) -> torch.nn.Sequential:
     while i < len(mods):
         if isinstance(mods[i], BayesLinear):
             run, slope, j = [mods[i]], None, i + 1
-            while (j + 1 < len(mods) and isinstance(mods[j], torch.nn.LeakyReLU)
+            # grow the run only over layers the tensor-core path tiles: a narrow head (C2's 1200 -> 10) must not
+            # keep the wide layers in front of it from chaining
+            while (FusedBayesMLP.supported(run, batch)
+                   and j + 1 < len(mods) and isinstance(mods[j], torch.nn.LeakyReLU)
                    and isinstance(mods[j + 1], BayesLinear)
+                   and FusedBayesMLP.supported([mods[j + 1]], batch)
                    and (slope is None or slope == mods[j].negative_slope)):
                 slope = mods[j].negative_slope
                 run.append(mods[j + 1])

@@ -316,6 +316,39 @@ def test_fused_mlp_equals_unfused_bf16_chain(plb, mc, b, dims, expand):
         assert torch.equal(a, r)
 
 
+def test_fused_chain_passes_gradients_upstream_and_fuses_supported_prefix(plb):
+    """A fused chain that is not the first module must hand dX to what precedes it, and a narrow head must not stop
+    the wide layers in front of it from chaining (fuse_bayes_mlp fuses the supported part of a run)."""
+    from pytorch_probabilisticlayers_b200.fused import fuse_bayes_mlp
+    mc, b = 2, 128
+    torch.manual_seed(5)
+    plb.manual_seed(77)
+    net = torch.nn.Sequential(plb.BayesLinear(24, 128), torch.nn.LeakyReLU(), plb.BayesLinear(128, 256),
+                              torch.nn.LeakyReLU(), plb.BayesLinear(256, 128), torch.nn.LeakyReLU(),
+                              plb.BayesLinear(128, 10)).cuda()
+    layers = [m for m in net if isinstance(m, plb.BayesLinear)]
+    for l in layers:
+        l.precision = "auto"
+    fused = fuse_bayes_mlp(net, b)
+    kinds = [type(m).__name__ for m in fused]
+    assert kinds == ["BayesLinear", "LeakyReLU", "FusedBayesMLP", "LeakyReLU", "BayesLinear"], kinds
+    x0 = torch.randn(mc, b, 24, device="cuda")
+    gy = torch.randn(mc, b, 10, device="cuda")
+
+    def run(model):
+        for l in layers:
+            l._calls = 0                              # same per-forward seed in both runs
+            l.zero_grad()
+        x = x0.clone().requires_grad_(True)
+        out = model(x)
+        (out * gy).sum().backward()
+        return [t.detach().clone() for t in (out, x.grad, layers[0].weight.loc.grad, layers[0].weight.logscale.grad,
+                                             layers[1].weight.loc.grad)]
+    ref, got = run(net), run(fused)
+    for a, r in zip(got, ref):
+        assert rel_err(a.cpu().numpy(), r.cpu().numpy()) < 5e-3
+
+
 def test_tc_backward_mc_shards_sum_to_unsharded_gradients(plb):
     """Full-width layer (4096 x 1024), bf16 kernels: the gradients of two MC shards add up to the
     unsharded gradients (the property the one-all-reduce-per-step train step relies on)."""
@@ -350,7 +383,7 @@ def test_tc_backward_mc_shards_sum_to_unsharded_gradients(plb):
 def test_train_step_with_fused_chain_matches_module_by_module(plb):
     from pytorch_probabilisticlayers_b200.fused import fuse_bayes_mlp
     from pytorch_probabilisticlayers_b200.train import ELBOTrainStep
-    dims, mc, b, ns = [256, 384, 256, 16], 4, 256, 1000
+    dims, mc, b, ns = [256, 384, 256, 16], 4, 256, 1000     # 256 -> 16 head: fp32 kernels after a fused bf16 chain
     results = []
     for fuse in (False, True):
         torch.manual_seed(5)
@@ -378,5 +411,5 @@ def test_train_step_with_fused_chain_matches_module_by_module(plb):
     (s0, p0), (s1, p1) = results
     for a, c in zip(s0, s1):
         assert abs(a[3] - c[3]) / abs(a[3]) < 1e-4                   # loss trajectory
-    for a, c in zip(p0, p1):
-        assert rel_err(c.cpu().numpy(), a.cpu().numpy()) < 2e-3
+    for a, c in zip(p0, p1):     # the chained dX / bias gradients see bf16-rounded dY: bf16 tolerance after 3 Adam steps
+        assert rel_err(c.cpu().numpy(), a.cpu().numpy()) < BF16_TOL
