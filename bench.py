@@ -292,10 +292,27 @@ def run_b200(args, wl):
         stats = step_resident()
     torch.cuda.synchronize()
 
+    # ---- roofline leg: per-call CUDA events over a few steps (same stream); before the timed region so that it
+    # still sees individual launches when the step is replayed from a CUDA graph afterwards ----
+    prof_steps = max(2, min(args.steps, 5))
+    barrier()
+    PF.profile_start()
+    for _ in range(prof_steps):
+        step_resident()
+    prof = PF.profile_stop()
+    launches_per_step = None
+    if args.cuda_graph:
+        assert world == 1, "--cuda-graph is a single-GPU option in this round"
+        l1 = lib.pl_launch_count()
+        step_resident()
+        launches_per_step = lib.pl_launch_count() - l1      # the graph replays exactly these launches
+        trainer.enable_cuda_graph(x_dev, y_dev)
+    torch.cuda.synchronize()
+
     # ---- headline: device-resident inputs ----
     l0 = lib.pl_launch_count()
     ms_total = timed(step_resident, args.steps)
-    launches = (lib.pl_launch_count() - l0) // 1
+    launches = (lib.pl_launch_count() - l0) if launches_per_step is None else launches_per_step * args.steps
     clock_info = clocks.stop() if clocks else None
     ms_step = ms_total / args.steps
     value = mc_total * batch / (ms_step * 1e-3)
@@ -306,13 +323,6 @@ def run_b200(args, wl):
     ms_e2e = timed(step_e2e, args.steps) / args.steps
     e2e_value = mc_total * batch / (ms_e2e * 1e-3)
 
-    # ---- roofline leg: per-call CUDA events over a few more steps (same stream) ----
-    prof_steps = max(2, min(args.steps, 5))
-    barrier()
-    PF.profile_start()
-    for _ in range(prof_steps):
-        step_resident()
-    prof = PF.profile_stop()
     final_stats = stats.tolist()
 
     # ---- N > 1 only, report-only: the same step with the per-GPU share held at the full MC (weak scaling:
@@ -412,6 +422,7 @@ def run_b200(args, wl):
         "config": {"workload": wl["name"], "mc_total": mc_total, "mc_per_gpu": mc_local,
                    "batch": batch, "num_samples": ns, "precision": args.precision,
                    "fused_chain": bool(args.fuse and not wl.get("conv") and args.precision in ("auto", "bf16")),
+                   "cuda_graph": bool(args.cuda_graph),
                    "parallelism": f"mc-shard x{world}" if world > 1 else "single",
                    "l2": "per-step working set (parameters + activations >> 126 MB) exceeds L2; "
                          "no explicit flush"},
@@ -447,6 +458,8 @@ def main():
     ap.add_argument("--mc", type=int, default=0,
                     help="developer option: override the workload's MC (e.g. 8 = the per-GPU share at N=8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="replay the whole step from a CUDA graph (device-side seed / Adam schedule); single GPU")
     ap.add_argument("--no-fuse", dest="fuse", action="store_false",
                     help="run BayesLinear / LeakyReLU module by module instead of as a fused chain")
     args = ap.parse_args()

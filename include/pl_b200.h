@@ -99,6 +99,11 @@ int pl_kl_bwd(const float* mu, const float* rho, int64_t n, float prior_scale,
 int pl_adam_kl_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t kind,
                     float prior_scale, float kl_scale, float lr, float beta1, float beta2, float eps,
                     int32_t step, double* kl_value, void* stream);
+/* The same pass with the step-dependent scalars read from device memory: sched_dev[0] = lr / (1 - beta1^t),
+ * sched_dev[1] = 1 / sqrt(1 - beta2^t).  For CUDA-graph replays, where the caller advances t on the device. */
+int pl_adam_kl_step_dev(float* p, const float* g, float* m, float* v, int64_t n, int32_t kind,
+                        float prior_scale, float kl_scale, float beta1, float beta2, float eps,
+                        const float* sched_dev, double* kl_value, void* stream);
 
 /* ---- MC-first cross entropy + accuracy + gradient (replaces MC_CrossEntropyLoss.forward,
  *      src/ProbabilisticLayers.py:32-43, MC_Accuracy, :46-90, and the autograd backward of both) ----
@@ -208,6 +213,9 @@ typedef struct pl_linear_args {
   const void* dy_lp; /* bwd: dY as bf16 [mc,batch,out]; replaces the cast pre-pass (dy may be NULL) */
   void* dx_lp;       /* bwd: write dX * act'(x) as bf16 [mc,batch,in] (needs x_lp); dx may be NULL */
   float x_act_slope; /* slope of the LeakyReLU that produced x: act'(x) = x > 0 ? 1 : x_act_slope */
+  const uint64_t* seed_dev; /* optional device pointer: the eps stream uses seed + *seed_dev (mod 2^64).  A captured
+                               CUDA graph replays fixed launch parameters, so the per-step part of the seed lives in
+                               device memory and is advanced inside the graph; NULL = seed as given. */
 } pl_linear_args;
 
 size_t pl_linear_workspace_bytes(const pl_linear_args* a);
@@ -249,6 +257,7 @@ typedef struct pl_conv2d_args {
      leaves the bf16 im2col matrix there and pl_conv2d_bwd given the same buffer does not rebuild it */
   void* fwd_state;
   size_t fwd_state_bytes;
+  const uint64_t* seed_dev; /* as pl_linear_args.seed_dev */
 } pl_conv2d_args;
 
 size_t pl_conv2d_workspace_bytes(const pl_conv2d_args* a);

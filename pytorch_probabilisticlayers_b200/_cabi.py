@@ -23,7 +23,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32}
 
 EXPORTS = (
     "pl_version", "pl_last_error", "pl_launch_count", "pl_device_supported", "pl_eps_dump",
-    "pl_kl_workspace_bytes", "pl_kl_fwd", "pl_kl_bwd", "pl_adam_kl_step",
+    "pl_kl_workspace_bytes", "pl_kl_fwd", "pl_kl_bwd", "pl_adam_kl_step", "pl_adam_kl_step_dev",
     "pl_mc_cross_entropy_workspace_bytes", "pl_mc_cross_entropy",
     "pl_bn_stats", "pl_bn_act_pool_workspace_bytes", "pl_bn_act_pool_fwd", "pl_bn_act_pool_bwd",
     "pl_linear_workspace_bytes", "pl_linear_state_bytes", "pl_linear_fwd", "pl_linear_bwd",
@@ -45,6 +45,7 @@ class LinearArgs(C.Structure):
         ("fwd_state", C.c_void_p), ("fwd_state_bytes", C.c_size_t),
         ("x_lp", C.c_void_p), ("y_lp", C.c_void_p), ("y_act", C.c_int32), ("y_act_slope", C.c_float),
         ("dy_lp", C.c_void_p), ("dx_lp", C.c_void_p), ("x_act_slope", C.c_float),
+        ("seed_dev", C.c_void_p),
     ]
 
 
@@ -61,6 +62,7 @@ class Conv2dArgs(C.Structure):
         ("dw_mu", C.c_void_p), ("dw_rho", C.c_void_p), ("db_mu", C.c_void_p), ("db_rho", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("stream", C.c_void_p),
         ("fwd_state", C.c_void_p), ("fwd_state_bytes", C.c_size_t),
+        ("seed_dev", C.c_void_p),
     ]
 
 
@@ -118,6 +120,10 @@ def lib():
                 l.pl_adam_kl_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                               C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
                                               C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p]
+                l.pl_adam_kl_step_dev.restype = C.c_int
+                l.pl_adam_kl_step_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                                  C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
+                                                  C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
                 l.pl_mc_cross_entropy_workspace_bytes.restype = C.c_size_t
                 l.pl_mc_cross_entropy.restype = C.c_int
                 l.pl_mc_cross_entropy.argtypes = [C.POINTER(CeArgs)]

@@ -31,7 +31,12 @@ template <int kKind>
 __global__ void __launch_bounds__(256)
 adam_kl_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                float* __restrict__ v, int64_t n, float ip2, float kl_scale, float step_size,
-               float inv_sqrt_bc2, float beta1, float beta2, float eps, double* __restrict__ kl_out) {
+               float inv_sqrt_bc2, float beta1, float beta2, float eps, double* __restrict__ kl_out,
+               const float* __restrict__ sched_dev) {
+  if (sched_dev) {   // CUDA-graph replays: the step-dependent scalars live in device memory
+    step_size = __ldg(sched_dev);
+    inv_sqrt_bc2 = __ldg(sched_dev + 1);
+  }
   float kl = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     const float w = p[i];
@@ -66,15 +71,16 @@ adam_kl_kernel(float* __restrict__ p, const float* __restrict__ g, float* __rest
 
 }  // namespace pl
 
-extern "C" int pl_adam_kl_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t kind,
+static int adam_kl_launch(const float* sched_dev, float* p, const float* g, float* m, float* v, int64_t n, int32_t kind,
                                float prior_scale, float kl_scale, float lr, float beta1, float beta2,
                                float eps, int32_t step, double* kl_value, void* stream) {
   using namespace pl;
   PL_CHECK_ARG(p && g && m && v, "pl_adam_kl_step: NULL pointer");
-  PL_CHECK_ARG(n >= 0 && step >= 1, "pl_adam_kl_step: bad n / step");
+  PL_CHECK_ARG(n >= 0 && (sched_dev || step >= 1), "pl_adam_kl_step: bad n / step");
   PL_CHECK_ARG(kind >= 0 && kind <= 2, "pl_adam_kl_step: kind must be 0, 1 or 2");
   PL_CHECK_ARG(kind == 0 || prior_scale > 0.f, "pl_adam_kl_step: prior_scale must be > 0");
   if (n == 0) return PL_OK;
+  if (sched_dev) step = 1;   // host-side scalars unused
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   const float ip2 = kind ? 1.f / (prior_scale * prior_scale) : 0.f;
@@ -85,10 +91,28 @@ extern "C" int pl_adam_kl_step(float* p, const float* g, float* m, float* v, int
     // constant part of the KL value of this (mu, rho) pair is added with the rho tensor
   }
   switch (kind) {
-    case 0: adam_kl_kernel<0><<<(int)blocks, 256, 0, st>>>(p, g, m, v, n, ip2, kl_scale, step_size, inv_sqrt_bc2, beta1, beta2, eps, kl_value); break;
-    case 1: adam_kl_kernel<1><<<(int)blocks, 256, 0, st>>>(p, g, m, v, n, ip2, kl_scale, step_size, inv_sqrt_bc2, beta1, beta2, eps, kl_value); break;
-    default: adam_kl_kernel<2><<<(int)blocks, 256, 0, st>>>(p, g, m, v, n, ip2, kl_scale, step_size, inv_sqrt_bc2, beta1, beta2, eps, kl_value); break;
+    case 0: adam_kl_kernel<0><<<(int)blocks, 256, 0, st>>>(p, g, m, v, n, ip2, kl_scale, step_size, inv_sqrt_bc2, beta1, beta2, eps, kl_value, sched_dev); break;
+    case 1: adam_kl_kernel<1><<<(int)blocks, 256, 0, st>>>(p, g, m, v, n, ip2, kl_scale, step_size, inv_sqrt_bc2, beta1, beta2, eps, kl_value, sched_dev); break;
+    default: adam_kl_kernel<2><<<(int)blocks, 256, 0, st>>>(p, g, m, v, n, ip2, kl_scale, step_size, inv_sqrt_bc2, beta1, beta2, eps, kl_value, sched_dev); break;
   }
   PL_LAUNCH_CHECK("adam_kl_kernel");
   return PL_OK;
+}
+
+extern "C" int pl_adam_kl_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t kind,
+                               float prior_scale, float kl_scale, float lr, float beta1, float beta2,
+                               float eps, int32_t step, double* kl_value, void* stream) {
+  return adam_kl_launch(nullptr, p, g, m, v, n, kind, prior_scale, kl_scale, lr, beta1, beta2, eps, step, kl_value,
+                        stream);
+}
+
+extern "C" int pl_adam_kl_step_dev(float* p, const float* g, float* m, float* v, int64_t n, int32_t kind,
+                                   float prior_scale, float kl_scale, float beta1, float beta2, float eps,
+                                   const float* sched_dev, double* kl_value, void* stream) {
+  if (!sched_dev) {
+    pl::set_error("pl_adam_kl_step_dev: NULL sched_dev");
+    return PL_ERR_BAD_ARG;
+  }
+  return adam_kl_launch(sched_dev, p, g, m, v, n, kind, prior_scale, kl_scale, 1.0f, beta1, beta2, eps, 1, kl_value,
+                        stream);
 }

@@ -110,16 +110,31 @@ struct Sampler {
   uint32_t k0, k1;     // seed
   uint32_t stream;     // 2*layer_id + is_bias
   uint32_t mc_offset;  // global MC index of local sample 0
+  const uint64_t* seed_dev;   // optional device-resident offset added to the seed (CUDA-graph replays), else NULL
 };
 
 __host__ __device__ inline Sampler make_sampler(uint64_t seed, uint32_t layer_id, bool bias,
-                                                uint32_t mc_offset) {
+                                                uint32_t mc_offset, const uint64_t* seed_dev = nullptr) {
   Sampler s;
   s.k0 = (uint32_t)(seed & 0xffffffffu);
   s.k1 = (uint32_t)(seed >> 32);
   s.stream = 2u * layer_id + (bias ? 1u : 0u);
   s.mc_offset = mc_offset;
+  s.seed_dev = seed_dev;
   return s;
+}
+
+// The sampler a kernel actually uses: key = seed + *seed_dev (mod 2^64) when a device-side offset is given.
+// A captured CUDA graph replays the same launch parameters every step; the per-step part of the seed therefore
+// lives in device memory and is advanced by one small kernel inside the graph.  Call once at kernel entry.
+__device__ __forceinline__ Sampler live(const Sampler& s) {
+  Sampler r = s;
+  if (s.seed_dev) {
+    const uint64_t key = (((uint64_t)s.k1 << 32) | (uint64_t)s.k0) + *s.seed_dev;
+    r.k0 = (uint32_t)(key & 0xffffffffu);
+    r.k1 = (uint32_t)(key >> 32);
+  }
+  return r;
 }
 
 // 8 standard normals for columns 8*group8 .. 8*group8+7 of `row` of MC sample `mc` (local index):

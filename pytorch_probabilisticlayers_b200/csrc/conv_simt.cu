@@ -92,6 +92,8 @@ __device__ __forceinline__ void conv_fma_tile(const float (*As)[kCT + kCPad],
 
 // forward: grid (ceil(Cout/64), ceil(M/64), MC)
 __global__ void __launch_bounds__(kCThreads) conv_fwd_simt(ConvParams p) {
+  p.sw = live(p.sw);   // seed + device-side offset (CUDA-graph replays), see common.cuh
+  p.sb = live(p.sb);
   __shared__ __align__(16) float As[kCK][kCT + kCPad];  // [kidx][pixel row]
   __shared__ __align__(16) float Bs[kCK][kCT + kCPad];  // [kidx][cout]
   const int mc = blockIdx.z, m0 = blockIdx.y * kCT, c0 = blockIdx.x * kCT;
@@ -143,6 +145,8 @@ __global__ void __launch_bounds__(kCThreads) conv_fwd_simt(ConvParams p) {
 
 // dX: M = B*H*W input pixels, N = Cin, K = Cout*k*k.   grid (ceil(Cin/64), ceil(M/64), MC)
 __global__ void __launch_bounds__(kCThreads) conv_dx_simt(ConvParams p) {
+  p.sw = live(p.sw);   // seed + device-side offset (CUDA-graph replays), see common.cuh
+  p.sb = live(p.sb);
   __shared__ __align__(16) float As[kCK][kCT + kCPad];  // [(co,kh,kw)][input pixel]
   __shared__ __align__(16) float Bs[kCK][kCT + kCPad];  // [(co,kh,kw)][cin]
   const int mc = blockIdx.z, m0 = blockIdx.y * kCT, c0 = blockIdx.x * kCT;
@@ -208,6 +212,8 @@ __global__ void __launch_bounds__(kCThreads) conv_dx_simt(ConvParams p) {
 
 // dW: tile (cout rows, kidx cols), loop MC and output pixels.  grid (ceil(Kdim/64), ceil(Cout/64))
 __global__ void __launch_bounds__(kCThreads) conv_dw_simt(ConvParams p) {
+  p.sw = live(p.sw);   // seed + device-side offset (CUDA-graph replays), see common.cuh
+  p.sb = live(p.sb);
   __shared__ __align__(16) float As[kCK][kCT + kCPad];  // [pixel][cout]
   __shared__ __align__(16) float Bs[kCK][kCT + kCPad];  // [pixel][kidx]
   const int c0 = blockIdx.y * kCT, q0 = blockIdx.x * kCT;
@@ -263,6 +269,8 @@ __global__ void __launch_bounds__(kCThreads) conv_dw_simt(ConvParams p) {
 
 // colsum[mc][co] = sum_{b,pix} dy ; one CTA per (co, mc)
 __global__ void __launch_bounds__(256) conv_bias_colsum_kernel(ConvParams p) {
+  p.sw = live(p.sw);   // seed + device-side offset (CUDA-graph replays), see common.cuh
+  p.sb = live(p.sb);
   __shared__ float sm[8];
   const int co = blockIdx.x, mc = blockIdx.y, hwo = p.ho * p.wo;
   const float* dyp = p.dy + (int64_t)mc * p.batch * p.cout * hwo;
@@ -283,6 +291,8 @@ __global__ void __launch_bounds__(256) conv_bias_colsum_kernel(ConvParams p) {
 }
 
 __global__ void __launch_bounds__(128) conv_bias_grad_kernel(ConvParams p) {
+  p.sw = live(p.sw);   // seed + device-side offset (CUDA-graph replays), see common.cuh
+  p.sb = live(p.sb);
   const int o = blockIdx.x * 128 + threadIdx.x;
   if (o >= p.cout) return;
   float am = 0.f, ar = 0.f;
@@ -317,8 +327,8 @@ static int fill_conv(const pl_conv2d_args* a, ConvParams& p, const char* who) {
   p.x = a->x; p.x_mc_stride = a->x_mc_stride;
   p.w_mu = a->w_mu; p.w_rho = a->w_rho; p.b_mu = a->b_mu; p.b_rho = a->b_rho;
   p.eps_w = a->eps_w; p.eps_b = a->eps_b;
-  p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
-  p.sb = make_sampler(a->seed, a->layer_id, true, a->mc_global_offset);
+  p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset, a->seed_dev);
+  p.sb = make_sampler(a->seed, a->layer_id, true, a->mc_global_offset, a->seed_dev);
   p.y = a->y; p.dy = a->dy; p.dx = a->dx;
   p.dw_mu = a->dw_mu; p.dw_rho = a->dw_rho; p.db_mu = a->db_mu; p.db_rho = a->db_rho;
   p.colsum = (float*)a->workspace;

@@ -295,7 +295,7 @@ int conv_fwd_tc_launch(const pl_conv2d_args* a) {
   rc = prep_params(a->w_mu, a->w_rho, w.sigma, g.cout, g.K, false, st);
   if (rc != PL_OK) return rc;
   sample_bias_kernel<<<ew_grid((int64_t)g.mc * ((g.cout + 3) / 4), 256), 256, 0, st>>>(
-      a->b_mu, a->b_rho, a->eps_b, make_sampler(a->seed, a->layer_id, true, a->mc_global_offset), g.mc,
+      a->b_mu, a->b_rho, a->eps_b, make_sampler(a->seed, a->layer_id, true, a->mc_global_offset, a->seed_dev), g.mc,
       g.cout, w.bias);
   PL_LAUNCH_CHECK("sample_bias_kernel");
   rc = launch_im2col(a, g, w.A, st);
@@ -308,7 +308,7 @@ int conv_fwd_tc_launch(const pl_conv2d_args* a) {
   p.w_in = g.cout; p.w_out = g.K;
   p.a_mc_rows = g.mcx == 1 ? 0 : g.M;
   p.w_mu = a->w_mu; p.w_sigma = w.sigma; p.w_pack = (const uint4*)w.sigma; p.eps_w = a->eps_w;
-  p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
+  p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset, a->seed_dev);
   p.bias = w.bias;
   p.out = a->y;
   p.out_hw = g.ho * g.wo;
@@ -356,7 +356,7 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     p.dy_broadcast = g.mcx == 1;
     p.w_aligned = (g.K % 4) == 0;
     p.w_rho = a->w_rho; p.eps_w = a->eps_w;
-    p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
+    p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset, a->seed_dev);
     p.dw_mu = a->dw_mu; p.dw_rho = a->dw_rho;
     // few weight tiles, long pixel reduction: one CTA per (tile, MC sample, pixel chunk)
     const int tiles = ((g.cout + 127) / 128) * ((g.K + 127) / 128);
@@ -394,7 +394,7 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     p.w_in = g.cout; p.w_out = g.K;
     p.a_mc_rows = g.M;
     p.w_mu = a->w_mu; p.w_sigma = w.sigma; p.w_pack = (const uint4*)w.sigma; p.eps_w = a->eps_w;
-    p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
+    p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset, a->seed_dev);
     p.bias = nullptr;
     p.out = nullptr;
     p.out_lp = w.dA;              // bf16 [mc][K][M]: K-major so that col2im reads contiguous pixels

@@ -89,6 +89,8 @@ __device__ __forceinline__ void fma_tile(const float (*As)[kT + kPad], const flo
 // forward: Y[mc] = X[mc] . W[mc] + b[mc]      grid (ceil(O/64), ceil(B/64), MC)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) linear_fwd_simt(LinearParams p) {
+  p.sw = live(p.sw);   // seed + device-side offset (CUDA-graph replays), see common.cuh
+  p.sb = live(p.sb);
   __shared__ __align__(16) float As[kK][kT + kPad];  // [k][batch row]
   __shared__ __align__(16) float Bs[kK][kT + kPad];  // [k][out col]
   const int mc = blockIdx.z, b0 = blockIdx.y * kT, o0 = blockIdx.x * kT;
@@ -144,6 +146,8 @@ __global__ void __launch_bounds__(kThreads) linear_fwd_simt(LinearParams p) {
 // dX[mc] = dY[mc] . W[mc]^T                   grid (ceil(I/64), ceil(B/64), MC)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) linear_dx_simt(LinearParams p) {
+  p.sw = live(p.sw);   // seed + device-side offset (CUDA-graph replays), see common.cuh
+  p.sb = live(p.sb);
   __shared__ __align__(16) float As[kK][kT + kPad];  // [o][batch row]
   __shared__ __align__(16) float Bs[kK][kT + kPad];  // [o][in col]
   const int mc = blockIdx.z, b0 = blockIdx.y * kT, i0 = blockIdx.x * kT;
@@ -191,6 +195,8 @@ __global__ void __launch_bounds__(kThreads) linear_dx_simt(LinearParams p) {
 // partial sums are combined with atomics into zero-initialised outputs (p.dw_atomic).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) linear_dw_simt(LinearParams p) {
+  p.sw = live(p.sw);   // seed + device-side offset (CUDA-graph replays), see common.cuh
+  p.sb = live(p.sb);
   __shared__ __align__(16) float As[kK][kT + kPad];  // [b][in row]
   __shared__ __align__(16) float Bs[kK][kT + kPad];  // [b][out col]
   const int i0 = blockIdx.y * kT, o0 = blockIdx.x * kT;
@@ -264,6 +270,8 @@ __global__ void __launch_bounds__(kThreads) linear_dw_simt(LinearParams p) {
 // bias gradients: colsum[mc][o] = sum_b dY[mc][b][o], then a deterministic pass over MC
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bias_colsum_kernel(LinearParams p) {
+  p.sw = live(p.sw);   // seed + device-side offset (CUDA-graph replays), see common.cuh
+  p.sb = live(p.sb);
   __shared__ float sm[8][33];
   const int mc = blockIdx.y, o = blockIdx.x * 32 + threadIdx.x, ys = threadIdx.y;
   const float* dyp = p.dy + (int64_t)mc * p.batch * p.out;
@@ -287,6 +295,8 @@ __global__ void __launch_bounds__(256) bias_colsum_kernel(LinearParams p) {
 }
 
 __global__ void __launch_bounds__(128) bias_grad_kernel(LinearParams p) {
+  p.sw = live(p.sw);   // seed + device-side offset (CUDA-graph replays), see common.cuh
+  p.sb = live(p.sb);
   const int o = blockIdx.x * 128 + threadIdx.x;
   if (o >= p.out) return;
   float am = 0.f, ar = 0.f;
@@ -318,8 +328,8 @@ static int fill_params(const pl_linear_args* a, LinearParams& p, const char* who
   p.x = a->x; p.x_mc_stride = a->x_mc_stride;
   p.w_mu = a->w_mu; p.w_rho = a->w_rho; p.b_mu = a->b_mu; p.b_rho = a->b_rho;
   p.eps_w = a->eps_w; p.eps_b = a->eps_b;
-  p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
-  p.sb = make_sampler(a->seed, a->layer_id, true, a->mc_global_offset);
+  p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset, a->seed_dev);
+  p.sb = make_sampler(a->seed, a->layer_id, true, a->mc_global_offset, a->seed_dev);
   p.y = a->y; p.dy = a->dy; p.dx = a->dx;
   p.dw_mu = a->dw_mu; p.dw_rho = a->dw_rho; p.db_mu = a->db_mu; p.db_rho = a->db_rho;
   p.colsum = (float*)a->workspace;

@@ -140,7 +140,7 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   }
   if (a->b_mu) {
     sample_bias_kernel<<<ew_grid(MC * ((O + 3) / 4), 256), 256, 0, st>>>(
-        a->b_mu, a->b_rho, a->eps_b, make_sampler(a->seed, a->layer_id, true, a->mc_global_offset),
+        a->b_mu, a->b_rho, a->eps_b, make_sampler(a->seed, a->layer_id, true, a->mc_global_offset, a->seed_dev),
         (int)MC, (int)O, w.bias);
     PL_LAUNCH_CHECK("sample_bias_kernel");
   }
@@ -154,7 +154,7 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   p.w_in = (int)I; p.w_out = (int)O;
   p.a_mc_rows = a->x_mc_stride == 0 ? 0 : B;
   p.w_mu = a->w_mu; p.w_sigma = state.sigma; p.w_pack = (const uint4*)state.sigma; p.eps_w = a->eps_w;
-  p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
+  p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset, a->seed_dev);
   p.bias = a->b_mu ? w.bias : nullptr;
   p.out = a->y;
   p.out_hw = 0;
@@ -213,7 +213,7 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
   }
   if (a->db_mu) {
     bias_grad_tc_kernel<<<(unsigned)((O + 127) / 128), 128, 0, st>>>(
-        w.colsum, a->b_rho, a->eps_b, make_sampler(a->seed, a->layer_id, true, a->mc_global_offset),
+        w.colsum, a->b_rho, a->eps_b, make_sampler(a->seed, a->layer_id, true, a->mc_global_offset, a->seed_dev),
         (int)MC, (int)O, a->db_mu, a->db_rho);
     PL_LAUNCH_CHECK("bias_grad_tc_kernel");
   }
@@ -227,7 +227,7 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
     p.w_in = (int)I; p.w_out = (int)O;
     p.a_mc_rows = B;
     p.w_mu = a->w_mu; p.w_sigma = state.sigma; p.w_pack = (const uint4*)state.sigma; p.eps_w = a->eps_w;
-    p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
+    p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset, a->seed_dev);
     p.bias = nullptr;
     p.out = a->dx;
     p.out_hw = 0;
@@ -262,7 +262,7 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
     p.dy_broadcast = 0;
     p.w_aligned = 1;
     p.w_rho = a->w_rho; p.eps_w = a->eps_w;
-    p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset);
+    p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset, a->seed_dev);
     p.dw_mu = a->dw_mu; p.dw_rho = a->dw_rho;
     const int tiles = (int)(((I + 127) / 128) * ((O + 127) / 128));
     int splits = 1;

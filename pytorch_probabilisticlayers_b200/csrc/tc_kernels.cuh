@@ -107,6 +107,7 @@ static __global__ void __launch_bounds__(256) sample_bias_kernel(const float* __
                                                           const float* __restrict__ b_rho,
                                                           const float* __restrict__ eps_b, Sampler sb,
                                                           int mc, int out, float* __restrict__ dst) {
+  sb = live(sb);
   const int groups = (out + 3) / 4;
   for (int t = blockIdx.x * 256 + threadIdx.x; t < mc * groups; t += gridDim.x * 256) {
     const int m = t / groups, g = t - m * groups;
@@ -202,6 +203,7 @@ static __global__ void __launch_bounds__(128) bias_grad_tc_kernel(const float* _
                                                            const float* __restrict__ eps_b, Sampler sb,
                                                            int mc, int out, float* __restrict__ db_mu,
                                                            float* __restrict__ db_rho) {
+  sb = live(sb);
   const int o = blockIdx.x * 128 + threadIdx.x;
   if (o >= out) return;
   float am = 0.f, ar = 0.f;
@@ -345,13 +347,13 @@ struct WGen {
   // The Philox words of a k-block are drawn one iteration ahead (words()) so that, inside one basic block,
   // the integer-multiply chain of block kb+1 interleaves with the MUFU-bound Box-Muller of block kb.
   uint4 wd[kInjected ? 1 : kGr];
-  __device__ __forceinline__ void words(const TcGemmParams& p, int mc, int k0) {
+  __device__ __forceinline__ void words(const TcGemmParams& p, const Sampler& sw, int mc, int k0) {
     if (kInjected) return;
 #pragma unroll
     for (int r = 0; r < kGr; ++r) {
       const int rown = kDx ? wrow[r] : k0 + wrow[r], coln = kDx ? k0 + wcol : wcol;
-      wd[r] = philox4x32_10((uint32_t)(coln >> 3), (uint32_t)rown, p.sw.mc_offset + (uint32_t)mc, p.sw.stream,
-                            p.sw.k0, p.sw.k1);
+      wd[r] = philox4x32_10((uint32_t)(coln >> 3), (uint32_t)rown, sw.mc_offset + (uint32_t)mc, sw.stream,
+                            sw.k0, sw.k1);
     }
   }
   __device__ __forceinline__ void noise() {
@@ -547,6 +549,7 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
     // ===================== W-tile generators =====================
     // operand element (n, k): forward W[i = k0+k][o = n0+n]; dX W[i = n0+n][o = k0+k]
     const int gw = warp - 2;  // 0..15
+    const Sampler sw = live(p.sw);
     WGen<kDx, kInjected, kTf32> gen;
     gen.init(gw, lane, n0);
     // tiles fully inside the weight matrix take the predicate-free path
@@ -558,13 +561,13 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
       else gen.template load<false>(p, mc, kb * kBKe);
 #endif
     };
-    gen.words(p, mc, 0);
+    gen.words(p, sw, mc, 0);
     load_block(0);
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % Cfg::kStagesB, ph = (kb / Cfg::kStagesB) & 1;
 #if PL_PROBE_W != 3
       gen.noise();                            // Box-Muller of this block ...
-      gen.words(p, mc, (kb + 1) * kBKe);      // ... interleaved with the Philox chain of the next one
+      gen.words(p, sw, mc, (kb + 1) * kBKe);      // ... interleaved with the Philox chain of the next one
       gen.pin();
 #endif
       // The previous k-block is published only now.  fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC:
@@ -788,6 +791,7 @@ sampled_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams 
   } else {
     // ===================== W-tile generators (both CTAs, own 128 columns) =====================
     const int gw = warp - 2;  // 0..15
+    const Sampler sw = live(p.sw);
     WGen<kDx, kInjected, false> gen;
     gen.init(gw, lane, nb0);
     const bool n_full = p.w_aligned && (kDx ? (nb0 + 128 <= p.w_in) : (nb0 + 128 <= p.w_out));
@@ -796,12 +800,12 @@ sampled_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams 
       if (n_full && (kb + 1) * kBK <= k_extent) gen.template load<true>(p, mc, kb * kBK);
       else gen.template load<false>(p, mc, kb * kBK);
     };
-    gen.words(p, mc, 0);
+    gen.words(p, sw, mc, 0);
     load_block(0);
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % Cfg::kStagesB, ph = (kb / Cfg::kStagesB) & 1;
       gen.noise();
-      gen.words(p, mc, (kb + 1) * kBK);
+      gen.words(p, sw, mc, (kb + 1) * kBK);
       gen.pin();
       if (kb > 0) {   // deferred publish of the previous k-block (see the 1-CTA kernel)
         fence_proxy_async_smem();
@@ -989,6 +993,7 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
   } else {
     // ===================== epilogue: eps regeneration + MC reduction =====================
     const int gw = warp - 2, q = warp & 3, h = gw >> 2;
+    const Sampler sw = live(p.sw);
     constexpr int kCols = 128 / (kGenWarps / 4);   // weight columns per thread (32)
     const int row = i0 + q * 32 + lane;          // weight row (in-feature) this thread owns
     const int col0 = o0 + h * kCols;             // first of its weight columns
@@ -1015,7 +1020,7 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
                          ? __ldg(p.eps_w + ((int64_t)mc * p.w_in + row) * p.w_out + col + t)
                          : 0.f;
           } else {
-            eps8(p.sw, mc, row, col >> 3, e);
+            eps8(sw, mc, row, col >> 3, e);
           }
           const int j = c * 16 + g * 8;
 #pragma unroll

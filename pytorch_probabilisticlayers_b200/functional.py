@@ -23,6 +23,7 @@ class SampleSpec:
     layer_id: int = 0
     mc_global_offset: int = 0          # first global MC index owned by this rank
     precision: int = _cabi.PREC_FP32
+    seed_dev: int = 0                  # device address of a uint64 added to ``seed`` by the kernels (CUDA graphs)
 
 
 # ---- optional per-call CUDA-event timing (bench.py's roofline leg) -----------------------------
@@ -176,6 +177,7 @@ class _BayesLinearFn(torch.autograd.Function):
         a.w_mu, a.w_rho = _cabi.ptr(w_mu_c), _cabi.ptr(w_rho_c)
         a.b_mu, a.b_rho = _cabi.ptr(b_mu_c), _cabi.ptr(b_rho_c)
         a.seed, a.layer_id, a.mc_global_offset = spec.seed, spec.layer_id, spec.mc_global_offset
+        a.seed_dev = spec.seed_dev or None
         a.eps_w, a.eps_b = _cabi.ptr(eps_w_c), _cabi.ptr(eps_b_c)
         a.y = _cabi.ptr(y)
         # tensor-core path: sigma and the bf16 copy of x are kept for the backward instead of fp32 x
@@ -222,6 +224,7 @@ class _BayesLinearFn(torch.autograd.Function):
         a.w_mu, a.w_rho = _cabi.ptr(w_mu), _cabi.ptr(w_rho)
         a.b_mu, a.b_rho = _cabi.ptr(b_mu), _cabi.ptr(b_rho)
         a.seed, a.layer_id, a.mc_global_offset = spec.seed, spec.layer_id, spec.mc_global_offset
+        a.seed_dev = spec.seed_dev or None
         a.eps_w, a.eps_b = _cabi.ptr(eps_w), _cabi.ptr(eps_b)
         a.dy, a.dx = _cabi.ptr(dy), _cabi.ptr(dx)
         a.dw_mu, a.dw_rho = _cabi.ptr(dw_mu), _cabi.ptr(dw_rho)
@@ -280,6 +283,7 @@ class _BayesConv2dFn(torch.autograd.Function):
         a.x, a.x_mc_stride = _cabi.ptr(xb), x_stride
         a.w_mu, a.w_rho, a.b_mu, a.b_rho = (_cabi.ptr(t) for t in tens[:4])
         a.seed, a.layer_id, a.mc_global_offset = spec.seed, spec.layer_id, spec.mc_global_offset
+        a.seed_dev = spec.seed_dev or None
         a.eps_w, a.eps_b = _cabi.ptr(tens[4]), _cabi.ptr(tens[5])
         a.y = _cabi.ptr(y)
         state = None
@@ -322,6 +326,7 @@ class _BayesConv2dFn(torch.autograd.Function):
         a.x, a.x_mc_stride = _cabi.ptr(xb), x_stride
         a.w_mu, a.w_rho, a.b_mu, a.b_rho = (_cabi.ptr(t) for t in (w_mu, w_rho, b_mu, b_rho))
         a.seed, a.layer_id, a.mc_global_offset = spec.seed, spec.layer_id, spec.mc_global_offset
+        a.seed_dev = spec.seed_dev or None
         a.eps_w, a.eps_b = _cabi.ptr(eps_w), _cabi.ptr(eps_b)
         a.dy, a.dx = _cabi.ptr(dy), _cabi.ptr(dx)
         a.dw_mu, a.dw_rho, a.db_mu, a.db_rho = (_cabi.ptr(t) for t in (dw_mu, dw_rho, db_mu, db_rho))

@@ -50,6 +50,7 @@ class _FusedMLPFn(torch.autograd.Function):
                 a.b_mu, a.b_rho = _cabi.ptr(b_mu), _cabi.ptr(b_rho)
                 sp = specs[li]
                 a.seed, a.layer_id, a.mc_global_offset = sp.seed, sp.layer_id, sp.mc_global_offset
+                a.seed_dev = sp.seed_dev or None
                 if last:
                     y = torch.empty((mc, batch, fout), dtype=torch.float32, device=dev)
                     a.y = _cabi.ptr(y)
@@ -96,6 +97,7 @@ class _FusedMLPFn(torch.autograd.Function):
                 a.b_mu, a.b_rho = _cabi.ptr(b_mu), _cabi.ptr(b_rho)
                 sp = specs[li]
                 a.seed, a.layer_id, a.mc_global_offset = sp.seed, sp.layer_id, sp.mc_global_offset
+                a.seed_dev = sp.seed_dev or None
                 a.fwd_state, a.fwd_state_bytes = _cabi.ptr(states[li]), states[li].numel()
                 if li == 0:
                     a.x_mc_stride = x_stride            # layer 0 reads the bf16 x kept in its state

@@ -36,6 +36,7 @@ _STATE = {
     "eps_source": "philox",      # 'philox' | 'torch_cpu'
     "mc_global_offset": 0,       # first global MC index of this rank (MC sharding)
     "next_layer_id": 0,
+    "seed_dev": None,            # int64[1] CUDA tensor added to every seed on the device (CUDA-graph replays)
 }
 _GOLDEN = 0x9E3779B97F4A7C15
 
@@ -55,6 +56,15 @@ def set_eps_source(source: str):
     if source not in ("philox", "torch_cpu"):
         raise ValueError(f"eps_source must be 'philox' or 'torch_cpu', got {source!r}")
     _STATE["eps_source"] = source
+
+
+def set_seed_device_offset(t):
+    """``t``: int64[1] CUDA tensor (or None).  While set, the kernels draw eps with key ``seed + t[0]`` (mod 2^64):
+    a captured CUDA graph replays fixed launch parameters, so the step-dependent part of the seed is advanced on
+    the device (train.ELBOTrainStep.enable_cuda_graph).  The lazy ``.eps`` / ``.sampled_w`` views do not follow it."""
+    if t is not None and not (t.is_cuda and t.dtype == torch.int64 and t.numel() == 1):
+        raise ValueError("seed offset must be an int64[1] CUDA tensor")
+    _STATE["seed_dev"] = t
 
 
 def set_mc_shard(mc_global_offset: int):
@@ -200,6 +210,10 @@ class _FusedBayesLayer(torch.nn.Module):
         spec = PF.SampleSpec(seed=seed, layer_id=self.layer_id,
                              mc_global_offset=_STATE["mc_global_offset"],
                              precision=self._precision_code(tc_ok))
+        if _STATE["seed_dev"] is not None:
+            if self._injected is not None or (self.eps_source or _STATE["eps_source"]) != "philox":
+                raise RuntimeError("a device-side seed offset (CUDA-graph mode) needs the on-chip Philox sampler")
+            spec.seed_dev = _STATE["seed_dev"].data_ptr()
         eps_w = eps_b = None
         if self._injected is not None:
             eps_w, eps_b = self._injected

@@ -31,6 +31,8 @@ from .layers import BayesConv2d, BayesLinear, SIVILayer
 from .functional import mc_cross_entropy_raw
 from .loss import MC_Accuracy, MC_CrossEntropyLoss
 
+_GOLDEN_SIGNED = layers._GOLDEN - (1 << 64)     # the per-call seed increment as a signed 64-bit value
+
 
 def collect_kl_div(net, kinds=(BayesLinear, SIVILayer)):
     """Sum of ``kl_div`` over the layer kinds the reference's collect_kl_div matches
@@ -107,6 +109,8 @@ class ELBOTrainStep:
         # per-layer slices of the flat buffer for the overlapped all-reduce
         self.overlap = overlap and self.world > 1
         self._handles = []
+        self._graph = None         # CUDA-graph mode (enable_cuda_graph)
+        self._capturing = False
         self._slices = []          # (start, end, layer or None)
         self._inv = 1.0 / (self.num_samples * self.world)
         if self.overlap:
@@ -172,6 +176,53 @@ class ELBOTrainStep:
 
     def step(self, x, y):
         """One optimiser step; returns a device tensor [LL, KL, ACC, loss] (global values)."""
+        if self._graph is not None:
+            self._gx.copy_(x, non_blocking=True)
+            self._gy.copy_(y, non_blocking=True)
+            self._graph.replay()
+            self.adam_t += 1
+            return self._gout.clone()
+        return self._eager_step(x, y)
+
+    def enable_cuda_graph(self, x, y, warmup: int = 3):
+        """Capture one whole step (forward, loss, backward, all-reduce, optimiser) in a CUDA graph and replay it from
+        now on: for small configurations the step is bound by Python / launch overhead, not by the GPU.
+        A graph replays fixed launch parameters, so what changes from step to step moves to device memory: the
+        per-step part of the eps seed (``layers.set_seed_device_offset``; the kernels draw with seed + offset) and
+        Adam's bias-correction scalars (``pl_adam_kl_step_dev``), both advanced by small kernels inside the graph.
+        ``x`` / ``y`` fix the input shapes; later ``step(x, y)`` calls copy into static buffers.  Runs ``warmup``
+        ordinary steps first (they count as training steps)."""
+        dev = self.flat.device
+        if not (self.fused_opt and dev.type == "cuda"):
+            raise RuntimeError("CUDA-graph mode needs the fused optimiser pass on a CUDA device")
+        if any(isinstance(m, SIVILayer) for m in self.net.modules()):
+            raise RuntimeError("CUDA-graph mode does not support SIVILayer (its hyper-net noise is drawn per call)")
+        self._gx, self._gy = x.clone(), y.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(int(warmup), 1)):
+                self._eager_step(self._gx, self._gy)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._t_dev = torch.full((1,), float(self.adam_t), dtype=torch.float64, device=dev)
+        self._sched = torch.zeros(2, dtype=torch.float32, device=dev)
+        layers.set_seed_device_offset(self._seed_dev)
+        graph = torch.cuda.CUDAGraph()
+        self._capturing = True
+        try:
+            with torch.cuda.graph(graph):
+                self._gout = self._eager_step(self._gx, self._gy)
+                # advance the device-side step state for the NEXT replay
+                self._seed_dev.add_(_GOLDEN_SIGNED)
+        finally:
+            self._capturing = False
+            layers.set_seed_device_offset(None)
+        self.adam_t -= 1            # the capture pass enqueued nothing: it was not a step
+        self._graph = graph
+        return self
+
+    def _eager_step(self, x, y):
         self.flat.zero_()
         pred = self.net(x)
         inv = 1.0 / (self.num_samples * self.world)
@@ -239,6 +290,11 @@ class ELBOTrainStep:
         dev = self.flat.device
         stream = _cabi.current_stream(dev)
         kl_scale = 1.0 / self.num_samples       # gradients are already summed over ranks
+        if self._capturing:                     # step-dependent scalars from device memory (see enable_cuda_graph)
+            self._t_dev.add_(1.0)
+            bc1 = 1.0 - torch.pow(torch.full_like(self._t_dev, self.betas[0]), self._t_dev)
+            bc2 = 1.0 - torch.pow(torch.full_like(self._t_dev, self.betas[1]), self._t_dev)
+            self._sched.copy_(torch.cat([self.lr / bc1, torch.rsqrt(bc2)]).float())
         # all-reduce slices complete in launch order; update each tensor as soon as ITS slice has arrived
         pending, waited = self._handles, 0
 
@@ -254,6 +310,12 @@ class ELBOTrainStep:
                 while waited <= k:
                     pending[waited][0].wait()
                     waited += 1
+                if self._capturing:
+                    _cabi.check(lib.pl_adam_kl_step_dev(
+                        p.data_ptr(), self.flat[off:off + n].data_ptr(), self.adam_m[off:off + n].data_ptr(),
+                        self.adam_v[off:off + n].data_ptr(), n, kind, prior, kl_scale, self.betas[0], self.betas[1],
+                        self.eps, self._sched.data_ptr(), self.kl_acc.data_ptr(), stream), "pl_adam_kl_step_dev")
+                    continue
                 PF._timed(f"adam_kl[{n}]", lambda: _cabi.check(
                     lib.pl_adam_kl_step(p.data_ptr(), self.flat[off:off + n].data_ptr(),
                                         self.adam_m[off:off + n].data_ptr(),

@@ -413,3 +413,48 @@ def test_train_step_with_fused_chain_matches_module_by_module(plb):
         assert abs(a[3] - c[3]) / abs(a[3]) < 1e-4                   # loss trajectory
     for a, c in zip(p0, p1):     # the chained dX / bias gradients see bf16-rounded dY: bf16 tolerance after 3 Adam steps
         assert rel_err(c.cpu().numpy(), a.cpu().numpy()) < BF16_TOL
+
+
+def test_cuda_graph_step_equals_eager_steps(plb):
+    """ELBOTrainStep.enable_cuda_graph: the whole step replayed from a CUDA graph, with the per-step part of the
+    eps seed and Adam's bias-correction scalars advanced in device memory, follows the eager trajectory."""
+    from pytorch_probabilisticlayers_b200.fused import fuse_bayes_mlp
+    from pytorch_probabilisticlayers_b200.train import ELBOTrainStep
+    dims, mc, b, ns = [256, 384, 256, 16], 4, 256, 1000     # fused bf16 chain + fp32 head + fused CE + fused Adam
+    results = []
+    for graph in (False, True):
+        torch.manual_seed(5)
+        plb.manual_seed(99)
+        plb.set_precision("auto")
+        try:
+            mods = [plb.MC_ExpansionLayer(mc, 2)]
+            for li in range(3):
+                mods.append(plb.BayesLinear(dims[li], dims[li + 1]))
+                if li < 2:
+                    mods.append(torch.nn.LeakyReLU())
+            net = torch.nn.Sequential(*mods).cuda()
+            layers = [m for m in net.modules() if isinstance(m, plb.BayesLinear)]
+            for k, l in enumerate(layers):
+                l.layer_id = 2000 + k                                # same eps stream in both runs
+            net = fuse_bayes_mlp(net, b)
+            tr = ELBOTrainStep(net, plb.MC_CrossEntropyLoss(ns), ns, lr=1e-3)
+            x = torch.randn(b, dims[0], device="cuda")
+            y = torch.randint(0, dims[-1], (b,), device="cuda")
+            if graph:
+                tr.enable_cuda_graph(x, y, warmup=3)                 # 3 eager steps, then replays
+                stats = [tr.step(x, y).tolist() for _ in range(5)]
+            else:
+                stats = [tr.step(x, y).tolist() for _ in range(8)][3:]
+            torch.cuda.synchronize()
+            results.append((stats, [p.detach().clone() for p in net.parameters()]))
+        finally:
+            plb.set_precision("fp32")
+    (s0, p0), (s1, p1) = results
+    assert len({tuple(s) for s in s1}) == 5                          # the replays really draw fresh eps each step
+    # not bit-equal: torch.pow vs libm pow for Adam's bias corrections (1 ulp of fp32) and the atomics of the split
+    # dW kernels reorder sums; both are amplified a little by the bf16 chain over 5 Adam steps
+    for a, c in zip(s0, s1):
+        for u, v in zip(a, c):
+            assert abs(u - v) <= 2e-4 * max(abs(u), 1e-6), (a, c)
+    for a, c in zip(p0, p1):     # Adam turns last-bit gradient differences of near-zero gradients into O(lr) steps
+        assert rel_err(c.cpu().numpy(), a.cpu().numpy()) < BF16_TOL
