@@ -67,26 +67,29 @@ __global__ void __launch_bounds__(256) im2col_bf16_kernel(const float* __restric
 // was issue bound: 2.1 ms for C3's layer 2, profiles/r01_experiments.md).
 // grid (ho, mcx*batch), dynamic smem = (Cin*k + 1)*ws*4 + Kp*2 bytes.
 // kK: compile-time kernel size (divisions by k and k*k become multiply-shift); 0 = run-time k.  All index
-// arithmetic is per (warp, row) or per (warp, output pixel), never per element.
+// arithmetic is per (warp, row) or per (warp, output pixel), never per element.  A CTA produces `rpb` consecutive
+// output rows from one staging of (rpb-1)*stride + (k-1)*dil + 1 input rows per channel (4 output rows share
+// 8 staged rows at k = 5 instead of staging 5 rows for each).
 template <int kK>
 __global__ void __launch_bounds__(256) im2col_rows_bf16_kernel(const float* __restrict__ x,
                                                                int64_t x_mc_stride,
-                                                               __nv_bfloat16* __restrict__ A, ConvGeom g) {
+                                                               __nv_bfloat16* __restrict__ A, ConvGeom g, int rpb) {
   extern __shared__ __align__(16) uint8_t im2col_smem[];
   const int k = kK ? kK : g.k;
   const int ws = g.w + 2 * g.pad;
-  const int nrow = g.cin * k;
+  const int rin = (rpb - 1) * g.stride + (k - 1) * g.dil + 1;   // staged input rows per channel
+  const int nrow = g.cin * rin;
   uint16_t* off = reinterpret_cast<uint16_t*>(im2col_smem);                 // [Kp]
   float* rows = reinterpret_cast<float*>(im2col_smem + (((size_t)g.Kp * 2 + 15) & ~(size_t)15));   // [nrow + 1][ws]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int oh = blockIdx.x, img = blockIdx.y, mc = img / g.batch, b = img - mc * g.batch;
+  const int oh0 = blockIdx.x * rpb, img = blockIdx.y, mc = img / g.batch, b = img - mc * g.batch;
   const float* xb = x + (int64_t)mc * x_mc_stride + (int64_t)b * g.cin * g.h * g.w;
-  const int ih0 = oh * g.stride - g.pad;
+  const int ih0 = oh0 * g.stride - g.pad;
   // staged rows: a warp pass covers 32 / cw rows of cw (8, 16 or 32) columns each, so narrow planes keep the lanes busy
   const int cw = ws <= 8 ? 8 : (ws <= 16 ? 16 : 32), rpp = 32 / cw;
   const int sub = lane / cw, col0 = lane - sub * cw;
   for (int rw = warp * rpp + sub; rw <= nrow; rw += 8 * rpp) {   // row nrow = zeros
-    const int c = rw / k, kh = rw - c * k, ih = ih0 + kh * g.dil;
+    const int c = rw / rin, r = rw - c * rin, ih = ih0 + r;
     const bool row_ok = rw < nrow && ih >= 0 && ih < g.h;
     const float* src = xb + ((int64_t)c * g.h + ih) * g.w - g.pad;
     for (int col = col0; col < ws; col += cw)
@@ -97,38 +100,57 @@ __global__ void __launch_bounds__(256) im2col_rows_bf16_kernel(const float* __re
     int o = nrow * ws;                                   // the zero row
     if (kidx < g.K) {
       const int c = kidx / kk2, r = kidx - c * kk2, kh = r / k, kw = r - kh * k;
-      o = (c * k + kh) * ws + kw * g.dil;
+      o = (c * rin + kh * g.dil) * ws + kw * g.dil;
     }
     off[kidx] = (uint16_t)o;
   }
   __syncthreads();
   const int chunks = g.Kp >> 3;
-  const int64_t m0 = ((int64_t)mc * g.batch + b) * g.ho * g.wo + (int64_t)oh * g.wo;   // first pixel row
-  for (int ow = warp; ow < g.wo; ow += 8) {
-    const float* base = rows + ow * g.stride;
-    __nv_bfloat16* dst = A + (m0 + ow) * (int64_t)g.Kp;
+  const int64_t m_img = ((int64_t)mc * g.batch + b) * g.ho * g.wo;
+  const int npix = min(rpb, g.ho - oh0) * g.wo;           // output pixels of this CTA (last block may be short)
+  for (int px = warp; px < npix; px += 8) {
+    const int j = px / g.wo, ow = px - j * g.wo;
+    // rows of the zero row must stay inside it: the shift below is only applied to real offsets (< nrow * ws)
+    const int shift = j * g.stride * ws + ow * g.stride;
+    const int zero_off = nrow * ws;
+    __nv_bfloat16* dst = A + (m_img + (int64_t)(oh0 + j) * g.wo + ow) * (int64_t)g.Kp;
     for (int kc = lane; kc < chunks; kc += 32) {
       const uint4 o8 = *reinterpret_cast<const uint4*>(off + (kc << 3));
-      const float v0 = base[o8.x & 0xffffu], v1 = base[o8.x >> 16], v2 = base[o8.y & 0xffffu], v3 = base[o8.y >> 16];
-      const float v4 = base[o8.z & 0xffffu], v5 = base[o8.z >> 16], v6 = base[o8.w & 0xffffu], v7 = base[o8.w >> 16];
+      const uint32_t ov[8] = {o8.x & 0xffffu, o8.x >> 16, o8.y & 0xffffu, o8.y >> 16,
+                              o8.z & 0xffffu, o8.z >> 16, o8.w & 0xffffu, o8.w >> 16};
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = rows[ov[e] == (uint32_t)zero_off ? zero_off : (int)ov[e] + shift];
       *reinterpret_cast<uint4*>(dst + (kc << 3)) =
-          make_uint4(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3), pack_bf16x2(v4, v5), pack_bf16x2(v6, v7));
+          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     }
   }
 }
 
-static size_t im2col_rows_smem(const ConvGeom& g) {
-  return (((size_t)g.Kp * 2 + 15) & ~(size_t)15) + (size_t)(g.cin * g.k + 1) * (g.w + 2 * g.pad) * sizeof(float);
+// output rows per CTA: as many (<= 4) as keep the staging under ~96 KB
+static int im2col_rpb(const ConvGeom& g) {
+  for (int rpb = 4; rpb > 1; rpb >>= 1) {
+    const size_t rin = (size_t)(rpb - 1) * g.stride + (size_t)(g.k - 1) * g.dil + 1;
+    if ((g.cin * rin + 2) * (size_t)(g.w + 2 * g.pad) * 4 + (size_t)g.Kp * 2 <= 96 * 1024 && g.ho >= rpb) return rpb;
+  }
+  return 1;
+}
+
+static size_t im2col_rows_smem(const ConvGeom& g, int rpb) {
+  const size_t rin = (size_t)(rpb - 1) * g.stride + (size_t)(g.k - 1) * g.dil + 1;
+  return (((size_t)g.Kp * 2 + 15) & ~(size_t)15) + (g.cin * rin + 1) * (size_t)(g.w + 2 * g.pad) * sizeof(float);
 }
 
 static int launch_im2col(const pl_conv2d_args* a, const ConvGeom& g, __nv_bfloat16* A, cudaStream_t st) {
-  const size_t smem = im2col_rows_smem(g);
+  const int rpb = im2col_rpb(g);
+  const size_t smem = im2col_rows_smem(g, rpb);
+  const size_t rin = (size_t)(rpb - 1) * g.stride + (size_t)(g.k - 1) * g.dil + 1;
   // the row kernel needs the staged rows + table in shared memory, uint16 offsets, and the standard output width
   const bool rows_ok = smem <= 200 * 1024 && (int64_t)g.mcx * g.batch <= 65535 &&
-                       (size_t)(g.cin * g.k + 2) * (g.w + 2 * g.pad) < 65536 &&
+                       (g.cin * rin + 2) * (size_t)(g.w + 2 * g.pad) < 65536 &&
                        (g.wo - 1) * g.stride + (g.k - 1) * g.dil < g.w + 2 * g.pad;
   if (rows_ok) {
-    dim3 grid((unsigned)g.ho, (unsigned)(g.mcx * g.batch));
+    dim3 grid((unsigned)((g.ho + rpb - 1) / rpb), (unsigned)(g.mcx * g.batch));
 #define PL_IM2COL(KK)                                                                                      \
   do {                                                                                                    \
     static size_t attr_set = 0;                                                                           \
@@ -137,7 +159,7 @@ static int launch_im2col(const pl_conv2d_args* a, const ConvGeom& g, __nv_bfloat
                                    (int)smem));                                                           \
       attr_set = smem;                                                                                    \
     }                                                                                                     \
-    im2col_rows_bf16_kernel<KK><<<grid, 256, smem, st>>>(a->x, a->x_mc_stride, A, g);                     \
+    im2col_rows_bf16_kernel<KK><<<grid, 256, smem, st>>>(a->x, a->x_mc_stride, A, g, rpb);                \
   } while (0)
     if (g.k == 5) PL_IM2COL(5);
     else if (g.k == 3) PL_IM2COL(3);
