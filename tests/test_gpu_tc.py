@@ -173,6 +173,8 @@ def test_tc_conv_injected_eps_matches_reference_golden(plb, name):
     (3, 2, 3, 96, 16, 5, 1, 2, 1, True),     # C3 conv1-like: K = 75 (unaligned rows), MC-broadcast input
     (2, 3, 16, 136, 9, 3, 2, 1, 1, False),   # stride 2, two Cout tiles
     (2, 2, 6, 33, 11, 3, 1, 2, 2, False),    # dilation 2
+    (2, 32, 5, 32, 4, 3, 1, 1, 1, False),    # 4x4 planes: tiled col2im with several channels per CTA (cpb > Cin)
+    (1, 4, 40, 64, 16, 5, 1, 2, 1, False),   # C3-like block: k5 p2, 16x16 planes, im2col with 4 output rows per CTA
 ])
 def test_tc_conv_philox_matches_fp64_oracle(plb, mc, b, cin, cout, hw, k, s, p, d, expand):
     torch.manual_seed(cout)
