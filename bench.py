@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """Headline benchmark: MC-sample*examples / second of one ELBO train step
-(forward + likelihood + KL + backward [+ gradient all-reduce] + Adam) -- BASELINE.json's metric.
+(forward + likelihood + KL + backward [+ gradient exchange] + Adam) -- BASELINE.json's metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2] [--precision ...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c3|c1|c5] [--precision ...]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...      # the reference's CPU path (oracle/torch_port.py)
+    python bench.py --impl reference ...      # the reference's own CPU path (oracle/_ref, unmodified), host cores
 
 Workloads (synthetic data, reference initialisation):
   c4  wide Bayesian MLP 4096-4096-4096-1000, MC=64, batch 512, num_samples 100000  (default: the
       config north_star's targets are quoted on; fits one GPU; MC-sharded over N GPUs -> strong scaling)
   c2  MNIST-shaped MLP 784-1200-1200-10, MC=32, batch 256, num_samples 55000
+  c3  CIFAR-shaped Bayesian ConvNet, MC=16, batch 128 (single GPU: MC_BatchNorm2D couples the samples)
+  c1  1-D regression MLP 1-49-51-52-1, MC=10, batch 50, MC_NLL (launch-latency bound: reports us/step)
+  c5  SIVI last layer on a deterministic feature extractor, MC=128, batch 100, MC_NLL
 
 One JSON line on stdout (rank 0).  `value` = device-resident inputs, CUDA-event timed, max over
 ranks.  `e2e` = the same step through the public API with pinned HOST inputs copied in and the
-loss read back every step.  `roofline` = the dominant kernel, timed live with CUDA events.
-`cpu_baseline` = oracle/torch_port.py (op-for-op port of the reference) on the host cores, on a
-bounded MC sample of the same workload.
+loss read back every step.  `roofline` = the dominant kernel, timed live with CUDA events (`frac` against the
+sustained measured peak, `frac_burst` against the burst one).  Secondary objects (N=1, rank 0 only; each
+bounded to a few seconds): `tf32` (the same step in the primary-tolerance TF32 mode), `gpu_eager_reference`
+(the UNMODIFIED reference run eagerly on this GPU, allow_tf32 off / on: the real bar), `cpu_baseline`
+(the unmodified reference on the host cores, bounded MC sample).
 """
 import argparse
 import json
@@ -31,19 +36,31 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "c4": dict(dims=[4096, 4096, 4096, 1000], mc=64, batch=512, num_samples=100000, lr=1e-3,
+    "c4": dict(dims=[4096, 4096, 4096, 1000], mc=64, batch=512, num_samples=100000, lr=1e-3, cpu_mc=8,
                name="C4 wide Bayesian MLP 4096-4096-4096-1000, MC=64, batch 512"),
-    "c2": dict(dims=[784, 1200, 1200, 10], mc=32, batch=256, num_samples=55000, lr=1e-3,
+    "c2": dict(dims=[784, 1200, 1200, 10], mc=32, batch=256, num_samples=55000, lr=1e-3, cpu_mc=8,
                name="C2 MNIST-shaped Bayesian MLP 784-1200-1200-10, MC=32, batch 256"),
     # CIFAR-shaped Bayesian ConvNet (experiments/BNN.py:228-253); single GPU only: MC_BatchNorm2D
     # pools statistics over MC
-    "c3": dict(conv=True, in_dims=(3, 32, 32), dims=[3 * 32 * 32, 10], mc=16, batch=128,
+    "c3": dict(conv=True, in_dims=(3, 32, 32), dims=[3 * 32 * 32, 10], mc=16, batch=128, cpu_mc=2,
                num_samples=50000, lr=1e-3, flops=1.8334e12,
                name="C3 CIFAR-shaped Bayesian ConvNet 3-96-128-256-128 (k5,p2)+BN+pool, 512-200-10, "
                     "MC=16, batch 128"),
+    # regression configs: MC_NLL couples the samples -> single GPU ("replicas only"), latency bound
+    "c1": dict(regression="mlp", dims=[1, 49, 51, 52, 1], mc=10, batch=50, num_samples=1000, lr=1e-2, cpu_mc=10,
+               name="C1 1-D regression Bayesian MLP 1-49-51-52-1 (ReLU), MC=10, batch 50, MC_NLL"),
+    "c5": dict(regression="sivi", dims=[1, 50, 50, 1], mc=128, batch=100, num_samples=1000, lr=1e-2, cpu_mc=128,
+               name="C5 SIVI last layer: Linear(1,50)-Linear(50,50)-SIVILayer(50,1,5), MC=128, batch 100, MC_NLL"),
 }
 METRIC = "mc_samples_x_examples_per_sec_per_train_step"
 UNIT = "MC-sample*examples/s"
+
+
+def workload_config(wl):
+    """The `config` object: identical for this repo's arm and the reference arm (the driver compares them)."""
+    return {"workload": wl["name"], "mc_total": wl["mc"], "batch": wl["batch"], "num_samples": wl["num_samples"],
+            "l2": "per-step working set (parameters + activations >> 126 MB) exceeds L2; no explicit flush"
+                  if not wl.get("regression") else "latency-bound toy config (fits L2); us/step is the figure of merit"}
 
 
 def step_flops(dims, mc, batch):
@@ -56,13 +73,16 @@ def step_flops(dims, mc, batch):
 
 
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernels at the
-# C4 shapes, from the committed `ncu --set full` capture profiles/r01_ncu_full_final_summary.json
+# C4 shapes, from the committed `ncu --set full` captures under profiles/ (file named per entry)
 NCU_TRAFFIC_BYTES = {
-    # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r01_ncu_full_*_v3_summary.json)
-    "linear_fwd[64x512x4096x4096]": 1.293e9 + 0.510e9,      # sampled_gemm_tc<4,0,0,0>, packed bf16 parameters, fp32 output
-    "linear_bwd_dx[64x512x4096x4096]": 2.619e9 + 0.257e9,   # sampled_gemm_tc<4,1,0,0> (v1 capture)
-    "linear_bwd_dw[64x512x4096x4096]": 2.281e9 + 0.130e9,   # dw_tc<0,0>
+    "linear_fwd[64x512x4096x4096]": 1.293e9 + 0.510e9,      # profiles/r01_ncu_full_fwd_v3_summary.json
+    "linear_bwd_dx[64x512x4096x4096]": 2.619e9 + 0.257e9,   # profiles/r01_ncu_full_final_summary.json
+    "linear_bwd_dw[64x512x4096x4096]": 2.281e9 + 0.130e9,   # profiles/r01_ncu_full_dw_v3_summary.json
 }
+_traffic_override = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # refreshed captures of later rounds
+if os.path.exists(_traffic_override):
+    with open(_traffic_override) as _f:
+        NCU_TRAFFIC_BYTES.update({k: v for k, v in json.load(_f).items() if not k.startswith("_")})
 
 
 def peaks():
@@ -78,52 +98,82 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference's own path (port), all host threads
+# reference arm: the reference's own modules (oracle/_ref, unmodified) or, if they did not travel, the
+# op-for-op port (oracle/torch_port.py); on the host cores, or eagerly on a CUDA device
 # ------------------------------------------------------------------------------------------------
-def cpu_port_throughput(wl, mc_sample, steps, warmup):
+def reference_throughput(wl, mc_sample, steps, warmup, device="cpu", allow_tf32=None):
+    """-> (value, ms_per_step, kind, threads).  Times `steps` train steps of the reference after `warmup`."""
     import torch
-    from oracle import torch_port as tp
+    from oracle import make_ref
+    use_ref = make_ref.available()
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    if device == "cpu":
+        torch.set_num_threads(cores)
+    dev = torch.device(device)
+    if allow_tf32 is not None:
+        torch.backends.cuda.matmul.allow_tf32 = bool(allow_tf32)
+        torch.backends.cudnn.allow_tf32 = bool(allow_tf32)
     torch.manual_seed(1234)
-    if wl.get("conv"):
-        net = tp.build_convnet(mc_sample, wl["in_dims"])
-        x = torch.randn(wl["batch"], *wl["in_dims"])
+    ns, batch = wl["num_samples"], wl["batch"]
+    if use_ref:
+        from oracle import ref_harness as rh
+        if wl.get("regression"):
+            net = rh.build_regression_mlp(mc_sample) if wl["regression"] == "mlp" else rh.SIVILastLayerNet(mc_sample)
+            crit, step_fn = rh.nll_criterion(ns), rh.train_step_regression
+        else:
+            net = rh.build_convnet(mc_sample, wl["in_dims"]) if wl.get("conv") else rh.build_mlp(wl["dims"], mc_sample)
+            crit, step_fn = rh.criterion(ns), rh.train_step
     else:
-        net = tp.build_mlp(wl["dims"], mc_sample, torch.nn.LeakyReLU)
-        x = torch.randn(wl["batch"], wl["dims"][0])
-    crit = tp.MCCrossEntropyPort(wl["num_samples"])
+        from oracle import torch_port as tp
+        if wl.get("regression"):
+            raise RuntimeError("the regression configs need oracle/_ref (python oracle/make_ref.py)")
+        net = tp.build_convnet(mc_sample, wl["in_dims"]) if wl.get("conv") else tp.build_mlp(wl["dims"], mc_sample)
+        crit = tp.MCCrossEntropyPort(ns)
+
+        def step_fn(net, crit, opt, x, y, ns):
+            return tp.train_step(net, crit, opt, x, y, ns)
+    net = net.to(dev)
     opt = torch.optim.Adam(net.parameters(), wl["lr"])
-    y = torch.randint(0, wl["dims"][-1], (wl["batch"],))
+    if wl.get("regression"):
+        x, y = torch.randn(batch, 1, device=dev), torch.randn(batch, 1, device=dev)
+    elif wl.get("conv"):
+        x, y = torch.randn(batch, *wl["in_dims"], device=dev), torch.randint(0, wl["dims"][-1], (batch,), device=dev)
+    else:
+        x, y = torch.randn(batch, wl["dims"][0], device=dev), torch.randint(0, wl["dims"][-1], (batch,), device=dev)
+
+    def sync():
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
     for _ in range(warmup):
-        tp.train_step(net, crit, opt, x, y, wl["num_samples"])
-    times = []
+        step_fn(net, crit, opt, x, y, ns)
+    sync()
+    t0 = time.perf_counter()
     for _ in range(steps):
-        t0 = time.perf_counter()
-        tp.train_step(net, crit, opt, x, y, wl["num_samples"])
-        times.append(time.perf_counter() - t0)
-    t = sum(times) / len(times)
-    return mc_sample * wl["batch"] / t, t * 1e3, cores
+        step_fn(net, crit, opt, x, y, ns)
+    sync()
+    t = (time.perf_counter() - t0) / steps
+    return mc_sample * batch / t, t * 1e3, ("reference" if use_ref else "port"), cores
 
 
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    mc_sample = {"c4": 4, "c2": 8, "c3": 2}[args.workload]
-    steps = max(1, min(args.steps, 10))
-    warmup = max(1, min(args.warmup, 2))
-    value, ms, cores = cpu_port_throughput(wl, mc_sample, steps, warmup)
-    sample = (f"MC={mc_sample} of {wl['mc']} (throughput in MC-sample*examples/s is ~MC-independent "
-              f"on the CPU path), full batch {wl['batch']}, {steps} timed steps")
+    mc_sample = min(wl["mc"], wl["cpu_mc"])
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    value, ms, kind, cores = reference_throughput(wl, mc_sample, steps, warmup)
+    sample = (f"MC={mc_sample} of {wl['mc']} per step (throughput in MC-sample*examples/s is MC-independent on the CPU "
+              f"path: every op is O(MC)), full batch {wl['batch']}, {steps} timed steps after {warmup} warm-up, "
+              f"torch CPU fp32, {cores} threads")
+    what = ("UNMODIFIED reference modules (oracle/_ref = copy of src/ProbabilisticLayers*.py) under "
+            "oracle/ref_harness.py" if kind == "reference" else "oracle/torch_port.py (op-for-op port; oracle/_ref absent)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "mc_sample": mc_sample,
-                   "note": "reference CPU path = oracle/torch_port.py (op-for-op port; the Python "
-                           "reference cannot travel to the GPU box)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(wl),
+        "impl_config": {"mc_sample": mc_sample, "what": what},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -179,13 +229,80 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def build_net(plb, wl, mc_local, dev, precision, fuse, world=1):
+    import torch
+    dims, batch = wl["dims"], wl["batch"]
+    if wl.get("regression") == "mlp":       # experiments/RegressionBNN.py:73-81
+        mods = [plb.MC_ExpansionLayer(num_MC=mc_local, input_dim=2)]
+        for li in range(len(dims) - 1):
+            mods.append(plb.BayesLinear(dims[li], dims[li + 1]))
+            if li + 2 < len(dims):
+                mods.append(torch.nn.ReLU())
+        return torch.nn.Sequential(*mods).to(dev)
+    if wl.get("regression") == "sivi":      # experiments/SIVILastLayer.py
+        return torch.nn.Sequential(torch.nn.Linear(1, 50), torch.nn.LeakyReLU(), torch.nn.Linear(50, 50),
+                                   torch.nn.LeakyReLU(), plb.MC_ExpansionLayer(num_MC=mc_local, input_dim=2),
+                                   plb.SIVILayer(50, 1, 5)).to(dev)
+    if wl.get("conv"):
+        assert world == 1, "C3 couples MC samples through MC_BatchNorm2D: single GPU (replicas only)"
+        chans = [wl["in_dims"][0], 96, 128, 256, 128]
+        mods = [plb.MC_ExpansionLayer(num_MC=mc_local, input_dim=4)]
+        for li in range(4):
+            mods += [plb.BayesConv2d(chans[li], chans[li + 1], 5, stride=1, padding=2, num_MC=mc_local),
+                     plb.MC_BatchNorm2D(chans[li + 1]), torch.nn.LeakyReLU(), plb.MC_MaxPool2d(2, 2)]
+        mods += [plb.BayesAdaptiveInit_FlattenAndLinear(200), torch.nn.LeakyReLU(),
+                 plb.BayesLinear(200, dims[-1])]
+        net = torch.nn.Sequential(*mods).to(dev)
+        with torch.no_grad():      # the reference's dry run (experiments/BNN.py:253), on the device
+            net(torch.randn(1, *wl["in_dims"], device=dev))
+        if fuse:
+            # same modules and parameters; each batch-norm / LeakyReLU / max-pool triple runs as one pass
+            from pytorch_probabilisticlayers_b200.bnpool import fuse_bn_act_pool
+            net = fuse_bn_act_pool(net)
+        return net
+    mods = [plb.MC_ExpansionLayer(num_MC=mc_local, input_dim=2)]
+    for li in range(len(dims) - 1):
+        mods.append(plb.BayesLinear(dims[li], dims[li + 1]))
+        if li + 2 < len(dims):
+            mods.append(torch.nn.LeakyReLU())
+    net = torch.nn.Sequential(*mods).to(dev)
+    if fuse and precision in FUSABLE:
+        # same layers and parameters; the Linear-LeakyReLU-Linear runs hand bf16 activations from
+        # GEMM epilogue to the next TMA load instead of four fp32 passes per hidden layer
+        from pytorch_probabilisticlayers_b200.fused import fuse_bayes_mlp
+        net = fuse_bayes_mlp(net, batch)
+    return net
+
+
+FUSABLE = ("auto", "bf16", "bf16_fast", "auto_fast")
+DTYPES = {"fp32": "f32", "bf16": "bf16", "auto": "bf16", "tf32": "tf32", "auto_tf32": "tf32", "bf16_fast": "bf16",
+          "auto_fast": "bf16", "tf32_fast": "tf32"}
+
+
+def make_inputs(torch, wl, pin=True):
+    batch, dims = wl["batch"], wl["dims"]
+    if wl.get("regression"):
+        x, y = torch.randn(batch, 1), torch.randn(batch, 1)
+    elif wl.get("conv"):
+        x, y = torch.randn(batch, *wl["in_dims"]), torch.randint(0, dims[-1], (batch,))
+    else:
+        x, y = torch.randn(batch, dims[0]), torch.randint(0, dims[-1], (batch,))
+    return (x.pin_memory(), y.pin_memory()) if pin else (x, y)
+
+
+def make_trainer(plb, wl, net, **kw):
+    from pytorch_probabilisticlayers_b200.train import ELBOTrainStep
+    ns = wl["num_samples"]
+    crit = plb.MC_NLL(ns) if wl.get("regression") else plb.MC_CrossEntropyLoss(ns)
+    return ELBOTrainStep(net, crit, ns, lr=wl["lr"], with_accuracy=not wl.get("regression"), **kw)
+
+
 def run_b200(args, wl):
     import torch
     import torch.distributed as dist
 
     import pytorch_probabilisticlayers_b200 as plb
     from pytorch_probabilisticlayers_b200 import functional as PF
-    from pytorch_probabilisticlayers_b200.train import ELBOTrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -213,46 +330,16 @@ def run_b200(args, wl):
     plb.manual_seed(20261019)
     torch.manual_seed(1234)                      # identical replicas + identical batch on all ranks
     dims, mc_total, batch, ns = wl["dims"], wl["mc"], wl["batch"], wl["num_samples"]
+    if wl.get("regression") or wl.get("conv"):
+        assert world == 1, "this workload couples the MC samples (MC_NLL / MC_BatchNorm2D): single GPU, replicas only"
     assert mc_total % world == 0
     mc_local = mc_total // world
-    def build_net(mc_local):
-        if wl.get("conv"):
-            assert world == 1, "C3 couples MC samples through MC_BatchNorm2D: single GPU (replicas only)"
-            chans = [wl["in_dims"][0], 96, 128, 256, 128]
-            mods = [plb.MC_ExpansionLayer(num_MC=mc_local, input_dim=4)]
-            for li in range(4):
-                mods += [plb.BayesConv2d(chans[li], chans[li + 1], 5, stride=1, padding=2, num_MC=mc_local),
-                         plb.MC_BatchNorm2D(chans[li + 1]), torch.nn.LeakyReLU(), plb.MC_MaxPool2d(2, 2)]
-            mods += [plb.BayesAdaptiveInit_FlattenAndLinear(200), torch.nn.LeakyReLU(),
-                     plb.BayesLinear(200, dims[-1])]
-            net = torch.nn.Sequential(*mods).to(dev)
-            with torch.no_grad():      # the reference's dry run (experiments/BNN.py:253), on the device
-                net(torch.randn(1, *wl["in_dims"], device=dev))
-            if args.fuse:
-                # same modules and parameters; each batch-norm / LeakyReLU / max-pool triple runs as one pass
-                from pytorch_probabilisticlayers_b200.bnpool import fuse_bn_act_pool
-                net = fuse_bn_act_pool(net)
-            return net
-        mods = [plb.MC_ExpansionLayer(num_MC=mc_local, input_dim=2)]
-        for li in range(len(dims) - 1):
-            mods.append(plb.BayesLinear(dims[li], dims[li + 1]))
-            if li + 2 < len(dims):
-                mods.append(torch.nn.LeakyReLU())
-        net = torch.nn.Sequential(*mods).to(dev)
-        if args.fuse and args.precision in ("auto", "bf16"):
-            # same layers and parameters; the Linear-LeakyReLU-Linear runs hand bf16 activations from
-            # GEMM epilogue to the next TMA load instead of four fp32 passes per hidden layer
-            from pytorch_probabilisticlayers_b200.fused import fuse_bayes_mlp
-            net = fuse_bayes_mlp(net, batch)
-        return net
 
-    net = build_net(mc_local)
-    trainer = ELBOTrainStep(net, plb.MC_CrossEntropyLoss(ns), ns, lr=wl["lr"])
+    net = build_net(plb, wl, mc_local, dev, args.precision, args.fuse, world)
+    trainer = make_trainer(plb, wl, net)
     assert trainer.set_shard(mc_total) == mc_local
 
-    x_host = (torch.randn(batch, *wl["in_dims"]) if wl.get("conv")
-              else torch.randn(batch, dims[0])).pin_memory()
-    y_host = torch.randint(0, dims[-1], (batch,)).pin_memory()
+    x_host, y_host = make_inputs(torch, wl)
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
     def barrier():
@@ -298,18 +385,22 @@ def run_b200(args, wl):
         barrier()
         PF.profile_start()
         for _ in range(n):
-            step_resident()
+            trainer._eager_step(x_dev, y_dev) if trainer._graph is not None else step_resident()
         return PF.profile_stop(), n
 
+    # launch-bound configurations replay the step from a CUDA graph by default (host enqueue >= GPU time)
+    use_graph = args.cuda_graph if args.cuda_graph is not None else bool(wl.get("regression"))
     prof = None
     launches_per_step = None
-    if args.cuda_graph:
+    eager_us = None
+    if use_graph:
+        assert world == 1, "--cuda-graph is a single-GPU option"
         # a replayed graph hides the individual launches: take the roofline leg (and the launch count) first
-        assert world == 1, "--cuda-graph is a single-GPU option in this round"
         prof, prof_steps = roofline_leg()
         l1 = lib.pl_launch_count()
         step_resident()
         launches_per_step = lib.pl_launch_count() - l1      # the graph replays exactly these launches
+        eager_us = timed(step_resident, args.steps) / args.steps * 1e3
         trainer.enable_cuda_graph(x_dev, y_dev)
     torch.cuda.synchronize()
 
@@ -336,11 +427,11 @@ def run_b200(args, wl):
     # ---- N > 1 only, report-only: the same step with the per-GPU share held at the full MC (weak scaling:
     # total MC = MC x N); the headline above is the strong-scaling figure BASELINE.json's config names ----
     weak = None
-    if world > 1 and not wl.get("conv"):
+    if world > 1 and not wl.get("conv") and not args.no_weak:
         del trainer, net
         torch.cuda.empty_cache()
-        net_w = build_net(mc_total)
-        trainer_w = ELBOTrainStep(net_w, plb.MC_CrossEntropyLoss(ns), ns, lr=wl["lr"])
+        net_w = build_net(plb, wl, mc_total, dev, args.precision, args.fuse, world)
+        trainer_w = make_trainer(plb, wl, net_w)
         assert trainer_w.set_shard(mc_total * world) == mc_total
 
         def step_weak():
@@ -359,91 +450,193 @@ def run_b200(args, wl):
         return
 
     pk = peaks()
-    per_call = {k: v[1] / v[0] for k, v in prof.items()}                  # ms per call
-    per_step = {k: v[1] / prof_steps for k, v in prof.items()}            # ms per step
-    top = max(per_step, key=per_step.get)
-    kind, amount = PF._WORK.get(top, ("flops", 0.0))
-    if kind == "flops":
-        achieved = amount / (per_call[top] * 1e-3) / 1e12
-        peak = pk["tf_sustained"]
-        roofline = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get(top),
-                    "peak_source": pk["source"] + " bf16 dense sustained",
-                    "ms_per_launch": per_call[top], "algorithmic_flops_per_launch": amount,
-                    "note": "C-ABI call = fused tcgen05 kernel + its HBM-bound pre-passes"}
-    else:
-        achieved = amount / (per_call[top] * 1e-3) / 1e9
-        roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": pk["hbm"],
-                    "unit": "GB/s", "frac": achieved / pk["hbm"], "traffic": None,
-                    "peak_source": pk["source"], "ms_per_launch": per_call[top],
-                    "algorithmic_bytes_per_launch": amount}
+
+    def roofline_of(prof, prof_steps, tf32=False):
+        per_call = {k: v[1] / v[0] for k, v in prof.items()}                  # ms per call
+        per_step = {k: v[1] / prof_steps for k, v in prof.items()}            # ms per step
+        top = max(per_step, key=per_step.get)
+        kind, amount = PF._WORK.get(top, ("flops", 0.0))
+        if kind == "flops":
+            achieved = amount / (per_call[top] * 1e-3) / 1e12
+            r = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"],
+                 "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
+                 "peak_burst": pk["tf_burst"], "frac_burst": achieved / pk["tf_burst"],
+                 "traffic": None if tf32 else NCU_TRAFFIC_BYTES.get(top),
+                 "peak_source": pk["source"] + ": dense bf16 torch.matmul, sustained (4 s back to back) and burst (best of 10)"
+                                + ("; the TF32 tensor peak is half of it" if tf32 else ""),
+                 "ms_per_launch": per_call[top], "algorithmic_flops_per_launch": amount,
+                 "note": "C-ABI call = fused tcgen05 kernel + its HBM-bound pre-passes"}
+        else:
+            achieved = amount / (per_call[top] * 1e-3) / 1e9
+            r = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": pk["hbm"],
+                 "unit": "GB/s", "frac": achieved / pk["hbm"], "frac_burst": achieved / pk["hbm"], "traffic": None,
+                 "peak_source": pk["source"], "ms_per_launch": per_call[top],
+                 "algorithmic_bytes_per_launch": amount}
+        # every tensor-core call of the step against both peaks
+        calls = {}
+        for k in per_call:
+            kd, am = PF._WORK.get(k, (None, 0.0))
+            if kd == "flops" and am > 0:
+                tf = am / (per_call[k] * 1e-3) / 1e12
+                calls[k] = {"ms": round(per_call[k], 4), "tflops": round(tf, 1),
+                            "frac": round(tf / pk["tf_sustained"], 3), "frac_burst": round(tf / pk["tf_burst"], 3)}
+        r["tensor_calls"] = calls
+        return r, per_step
+
+    roofline, per_step = roofline_of(prof, prof_steps)
+
     # secondary: the KL reduction against the HBM roofline (north_star target (c)): the kernel
     # launched back to back over the two 4096x4096 layers' (mu, rho) in turn (2 x 134 MB > L2, so
-    # every launch streams from HBM), CUDA events around the batch
+    # every launch streams from HBM), CUDA events around the batch; once on the live parameters
+    # (fresh-init sigma ~1e-5: the small-sigma path) and once on copies with sigma ~ 0.5 (general path)
     kl_info = None
     big = [m for m in net.modules() if isinstance(m, plb.BayesLinear)]
     big = [m for m in big if m.weight.loc.numel() == max(b.weight.loc.numel() for b in big)]
-    if big:
+    if big and not wl.get("regression"):
         reps = 40
         out2 = torch.empty(2, device=dev)
         ws = torch.zeros(int(lib.pl_kl_workspace_bytes()), dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        ptrs = [(m.weight.loc.data_ptr(), m.weight.logscale.data_ptr(), m.weight.loc.numel()) for m in big]
-
-        def kl_call(i):          # straight through the C ABI: no Python-side autograd overhead
-            mu_p, rho_p, n_el = ptrs[i % len(ptrs)]
-            rc = lib.pl_kl_fwd(mu_p, rho_p, n_el, 1.0, None, out2.data_ptr(), ws.data_ptr(),
-                               ws.numel(), stream)
-            assert rc == 0
-        for i in range(4):
-            kl_call(i)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for i in range(reps):
-            kl_call(i)
-        b.record()
-        torch.cuda.synchronize()
-        us = a.elapsed_time(b) * 1e3 / reps
         n_ = big[0].weight.loc.numel()
-        gbs = 8.0 * n_ / (us * 1e-6) / 1e9
+
+        def kl_leg(ptrs):
+            def kl_call(i):          # straight through the C ABI: no Python-side autograd overhead
+                mu_p, rho_p, n_el = ptrs[i % len(ptrs)]
+                rc = lib.pl_kl_fwd(mu_p, rho_p, n_el, 1.0, None, out2.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), stream)
+                assert rc == 0
+            for i in range(4):
+                kl_call(i)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(reps):
+                kl_call(i)
+            b.record()
+            torch.cuda.synchronize()
+            us = a.elapsed_time(b) * 1e3 / reps
+            return us, 8.0 * n_ / (us * 1e-6) / 1e9
+        us, gbs = kl_leg([(m.weight.loc.data_ptr(), m.weight.logscale.data_ptr(), n_) for m in big])
+        wide = [(m.weight.loc.detach().clone(), torch.empty_like(m.weight.logscale).uniform_(-1.0, 0.5)) for m in big]
+        us_w, gbs_w = kl_leg([(a_.data_ptr(), b_.data_ptr(), n_) for a_, b_ in wide])
+        del wide
         kl_info = {"kernel": f"kl_fwd_kernel[{n_}]", "us_per_launch": us, "achieved_gbs": gbs,
                    "frac_of_hbm_peak": gbs / pk["hbm"], "algorithmic_bytes_per_launch": 8 * n_,
+                   "general_sigma_path": {"us_per_launch": us_w, "achieved_gbs": gbs_w, "frac_of_hbm_peak": gbs_w / pk["hbm"],
+                                          "note": "rho ~ U(-1, 0.5), sigma 0.3-1: the general (log + softplus) path"},
                    "note": f"{reps} back-to-back single-launch reductions alternating over "
-                           f"{len(big)} layers (working set {len(big) * 8 * n_ / 1e6:.0f} MB)"}
-
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        mc_sample = {"c4": 4, "c2": 8, "c3": 2}[args.workload]
-        v, ms, cores = cpu_port_throughput(wl, mc_sample, 3, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step_sample": ms,
-               "sample": f"MC={mc_sample} of {wl['mc']}, full batch {wl['batch']}, 3 timed steps "
-                         f"after 1 warm-up, torch CPU fp32, {cores} threads"}
+                           f"{len(big)} layers (working set {len(big) * 8 * n_ / 1e6:.0f} MB); first figure: "
+                           f"live parameters (fresh-init sigma ~1e-5, small-sigma path)"}
 
     flops = wl.get("flops") or step_flops(dims, mc_total, batch)
+
+    # ---- secondary legs (single GPU): other precision modes of the same step, the reference eagerly on this GPU,
+    # the reference on the host cores ----
+    def side_leg(precision, steps):
+        """ms/step + roofline of the same workload under another precision mode (own net / trainer)."""
+        try:
+            plb.set_precision(precision)
+            torch.manual_seed(1234)
+            net2 = build_net(plb, wl, mc_total, dev, precision, args.fuse)
+            tr2 = make_trainer(plb, wl, net2)
+            tr2.set_shard(mc_total)
+            for _ in range(3):
+                tr2.step(x_dev, y_dev)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                st2 = tr2.step(x_dev, y_dev)
+            b.record()
+            torch.cuda.synchronize()
+            ms2 = a.elapsed_time(b) / steps
+            PF.profile_start()
+            for _ in range(2):
+                tr2.step(x_dev, y_dev)
+            r2, _ = roofline_of(PF.profile_stop(), 2, tf32=precision.startswith("tf32") or precision == "auto_tf32")
+            out = {"precision": precision, "ms_per_step": ms2, "value": mc_total * batch / (ms2 * 1e-3), "unit": UNIT,
+                   "steps": steps, "step_tflops": flops / (ms2 * 1e-3) / 1e12, "roofline": r2,
+                   "final_stats": [float(v) for v in st2.tolist()]}
+            del tr2, net2
+            torch.cuda.empty_cache()
+            return out
+        except Exception as e:  # a secondary leg must never take the headline line down
+            return {"precision": precision, "error": f"{type(e).__name__}: {e}"[:300]}
+        finally:
+            plb.set_precision(args.precision)
+
+    side = {}
+    eager_ref = None
+    cpu = None
+    exchange = getattr(trainer, "exchange", None) if world > 1 and weak is None else None
+    if world == 1 and not args.no_side_legs:
+        n_side = max(3, min(args.steps, 10))
+        if not wl.get("regression") and not wl.get("conv"):
+            for prec in ("auto_tf32", "auto_fast"):
+                if prec != args.precision:
+                    side[prec] = side_leg(prec, n_side)
+        # the reference itself, eagerly on this GPU: the bar a PyTorch user starts from (BASELINE.md section 4)
+        del trainer
+        torch.cuda.empty_cache()
+        eager_ref = {}
+        for name, tf in (("fp32", False), ("allow_tf32", True)):
+            mc_try = mc_total
+            while mc_try >= 1:
+                try:
+                    v, ms, kind, _ = reference_throughput(wl, mc_try, max(3, min(args.steps, 10)), 3, device=str(dev),
+                                                          allow_tf32=tf)
+                    eager_ref[name] = {"value": v, "unit": UNIT, "ms_per_step": ms * mc_total / mc_try, "mc": mc_try,
+                                       "ms_per_step_at_mc": ms, "kind": kind}
+                    break
+                except torch.cuda.OutOfMemoryError:
+                    torch.cuda.empty_cache()
+                    mc_try //= 2
+                except Exception as e:
+                    eager_ref[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                    break
+            torch.cuda.empty_cache()
+        torch.backends.cuda.matmul.allow_tf32 = False
+        eager_ref["note"] = ("UNMODIFIED reference modules (oracle/_ref) under oracle/ref_harness.py, device = this GPU, "
+                             "eager PyTorch (cuBLAS bmm + materialised eps / W of shape [MC,I,O]); ms_per_step is scaled "
+                             "to the full MC when a smaller MC had to be used (memory)")
+        if not args.no_cpu_baseline:
+            mc_sample = min(wl["mc"], wl["cpu_mc"])
+            try:
+                v, ms, kind, cores = reference_throughput(wl, mc_sample, 3, 1)
+                cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "ms_per_step_sample": ms,
+                       "sample": f"MC={mc_sample} of {wl['mc']}, full batch {wl['batch']}, 3 timed steps "
+                                 f"after 1 warm-up, torch CPU fp32, {cores} threads"}
+            except Exception as e:
+                cpu = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "bf16": "bf16", "auto": "bf16", "tf32": "tf32", "auto_tf32": "tf32"}[args.precision],
+        "dtype": DTYPES[args.precision],
         "data": "synthetic",
-        "config": {"workload": wl["name"], "mc_total": mc_total, "mc_per_gpu": mc_local,
-                   "batch": batch, "num_samples": ns, "precision": args.precision,
-                   "fused_chain": bool(args.fuse and not wl.get("conv") and args.precision in ("auto", "bf16")),
-                   "cuda_graph": bool(args.cuda_graph),
-                   "parallelism": f"mc-shard x{world}" if world > 1 else "single",
-                   "l2": "per-step working set (parameters + activations >> 126 MB) exceeds L2; "
-                         "no explicit flush"},
+        "config": workload_config(wl),
+        "impl_config": {"precision": args.precision, "mc_per_gpu": mc_local,
+                        "fused_chain": bool(args.fuse and not wl.get("conv") and not wl.get("regression")
+                                            and args.precision in FUSABLE),
+                        "cuda_graph": bool(use_graph),
+                        "parallelism": f"mc-shard x{world}" if world > 1 else "single",
+                        "grad_exchange": exchange},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
+                "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size(),
                 "d2h_bytes_per_step": 16},
         "gpu_launches": int(launches),
+        "us_per_step": ms_step * 1e3,
+        "eager_us_per_step": eager_us,
         "host_enqueue_ms_per_step": round(host_ms.get("step_resident", 0.0), 3),
         "clocks": clock_info,
         "roofline": roofline,
         "kl_roofline": kl_info,
         "step_tflops": flops / (ms_step * 1e-3) / 1e12 * (1.0 / world),
         "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+        "tf32": side.get("auto_tf32"),
+        "bf16_fast": side.get("auto_fast"),
+        "gpu_eager_reference": eager_ref,
         "cpu_baseline": cpu,
         "weak_scaling": weak,
         "final_stats": {"LL": final_stats[0], "KL": final_stats[1], "ACC": final_stats[2],
@@ -461,13 +654,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c4")
-    ap.add_argument("--precision", choices=["fp32", "tf32", "bf16", "auto", "auto_tf32"], default="auto",
-                    help="auto = bf16 tcgen05 kernels wherever the layer shape tiles, fp32 kernels for tiny layers")
+    ap.add_argument("--precision", choices=sorted(DTYPES), default="auto",
+                    help="auto = bf16 tcgen05 kernels (noise-preserving split operand) wherever the layer shape tiles, "
+                         "fp32 kernels for tiny layers; *_fast = single rounded operand (opt-in)")
     ap.add_argument("--mc", type=int, default=0,
                     help="developer option: override the workload's MC (e.g. 8 = the per-GPU share at N=8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cuda-graph", action="store_true",
-                    help="replay the whole step from a CUDA graph (device-side seed / Adam schedule); single GPU")
+    ap.add_argument("--no-side-legs", action="store_true",
+                    help="skip the secondary legs (tf32 / bf16_fast / gpu_eager_reference / cpu_baseline)")
+    ap.add_argument("--no-weak", action="store_true", help="N>1: skip the report-only weak-scaling leg")
+    ap.add_argument("--cuda-graph", dest="cuda_graph", action="store_true", default=None,
+                    help="replay the whole step from a CUDA graph (default for the launch-bound c1 / c5)")
+    ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
     ap.add_argument("--no-fuse", dest="fuse", action="store_false",
                     help="run BayesLinear / LeakyReLU module by module instead of as a fused chain")
     args = ap.parse_args()

@@ -44,8 +44,16 @@ typedef enum pl_status {
 
 typedef enum pl_precision {
   PL_PREC_FP32 = 0, /* fp32 FFMA kernels, any shape (exact-parity / tiny layers)              */
-  PL_PREC_BF16 = 1, /* tcgen05 kind::f16, bf16 operands, fp32 TMEM accumulators               */
-  PL_PREC_TF32 = 2  /* tcgen05 kind::tf32 (reserved)                                           */
+  /* Tensor-core modes (tcgen05, fp32 TMEM accumulators).  BF16 / TF32 keep the Monte-Carlo noise in its OWN MMA
+   * operand: Y = X.round(mu) + X.round(sigma*eps), two MMAs per k-step into one accumulator (the mean tile by TMA,
+   * the noise tile synthesised on chip).  The reference initialises sigma_w = sqrt(2/(I+O))/O
+   * (src/ProbabilisticLayers.py:881), ~3e-4 of |mu|: a single operand round(mu + sigma*eps) is identical for all
+   * MC samples until sigma has grown ~10x.  The *_FAST modes are that single rounded operand (half the MMAs):
+   * valid once sigma >~ ulp(mu), opt-in. */
+  PL_PREC_BF16 = 1,      /* kind::f16, bf16 operands, split mean / noise operands              */
+  PL_PREC_TF32 = 2,      /* kind::tf32, fp32 inputs read as tf32, split mean / noise operands  */
+  PL_PREC_BF16_FAST = 3, /* kind::f16, one operand bf16(mu + sigma*eps)                        */
+  PL_PREC_TF32_FAST = 4  /* kind::tf32, one operand tf32(mu + sigma*eps)                       */
 } pl_precision;
 
 typedef enum pl_param_mode {
@@ -70,6 +78,10 @@ int pl_device_supported(void);
  * 4*ceil(cols/8)] raw Philox words (raw == 1) of stream `stream_id` (2*layer_id + is_bias). */
 int pl_eps_dump(uint64_t seed, uint32_t stream_id, uint32_t mc_global_offset, int32_t num_mc,
                 int32_t rows, int32_t cols, void* out, int32_t raw, void* stream);
+/* The same with key = seed + *seed_dev (device-resident per-step offset, NULL = none): how SIVILayer draws its
+ * hyper-network noise (torch.randn at src/ProbabilisticLayers.py:301-305) inside a captured CUDA graph. */
+int pl_eps_dump_dev(uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id, uint32_t mc_global_offset,
+                    int32_t num_mc, int32_t rows, int32_t cols, void* out, int32_t raw, void* stream);
 
 /* ---- KL(q||p) + entropy (replaces torch.distributions.kl_divergence(...).sum() and
  *      Normal.entropy().sum() at src/ProbabilisticLayers.py:955-956 and :1059) ---------------

@@ -17,12 +17,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PL_B200_LIB") or os.path.join(_HERE, "lib", "libpl_b200.so")
 
 PL_OK = 0
-PREC_FP32, PREC_BF16, PREC_TF32 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_TF32, PREC_BF16_FAST, PREC_TF32_FAST = 0, 1, 2, 3, 4
 PARAM_SHARED_RHO, PARAM_PER_MC_SIGMA = 0, 1
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32}
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32, "bf16_fast": PREC_BF16_FAST,
+              "tf32_fast": PREC_TF32_FAST}
+BF16_CLASS = (PREC_BF16, PREC_BF16_FAST)       # bf16 MMA operands (activation chaining, bf16 x kept as backward state)
 
 EXPORTS = (
-    "pl_version", "pl_last_error", "pl_launch_count", "pl_device_supported", "pl_eps_dump",
+    "pl_version", "pl_last_error", "pl_launch_count", "pl_device_supported", "pl_eps_dump", "pl_eps_dump_dev",
     "pl_kl_workspace_bytes", "pl_kl_fwd", "pl_kl_bwd", "pl_adam_kl_step", "pl_adam_kl_step_dev",
     "pl_mc_cross_entropy_workspace_bytes", "pl_mc_cross_entropy",
     "pl_bn_stats", "pl_bn_act_pool_workspace_bytes", "pl_bn_act_pool_fwd", "pl_bn_act_pool_bwd",
@@ -108,6 +110,9 @@ def lib():
                 l.pl_eps_dump.restype = C.c_int
                 l.pl_eps_dump.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32,
                                           C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+                l.pl_eps_dump_dev.restype = C.c_int
+                l.pl_eps_dump_dev.argtypes = [C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32,
+                                              C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
                 l.pl_kl_workspace_bytes.restype = C.c_size_t
                 l.pl_kl_fwd.restype = C.c_int
                 l.pl_kl_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p,

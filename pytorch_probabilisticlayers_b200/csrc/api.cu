@@ -28,6 +28,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 // out[mc][row][col] (normals) or out[mc][row][4*ceil(cols/8)] (raw Philox words, one call per 8
 // columns); one thread per 4 columns
 __global__ void eps_dump_kernel(Sampler s, int num_mc, int rows, int cols, void* out, int raw) {
+  s = live(s);
   const int groups = 2 * ((cols + 7) / 8);
   const int64_t total = (int64_t)num_mc * rows * groups;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -67,6 +68,12 @@ extern "C" int pl_device_supported(void) {
 extern "C" int pl_eps_dump(uint64_t seed, uint32_t stream_id, uint32_t mc_global_offset,
                            int32_t num_mc, int32_t rows, int32_t cols, void* out, int32_t raw,
                            void* stream) {
+  return pl_eps_dump_dev(seed, nullptr, stream_id, mc_global_offset, num_mc, rows, cols, out, raw, stream);
+}
+
+extern "C" int pl_eps_dump_dev(uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id, uint32_t mc_global_offset,
+                               int32_t num_mc, int32_t rows, int32_t cols, void* out, int32_t raw,
+                               void* stream) {
   using namespace pl;
   PL_CHECK_ARG(out, "pl_eps_dump: NULL out");
   PL_CHECK_ARG(num_mc >= 0 && rows >= 0 && cols >= 0, "pl_eps_dump: negative size");
@@ -77,6 +84,7 @@ extern "C" int pl_eps_dump(uint64_t seed, uint32_t stream_id, uint32_t mc_global
   s.k1 = (uint32_t)(seed >> 32);
   s.stream = stream_id;
   s.mc_offset = mc_global_offset;
+  s.seed_dev = seed_dev;
   const int threads = 256;
   int64_t blocks = ceil_div64(total, threads);
   if (blocks > 148 * 16) blocks = 148 * 16;

@@ -342,10 +342,13 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a);
 
 }  // namespace pl
 
+// tensor-core conv: bf16 operands only (split or single operand); there is no tf32 conv kernel
+static inline bool conv_is_tc(int p) { return p == PL_PREC_BF16 || p == PL_PREC_BF16_FAST; }
+
 extern "C" size_t pl_conv2d_workspace_bytes(const pl_conv2d_args* a) {
   if (!a) return 0;
   const size_t colsum = sizeof(float) * (size_t)(a->mc > 0 ? a->mc : 0) * (size_t)(a->cout > 0 ? a->cout : 0) + 256;
-  if (a->precision == PL_PREC_BF16) {
+  if (conv_is_tc(a->precision)) {
     const size_t tc = pl::conv_tc_workspace_bytes(a);
     return tc > colsum ? tc : colsum;
   }
@@ -353,14 +356,14 @@ extern "C" size_t pl_conv2d_workspace_bytes(const pl_conv2d_args* a) {
 }
 
 extern "C" size_t pl_conv2d_state_bytes(const pl_conv2d_args* a) {
-  if (!a || a->precision != PL_PREC_BF16) return 0;
+  if (!a || !conv_is_tc(a->precision)) return 0;
   return pl::conv_tc_state_bytes(a);
 }
 
 extern "C" int pl_conv2d_fwd(const pl_conv2d_args* a) {
   using namespace pl;
   PL_CHECK_ARG(a, "pl_conv2d_fwd: NULL args");
-  if (a->precision == PL_PREC_BF16) return conv_fwd_tc_launch(a);
+  if (conv_is_tc(a->precision)) return conv_fwd_tc_launch(a);
   ConvParams p;
   int rc = fill_conv(a, p, "pl_conv2d_fwd");
   if (rc != PL_OK) return rc;
@@ -381,7 +384,7 @@ extern "C" int pl_conv2d_fwd(const pl_conv2d_args* a) {
 extern "C" int pl_conv2d_bwd(const pl_conv2d_args* a) {
   using namespace pl;
   PL_CHECK_ARG(a, "pl_conv2d_bwd: NULL args");
-  if (a->precision == PL_PREC_BF16 && a->mc > 0 && a->batch > 0) {
+  if (conv_is_tc(a->precision) && a->mc > 0 && a->batch > 0) {
     // tensor-core kernels for dX / dW; the bias gradients are HBM-bound column sums (fp32 kernels)
     int rc = conv_bwd_tc_launch(a);
     if (rc != PL_OK || !a->db_mu) return rc;
@@ -397,7 +400,7 @@ extern "C" int pl_conv2d_bwd(const pl_conv2d_args* a) {
   PL_CHECK_ARG(a->dy, "pl_conv2d_bwd: NULL dy");
   PL_CHECK_ARG((a->dw_mu == nullptr) == (a->dw_rho == nullptr), "pl_conv2d_bwd: dw_mu/dw_rho must both be set or NULL");
   PL_CHECK_ARG((a->db_mu == nullptr) == (a->db_rho == nullptr), "pl_conv2d_bwd: db_mu/db_rho must both be set or NULL");
-  if (a->precision != PL_PREC_FP32 && a->precision != PL_PREC_BF16) {
+  if (a->precision != PL_PREC_FP32 && !conv_is_tc(a->precision)) {
     set_error("pl_conv2d_bwd: precision %d not implemented", a->precision);
     return PL_ERR_UNSUPPORTED;
   }

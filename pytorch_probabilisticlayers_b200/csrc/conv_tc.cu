@@ -153,12 +153,9 @@ static int launch_im2col(const pl_conv2d_args* a, const ConvGeom& g, __nv_bfloat
     dim3 grid((unsigned)((g.ho + rpb - 1) / rpb), (unsigned)(g.mcx * g.batch));
 #define PL_IM2COL(KK)                                                                                      \
   do {                                                                                                    \
-    static size_t attr_set = 0;                                                                           \
-    if (smem > 48 * 1024 && smem > attr_set) {                                                            \
+    if (smem > 48 * 1024)   /* per call: the attribute is per device, a process-wide cache would miss GPU #2 */ \
       PL_CUDA(cudaFuncSetAttribute(im2col_rows_bf16_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)smem));                                                           \
-      attr_set = smem;                                                                                    \
-    }                                                                                                     \
     im2col_rows_bf16_kernel<KK><<<grid, 256, smem, st>>>(a->x, a->x_mc_stride, A, g, rpb);                \
   } while (0)
     if (g.k == 5) PL_IM2COL(5);
@@ -174,12 +171,12 @@ static int launch_im2col(const pl_conv2d_args* a, const ConvGeom& g, __nv_bfloat
 }
 
 // dy [mc*B, Cout, HW] fp32 -> dYt [mc*B*HW, Coutp] bf16 (pixel-major rows = GEMM operand), zero padded
-// grid (ceil(HW/32), ceil(Coutp/32), mc*B), block (32, 8)
+// grid (mc*B, ceil(Coutp/32), ceil(HW/32)), block (32, 8)   (the image index rides on grid.x: no 65535 limit)
 __global__ void __launch_bounds__(256) dy_pixel_major_kernel(const float* __restrict__ dy,
                                                              __nv_bfloat16* __restrict__ dyt, int cout,
                                                              int coutp, int hw) {
   __shared__ float tile[32][33];
-  const int img = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int img = blockIdx.x, p0 = blockIdx.z * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -351,7 +348,11 @@ int conv_fwd_tc_launch(const pl_conv2d_args* a) {
   }
   ConvScratch w = conv_carve(g, a->workspace, false, false, a->fwd_state);
   const int64_t nw = (int64_t)g.cout * g.K;
-  rc = prep_params(a->w_mu, a->w_rho, w.sigma, g.cout, g.K, false, st);
+  // split operand (PL_PREC_BF16): the buffer holds mu16 [cout][Kp] then sig16 [cout][Kp] (half of pack_bytes each)
+  const bool split = a->precision == PL_PREC_BF16;
+  void* sig16 = (uint8_t*)w.sigma + split16_bytes((size_t)g.cout, (size_t)g.K);
+  rc = split ? prep_params_split(a->w_mu, a->w_rho, w.sigma, sig16, g.cout, g.K, false, st)
+             : prep_params(a->w_mu, a->w_rho, w.sigma, g.cout, g.K, false, st);
   if (rc != PL_OK) return rc;
   sample_bias_kernel<<<ew_grid((int64_t)g.mc * ((g.cout + 3) / 4), 256), 256, 0, st>>>(
       a->b_mu, a->b_rho, a->eps_b, make_sampler(a->seed, a->layer_id, true, a->mc_global_offset, a->seed_dev), g.mc,
@@ -372,6 +373,14 @@ int conv_fwd_tc_launch(const pl_conv2d_args* a) {
   p.out = a->y;
   p.out_hw = g.ho * g.wo;
   p.w_aligned = (g.K % 4) == 0;
+  if (split) {
+    p.w_sig16 = (const uint4*)sig16;
+    CUtensorMap tmb;
+    rc = make_tmap_mean(&tmb, w.sigma, (uint64_t)g.cout, (uint64_t)g.K, (uint64_t)g.Kp, true, false);
+    if (rc != PL_OK) return rc;
+    return a->eps_w ? launch_gemm<true, true, false, true>(tm, p, st, &tmb)
+                    : launch_gemm<true, false, false, true>(tm, p, st, &tmb);
+  }
   return a->eps_w ? launch_gemm<true, true>(tm, p, st) : launch_gemm<true, false>(tm, p, st);
 }
 
@@ -394,8 +403,9 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
   const int hwo = g.ho * g.wo;
   const int64_t nw = (int64_t)g.cout * g.K;
   if (a->dx || a->dw_mu) {
-    dim3 grid((unsigned)((hwo + 31) / 32), (unsigned)((g.Coutp + 31) / 32), (unsigned)(g.mc * g.batch));
-    PL_CHECK_ARG((int64_t)g.mc * g.batch <= 65535, "pl_conv2d_bwd: mc*batch too large for the transpose grid");
+    dim3 grid((unsigned)(g.mc * g.batch), (unsigned)((g.Coutp + 31) / 32), (unsigned)((hwo + 31) / 32));
+    PL_CHECK_ARG((int64_t)g.mc * g.batch < (1ll << 31) && (hwo + 31) / 32 <= 65535 && (g.Coutp + 31) / 32 <= 65535,
+                 "pl_conv2d_bwd: transpose grid too large");
     dy_pixel_major_kernel<<<grid, dim3(32, 8), 0, st>>>(a->dy, w.dyt, g.cout, g.Coutp, hwo);
     PL_LAUNCH_CHECK("dy_pixel_major_kernel");
   }
@@ -443,7 +453,10 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     PL_LAUNCH_CHECK("dw_tc");
   }
   if (a->dx) {
-    rc = prep_params(a->w_mu, a->w_rho, w.sigma, g.cout, g.K, false, st);
+    const bool split = a->precision == PL_PREC_BF16;
+    void* sig16 = (uint8_t*)w.sigma + split16_bytes((size_t)g.cout, (size_t)g.K);
+    rc = split ? prep_params_split(a->w_mu, a->w_rho, w.sigma, sig16, g.cout, g.K, false, st)
+               : prep_params(a->w_mu, a->w_rho, w.sigma, g.cout, g.K, false, st);
     if (rc != PL_OK) return rc;
     CUtensorMap tm;
     rc = make_tmap_bf16(&tm, w.dyt, (uint64_t)g.mc * g.M, (uint64_t)g.Coutp, 128, kBK);
@@ -459,7 +472,16 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     p.out_lp = w.dA;              // bf16 [mc][K][M]: K-major so that col2im reads contiguous pixels
     p.out_hw = (int)g.M;
     p.w_aligned = (g.K % 4) == 0;
-    rc = a->eps_w ? launch_gemm<false, true>(tm, p, st) : launch_gemm<false, false>(tm, p, st);
+    if (split) {
+      p.w_sig16 = (const uint4*)sig16;
+      CUtensorMap tmb;
+      rc = make_tmap_mean(&tmb, w.sigma, (uint64_t)g.cout, (uint64_t)g.K, (uint64_t)g.Kp, false, false);
+      if (rc != PL_OK) return rc;
+      rc = a->eps_w ? launch_gemm<false, true, false, true>(tm, p, st, &tmb)
+                    : launch_gemm<false, false, false, true>(tm, p, st, &tmb);
+    } else {
+      rc = a->eps_w ? launch_gemm<false, true>(tm, p, st) : launch_gemm<false, false>(tm, p, st);
+    }
     if (rc != PL_OK) return rc;
     const int64_t n = (int64_t)g.mc * g.batch * g.cin * g.h * g.w;
     const int hwo = g.ho * g.wo, hw = g.h * g.w;
@@ -468,11 +490,8 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     const size_t tile_smem = (size_t)cpb * g.k * g.k * hwo * 2;
     if (g.stride == 1 && g.dil == 1 && (hwo & 7) == 0 && (g.M & 7) == 0 && tile_smem <= 96 * 1024 &&
         g.batch <= 65535 && g.mc <= 65535) {
-      static size_t attr_set = 0;
-      if (tile_smem > 48 * 1024 && tile_smem > attr_set) {
+      if (tile_smem > 48 * 1024)   // per call: the attribute is per device
         PL_CUDA(cudaFuncSetAttribute(col2im_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-        attr_set = tile_smem;
-      }
       dim3 grid((unsigned)((g.cin + cpb - 1) / cpb), (unsigned)g.batch, (unsigned)g.mc);
       col2im_tile_kernel<<<grid, 256, tile_smem, st>>>(w.dA, a->dx, g, cpb);
     } else if (g.stride == 1 && g.dil == 1) {

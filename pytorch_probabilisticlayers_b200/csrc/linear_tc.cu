@@ -25,13 +25,18 @@
 
 namespace pl {
 
-// forward->backward state: parameters as the kernels read them (bf16: packed {mu|sigma} groups of 8,
-// tf32: sigma [I*O] f32) | x as bf16 [x_rows*I]
+// forward->backward state: parameters as the kernels read them | x as bf16 [x_rows*I]
+//   PL_PREC_BF16 (split operand):  mu16 [I][O] bf16 (TMA) | sig16 [I][O] bf16 (generators)
+//   PL_PREC_TF32 (split operand):  mu_hi [I*O] f32 tf32-rounded (TMA) | sigma [I*O] f32
+//   PL_PREC_BF16_FAST: packed {8 mu | 8 sigma} bf16 groups;  PL_PREC_TF32_FAST: sigma [I*O] f32
 struct TcState {
-  float* sigma;
+  float* sigma;      // fast: the packed / sigma buffer; split: the sigma half
+  float* mean;       // split: the rounded-mean matrix the TMA reads, else NULL
   __nv_bfloat16* x_bf16;
   size_t total;
 };
+static inline bool prec_tf32(int p) { return p == PL_PREC_TF32 || p == PL_PREC_TF32_FAST; }
+static inline bool prec_split(int p) { return p == PL_PREC_BF16 || p == PL_PREC_TF32; }
 // per-call scratch: [state, when the caller keeps none] | sampled bias [mc*O] | colsum [mc*O] |
 // dy as bf16 [mc*B*O]
 struct TcScratch {
@@ -48,7 +53,14 @@ static TcState carve_state(const pl_linear_args* a, void* base) {
   uint8_t* b = (uint8_t*)(((uintptr_t)base + 255) & ~(uintptr_t)255);
   TcState s;
   size_t off = 0;
-  s.sigma = (float*)(b + off); off += align256(std::max(I * O * 4, pack_bytes(I, O)));
+  s.mean = nullptr;
+  if (prec_split(a->precision)) {
+    const size_t half = align256(prec_tf32(a->precision) ? I * O * 4 : split16_bytes(I, O));
+    s.mean = (float*)(b + off); off += half;
+    s.sigma = (float*)(b + off); off += half;
+  } else {
+    s.sigma = (float*)(b + off); off += align256(std::max(I * O * 4, pack_bytes(I, O)));
+  }
   s.x_bf16 = (__nv_bfloat16*)(b + off); off += align256(x_rows * I * 2);
   s.total = off + 256;
   return s;
@@ -63,7 +75,7 @@ static TcScratch carve_scratch(const pl_linear_args* a, void* base, bool with_st
     w.st = carve_state(a, b);
     off += w.st.total;
   } else {
-    w.st = TcState{nullptr, nullptr, 0};
+    w.st = TcState{nullptr, nullptr, nullptr, 0};
   }
   w.bias = (float*)(b + off); off += align256(MC * O * 4);
   w.colsum = (float*)(b + off); off += align256(MC * O * 4);
@@ -84,7 +96,7 @@ size_t linear_tc_workspace_bytes(const pl_linear_args* a) {
 
 static int tc_shape_ok(const pl_linear_args* a, const char* who) {
   if (a->param_mode != PL_PARAM_SHARED_RHO) {
-    set_error("%s: PL_PREC_BF16 supports PL_PARAM_SHARED_RHO only", who);
+    set_error("%s: the tensor-core precisions support PL_PARAM_SHARED_RHO only", who);
     return PL_ERR_UNSUPPORTED;
   }
   if (a->in_features % 8 || a->out_features % 8 || a->in_features < 8 || a->out_features < 8) {
@@ -100,6 +112,22 @@ static int tc_shape_ok(const pl_linear_args* a, const char* who) {
 }
 
 int linear_bwd_simt_launch(const pl_linear_args* a);
+
+// picks the sampled_gemm_tc instantiation for (injected eps, tf32, split operand); `mean` = the rounded-mean matrix
+// [w_rows][pitch] of the split kernels
+template <bool kDx>
+static int dispatch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_t st, const void* mean,
+                         int64_t w_rows, int64_t w_cols, int64_t pitch, bool inj, bool tf32, bool split) {
+  if (split) {
+    CUtensorMap tmb;
+    int rc = make_tmap_mean(&tmb, mean, (uint64_t)w_rows, (uint64_t)w_cols, (uint64_t)pitch, kDx, tf32);
+    if (rc != PL_OK) return rc;
+    if (tf32) return inj ? launch_gemm<kDx, true, true, true>(tm, p, st, &tmb) : launch_gemm<kDx, false, true, true>(tm, p, st, &tmb);
+    return inj ? launch_gemm<kDx, true, false, true>(tm, p, st, &tmb) : launch_gemm<kDx, false, false, true>(tm, p, st, &tmb);
+  }
+  if (tf32) return inj ? launch_gemm<kDx, true, true>(tm, p, st) : launch_gemm<kDx, false, true>(tm, p, st);
+  return inj ? launch_gemm<kDx, true>(tm, p, st) : launch_gemm<kDx, false>(tm, p, st);
+}
 
 static int check_buffers(const pl_linear_args* a, const char* who) {
   if (!a->workspace || a->workspace_bytes < linear_tc_workspace_bytes(a)) {
@@ -130,8 +158,10 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   const TcState state = a->fwd_state ? carve_state(a, a->fwd_state) : w.st;
   const int64_t I = a->in_features, O = a->out_features, MC = a->mc, B = a->batch;
   const int64_t x_rows = a->x_mc_stride == 0 ? B : MC * B;
-  const bool tf32 = a->precision == PL_PREC_TF32;   // fp32 operands straight from the caller's tensors
-  rc = prep_params(a->w_mu, a->w_rho, state.sigma, I, O, tf32, st);
+  const bool tf32 = prec_tf32(a->precision);   // fp32 operands straight from the caller's tensors
+  const bool split = prec_split(a->precision);
+  rc = split ? prep_params_split(a->w_mu, a->w_rho, state.mean, state.sigma, I, O, tf32, st)
+             : prep_params(a->w_mu, a->w_rho, state.sigma, I, O, tf32, st);
   if (rc != PL_OK) return rc;
   PL_CHECK_ARG(!tf32 || !(a->x_lp || a->y_lp), "pl_linear_fwd: bf16 activation chaining needs PL_PREC_BF16");
   if (!tf32 && !a->x_lp) {
@@ -154,6 +184,7 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   p.w_in = (int)I; p.w_out = (int)O;
   p.a_mc_rows = a->x_mc_stride == 0 ? 0 : B;
   p.w_mu = a->w_mu; p.w_sigma = state.sigma; p.w_pack = (const uint4*)state.sigma; p.eps_w = a->eps_w;
+  p.w_sig16 = (const uint4*)state.sigma;
   p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset, a->seed_dev);
   p.bias = a->b_mu ? w.bias : nullptr;
   p.out = a->y;
@@ -162,15 +193,15 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   p.out_lp = (__nv_bfloat16*)a->y_lp;
   p.act = a->y_act;
   p.act_slope = a->y_act_slope;
-  if (tf32) return a->eps_w ? launch_gemm<false, true, true>(tm, p, st) : launch_gemm<false, false, true>(tm, p, st);
-  return a->eps_w ? launch_gemm<false, true>(tm, p, st) : launch_gemm<false, false>(tm, p, st);
+  return dispatch_gemm<false>(tm, p, st, state.mean, I, O, O, a->eps_w != nullptr, tf32, split);
 }
 
 int linear_bwd_tc_launch(const pl_linear_args* a) {
   PL_CHECK_ARG(a, "pl_linear_bwd: NULL args");
   if (a->mc == 0 || a->batch == 0) return linear_bwd_simt_launch(a);
   const bool have_state = a->fwd_state != nullptr;
-  const bool tf32 = a->precision == PL_PREC_TF32;
+  const bool tf32 = prec_tf32(a->precision);
+  const bool split = prec_split(a->precision);
   PL_CHECK_ARG((a->x || a->x_lp || (have_state && !tf32)) && a->w_mu && a->w_rho && (a->dy || a->dy_lp),
                "pl_linear_bwd: NULL pointer");
   PL_CHECK_ARG(!tf32 || !(a->x_lp || a->dy_lp || a->dx_lp), "pl_linear_bwd: bf16 activation chaining needs PL_PREC_BF16");
@@ -188,7 +219,8 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
   const int64_t x_rows = a->x_mc_stride == 0 ? B : MC * B;
   if (!have_state) {
     if (a->dx || a->dx_lp) {
-      rc = prep_params(a->w_mu, a->w_rho, state.sigma, I, O, tf32, st);
+      rc = split ? prep_params_split(a->w_mu, a->w_rho, state.mean, state.sigma, I, O, tf32, st)
+                 : prep_params(a->w_mu, a->w_rho, state.sigma, I, O, tf32, st);
       if (rc != PL_OK) return rc;
     }
     if (a->dw_mu && !tf32 && !a->x_lp) {
@@ -227,6 +259,7 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
     p.w_in = (int)I; p.w_out = (int)O;
     p.a_mc_rows = B;
     p.w_mu = a->w_mu; p.w_sigma = state.sigma; p.w_pack = (const uint4*)state.sigma; p.eps_w = a->eps_w;
+    p.w_sig16 = (const uint4*)state.sigma;
     p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset, a->seed_dev);
     p.bias = nullptr;
     p.out = a->dx;
@@ -237,8 +270,7 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
       p.mask_src = (const __nv_bfloat16*)a->x_lp;
       p.mask_slope = a->x_act_slope;
     }
-    if (tf32) rc = a->eps_w ? launch_gemm<true, true, true>(tm, p, st) : launch_gemm<true, false, true>(tm, p, st);
-    else rc = a->eps_w ? launch_gemm<true, true>(tm, p, st) : launch_gemm<true, false>(tm, p, st);
+    rc = dispatch_gemm<true>(tm, p, st, state.mean, I, O, O, a->eps_w != nullptr, tf32, split);
     if (rc != PL_OK) return rc;
   }
   if (a->dw_mu) {

@@ -27,6 +27,8 @@ struct TcGemmParams {
   const float* w_mu;            // [I, O]
   const float* w_sigma;         // softplus(rho), [I, O]                              (tf32 kernels)
   const uint4* w_pack;          // bf16 kernels: [I][ceil(O/8)] x {8 mu bf16 | 8 sigma bf16}, zero padded
+  const uint4* w_sig16;         // split bf16 kernels: sigma as bf16 [I][ceil(O/8)] x 8, zero padded (the mean operand
+                                // comes by TMA from a bf16 / tf32-rounded copy of mu: tmap_b of the kernel)
   const float* eps_w;           // optional injected eps [mc, I, O]
   Sampler sw;
   const float* bias;            // optional sampled bias [mc, ndim] (forward only)
@@ -89,6 +91,58 @@ static __global__ void __launch_bounds__(256) pack_mu_sigma_kernel(const float* 
   }
 }
 static inline size_t pack_bytes(size_t rows, size_t cols) { return rows * ((cols + 7) / 8) * 32; }
+
+// Split-operand (noise-preserving) kernels: the mean and the noise are separate MMA operands,
+//   Y = X . round(mu) + X . round(sigma * eps),
+// so sigma*eps is never added to mu in the operand precision.  (At the reference's initialisation sigma_w =
+// sqrt(2/(I+O))/O is ~3e-4 of |mu| (src/ProbabilisticLayers.py:881), far below half a bf16 / tf32 ulp of mu: one
+// rounded operand round(mu + sigma*eps) is the same number for every MC sample.)
+// bf16: mu16 / sig16 = bf16 [rows][pitch], pitch = cols rounded up to 8, zero padded: mu16 is read by TMA
+// (MN-major boxes forward, K-major boxes dX), sig16 by the generators (one 16-byte load per Philox group of 8).
+static __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ mu,
+                                                                const float* __restrict__ rho,
+                                                                uint4* __restrict__ mu16, uint4* __restrict__ sig16,
+                                                                int rows, int cols) {
+  const int groups = (cols + 7) >> 3;
+  const int64_t n = (int64_t)rows * groups;
+  const bool vec = (cols & 3) == 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int r = (int)(i / groups), c = (int)(i - (int64_t)r * groups) * 8;
+    const int64_t idx = (int64_t)r * cols + c;
+    float m[8], sg[8];
+    if (vec && c + 8 <= cols) {
+      const float4 m0 = __ldg(reinterpret_cast<const float4*>(mu + idx)),
+                   m1 = __ldg(reinterpret_cast<const float4*>(mu + idx) + 1),
+                   r0 = __ldg(reinterpret_cast<const float4*>(rho + idx)),
+                   r1 = __ldg(reinterpret_cast<const float4*>(rho + idx) + 1);
+      m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w; m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
+      sg[0] = softplus_f(r0.x); sg[1] = softplus_f(r0.y); sg[2] = softplus_f(r0.z); sg[3] = softplus_f(r0.w);
+      sg[4] = softplus_f(r1.x); sg[5] = softplus_f(r1.y); sg[6] = softplus_f(r1.z); sg[7] = softplus_f(r1.w);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = c + j < cols;
+        m[j] = ok ? __ldg(mu + idx + j) : 0.f;
+        sg[j] = ok ? softplus_f(__ldg(rho + idx + j)) : 0.f;
+      }
+    }
+    mu16[i] = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]),
+                         pack_bf16x2(m[6], m[7]));
+    sig16[i] = make_uint4(pack_bf16x2(sg[0], sg[1]), pack_bf16x2(sg[2], sg[3]), pack_bf16x2(sg[4], sg[5]),
+                          pack_bf16x2(sg[6], sg[7]));
+  }
+}
+// tf32: mu_hi = mu rounded to tf32 (fp32 word with the low 13 mantissa bits clear, read by TMA) and sigma, fp32 [rows][cols]
+static __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ mu,
+                                                                const float* __restrict__ rho,
+                                                                float* __restrict__ mu_hi, float* __restrict__ sigma,
+                                                                int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    mu_hi[i] = __uint_as_float(to_tf32(mu[i]));
+    sigma[i] = softplus_f(rho[i]);
+  }
+}
+static inline size_t split16_bytes(size_t rows, size_t cols) { return rows * ((cols + 7) / 8) * 16; }
 
 // fp32 -> bf16, 8 elements per thread per iteration (n % 8 == 0, 16-byte aligned)
 static __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src,
@@ -241,7 +295,7 @@ static __global__ void __launch_bounds__(128) bias_grad_tc_kernel(const float* _
 #ifndef PL_PROBE_W
 #define PL_PROBE_W 0     // tools/build_probe.sh builds instrumented copies with 1 / 2 (never the product)
 #endif
-template <bool kDx, bool kInjected, bool kTf32>
+template <bool kDx, bool kInjected, bool kTf32, bool kSplit = false>
 struct WGen {
   static constexpr int kGr = kTf32 ? 1 : 2;
   static constexpr int kBKe = kTf32 ? 32 : 64;
@@ -295,16 +349,21 @@ struct WGen {
       const int64_t idx = (int64_t)row[r] * p.w_out + col;
 #endif
       if (!kTf32) {
+        const uint4 zz = make_uint4(0, 0, 0, 0);
+        if (kSplit) {
+          // noise operand only: one aligned 16-byte load of 8 bf16 sigmas (zero beyond w_out)
+          pk[r][1] = ok ? __ldg(p.w_sig16 + (int64_t)row[r] * pack_groups + (col >> 3)) : zz;
+        } else {
         // packed parameters: always two aligned 16-byte loads; the pack is zero beyond w_out
         const uint4* src = p.w_pack + ((int64_t)row[r] * pack_groups + (col >> 3)) * 2;
 #if PL_PROBE_W == 2      // probe: no parameter loads at all
         pk[r][0] = make_uint4(0x3dcc3dcc, 0x3dcc3dcc, 0x3dcc3dcc, 0x3dcc3dcc);
         pk[r][1] = make_uint4(0x3c233c23, 0x3c233c23, 0x3c233c23, 0x3c233c23);
 #else
-        const uint4 zz = make_uint4(0, 0, 0, 0);
         pk[r][0] = ok ? __ldg(src) : zz;
         pk[r][1] = ok ? __ldg(src + 1) : zz;
 #endif
+        }
         if (kInjected) {
           float e8[8];
 #pragma unroll
@@ -317,7 +376,7 @@ struct WGen {
       if (kFull || (p.w_aligned && col + 8 <= p.w_out)) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          mu[r][h] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_mu + idx) + h) : z;
+          mu[r][h] = (ok && !kSplit) ? __ldg(reinterpret_cast<const float4*>(p.w_mu + idx) + h) : z;
           sg[r][h] = ok ? __ldg(reinterpret_cast<const float4*>(p.w_sigma + idx) + h) : z;
           if (kInjected) ep[r][h] = ok ? __ldg(reinterpret_cast<const float4*>(eps_base + idx) + h) : z;
         }
@@ -326,7 +385,7 @@ struct WGen {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const bool okj = ok && col + j < p.w_out;
-          m8[j] = okj ? __ldg(p.w_mu + idx + j) : 0.f;
+          m8[j] = (okj && !kSplit) ? __ldg(p.w_mu + idx + j) : 0.f;
           s8[j] = okj ? __ldg(p.w_sigma + idx + j) : 0.f;
           e8[j] = (kInjected && okj) ? __ldg(eps_base + idx + j) : 0.f;
         }
@@ -402,6 +461,11 @@ struct WGen {
         // W = mu + sigma * eps, two weights per HFMA2.BF16 (eps rounded to bf16, one rounding of the result)
         uint32_t a0 = dst + soff[r];
         if (kDx) a0 += (uint32_t)(((lane & 7) ^ ((soff[r] >> 7) & 7)) << 4);
+        if (kSplit)   // noise operand: sigma * eps alone (the mean operand is a separate TMA-loaded tile)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0),
+                       "r"(mul_bf16x2(pk[r][1].x, nz[r][0])), "r"(mul_bf16x2(pk[r][1].y, nz[r][1])),
+                       "r"(mul_bf16x2(pk[r][1].z, nz[r][2])), "r"(mul_bf16x2(pk[r][1].w, nz[r][3])) : "memory");
+        else
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0),
                      "r"(fma_bf16x2(pk[r][1].x, nz[r][0], pk[r][0].x)),
                      "r"(fma_bf16x2(pk[r][1].y, nz[r][1], pk[r][0].y)),
@@ -432,26 +496,35 @@ struct WGen {
 // ---------------------------------------------------------------------------------------------
 // fused sample + GEMM (forward: kDx = false, B operand MN-major; dX: kDx = true, B operand K-major)
 // ---------------------------------------------------------------------------------------------
-template <int MT>
+template <int MT, bool kSplit = false>
 struct TcCfg {
-  static constexpr int kStagesA = MT == 4 ? PL_STAGES_A4 : 4;
-  static constexpr int kStagesB = PL_STAGES_B;
+  // split: every B stage holds the generated noise tile AND the TMA-loaded mean tile (2 x 16 KB)
+  static constexpr int kStagesA = MT == 4 ? PL_STAGES_A4 : ((MT == 2 && kSplit) ? 3 : 4);
+  static constexpr int kStagesB = kSplit ? (MT == 1 ? 4 : 3) : PL_STAGES_B;
   static constexpr int kABytes = MT * kSubTileBytes;
-  static constexpr int kSmemBytes = kStagesA * kABytes + kStagesB * kSubTileBytes + 1024 /*bias + barriers*/
+  static constexpr int kBBytes = (kSplit ? 2 : 1) * kSubTileBytes;
+  static constexpr int kSmemBytes = kStagesA * kABytes + kStagesB * kBBytes + 1024 /*bias + barriers*/
                                     + 1024 /*alignment slack*/;
   static constexpr int kTmemCols = MT * kBN;  // 128, 256 or 512: powers of two
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 };
 
-template <int MT, bool kDx, bool kInjected, bool kTf32>
+// kSplit: the weight operand is two tiles per k-block, accumulated into the same TMEM columns:
+//   the mean tile  round(mu)          loaded by TMA (tmap_b) from a bf16 / tf32-rounded copy of mu, and
+//   the noise tile round(sigma * eps) synthesised by the generator warps,
+// i.e. twice the MMAs (the tensor pipe is ~40 % busy in the single-operand kernel) for a forward whose
+// Monte-Carlo noise survives however small sigma is next to mu.
+template <int MT, bool kDx, bool kInjected, bool kTf32, bool kSplit>
 __global__ void __launch_bounds__(kTcThreads, 1)
-sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p) {
-  using Cfg = TcCfg<MT>;
+sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const TcGemmParams p) {
+  using Cfg = TcCfg<MT, kSplit>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + Cfg::kStagesA * Cfg::kABytes;
-  const uint32_t sMisc = sB + Cfg::kStagesB * kSubTileBytes;
+  const uint32_t sMisc = sB + Cfg::kStagesB * Cfg::kBBytes;
   float* bias_s = reinterpret_cast<float*>(smem + (sMisc - smem_base));  // 128 floats
   const uint32_t bar0 = sMisc + 512;
   // barrier map (8 bytes each)
@@ -478,12 +551,13 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < Cfg::kStagesB; ++s) {
-      mbar_init(b_full(s), kGenWarps);   // one elected arrival per generator warp
+      mbar_init(b_full(s), kGenWarps + (kSplit ? 1 : 0));   // one elected arrival per generator warp (+ the mean tile's TMA)
       mbar_init(b_empty(s), 1);
     }
     mbar_init(acc_full, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmap_a);
+    if (kSplit) tma_prefetch_desc(&tmap_b);
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   if (warp >= 2) {  // stage the sampled bias of this column tile
@@ -500,6 +574,23 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
     if (lane == 0) {
       const int row0 = (int)(mc * p.a_mc_rows) + m0;
       for (int kb = 0; kb < num_kb; ++kb) {
+        if (kSplit) {
+          // mean tile of this k-block into the second half of B stage sb (freed by the same commit as the noise half)
+          const int sb = kb % Cfg::kStagesB, pb = (kb / Cfg::kStagesB) & 1;
+          mbar_wait(b_empty(sb), pb ^ 1);
+          mbar_expect_tx(b_full(sb), kSubTileBytes);
+          const uint32_t dst = sB + sb * Cfg::kBBytes + kSubTileBytes;
+          if (kDx) {
+            // K-major: [128 weight rows n0..] x [kBKe weight columns] = one 16 KB box
+            tma_load_2d(dst, &tmap_b, b_full(sb), kb * kBKe, n0);
+          } else {
+            // MN-major: [kBKe weight rows] x [128 weight columns n0..] as 128-byte wide boxes
+            constexpr int kBoxes = kTf32 ? 4 : 2, kCols = kTf32 ? 32 : 64;
+#pragma unroll
+            for (int g = 0; g < kBoxes; ++g)
+              tma_load_2d(dst + g * (kSubTileBytes / kBoxes), &tmap_b, b_full(sb), n0 + g * kCols, kb * kBKe);
+          }
+        }
         const int s = kb % Cfg::kStagesA, ph = (kb / Cfg::kStagesA) & 1;
         mbar_wait(a_empty(s), ph ^ 1);
         mbar_expect_tx(a_full(s), Cfg::kABytes);
@@ -521,7 +612,7 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
         mbar_wait(b_full(sb), pb);
         tc_fence_after_sync();
         const uint32_t a_addr = sA + sa * Cfg::kABytes;
-        const uint32_t b_addr = sB + sb * kSubTileBytes;
+        const uint32_t b_addr = sB + sb * Cfg::kBBytes;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           // A: K-major SW128 (8-row groups 1024 B apart); advancing K by 16 bf16 = 32 B
@@ -529,14 +620,24 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
           //    16 k = 2 groups = 2048 B); dX K-major SW128 like A
           // (tf32 MN-major: SWIZZLE_128B_BASE32B, 32-col groups 4096 B apart, 4-k groups 512 B apart,
           //  8 k = 1024 B per MMA)
-          const uint64_t b_desc =
-              kDx ? smem_desc_sw128(b_addr + ks * 32, 16, 1024)
-                  : (kTf32 ? smem_desc_sw128_base32(b_addr + ks * 1024, 4096, 512)
-                           : smem_desc_sw128(b_addr + ks * 2048, 8192, 1024));
+          auto b_desc_at = [&](uint32_t base) {
+            return kDx ? smem_desc_sw128(base + ks * 32, 16, 1024)
+                       : (kTf32 ? smem_desc_sw128_base32(base + ks * 1024, 4096, 512)
+                                : smem_desc_sw128(base + ks * 2048, 8192, 1024));
+          };
+          const uint64_t b_desc = b_desc_at(b_addr);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             const uint64_t a_desc = smem_desc_sw128(a_addr + mt * kSubTileBytes + ks * 32, 16, 1024);
             mma_ss<kTf32>(tmem_base + mt * kBN, a_desc, b_desc, idesc, (kb | ks) != 0);
+          }
+          if (kSplit) {   // the mean tile (same layout, second half of the stage) into the same accumulators
+            const uint64_t m_desc = b_desc_at(b_addr + kSubTileBytes);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t a_desc = smem_desc_sw128(a_addr + mt * kSubTileBytes + ks * 32, 16, 1024);
+              mma_ss<kTf32>(tmem_base + mt * kBN, a_desc, m_desc, idesc, 1u);
+            }
           }
         }
         mma_commit(a_empty(sa));   // frees the activation stage when these MMAs retire
@@ -550,7 +651,7 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
     // operand element (n, k): forward W[i = k0+k][o = n0+n]; dX W[i = n0+n][o = k0+k]
     const int gw = warp - 2;  // 0..15
     const Sampler sw = live(p.sw);
-    WGen<kDx, kInjected, kTf32> gen;
+    WGen<kDx, kInjected, kTf32, kSplit> gen;
     gen.init(gw, lane, n0);
     // tiles fully inside the weight matrix take the predicate-free path
     const bool n_full = p.w_aligned && (kDx ? (n0 + kBN <= p.w_in) : (n0 + kBN <= p.w_out));
@@ -580,7 +681,7 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p
       }
       mbar_wait(b_empty(s), ph ^ 1);
 #if PL_PROBE_W != 3
-      gen.store(sB + s * kSubTileBytes, lane);
+      gen.store(sB + s * Cfg::kBBytes, lane);
 #endif
       if (kb + 1 < num_kb) load_block(kb + 1);
     }
@@ -1190,13 +1291,17 @@ static inline int prep_params(const float* mu, const float* rho, float* buf, int
 // Kept (parity-tested) for when the sampler gets cheaper.
 static int g_force_1cta = -1;
 
-template <bool kDx, bool kInj, bool kTf32 = false>
-static int launch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_t st) {
+template <bool kDx, bool kInj, bool kTf32 = false, bool kSplit = false>
+static int launch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_t st, const CUtensorMap* tm_b = nullptr) {
   if (g_force_1cta < 0) {
     const char* e = getenv("PL_TC_2CTA");
     g_force_1cta = (e && e[0] == '1') ? 0 : 1;
   }
-  if (!kTf32 && !g_force_1cta && p.rows > 128 && p.ndim > 128 && p.out && !p.out_lp && !p.mask_src && !p.act) {
+  if (kSplit && !tm_b) {
+    set_error("launch_gemm: the split-operand kernel needs the mean operand's tensor map");
+    return PL_ERR_BAD_ARG;
+  }
+  if (!kTf32 && !kSplit && !g_force_1cta && p.rows > 128 && p.ndim > 128 && p.out && !p.out_lp && !p.mask_src && !p.act) {
     const int pair_rows = p.rows > 256 ? 512 : 256;
     dim3 grid(2u * (unsigned)((p.ndim + 255) / 256), (unsigned)((p.rows + pair_rows - 1) / pair_rows),
               (unsigned)p.mc);
@@ -1215,18 +1320,61 @@ static int launch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_
   const int mt_rows = p.rows > 256 ? 512 : (p.rows > 128 ? 256 : 128);
   dim3 grid((unsigned)((p.ndim + kBN - 1) / kBN), (unsigned)((p.rows + mt_rows - 1) / mt_rows),
             (unsigned)p.mc);
+  const CUtensorMap& tmb = tm_b ? *tm_b : tm;
 #define PL_LAUNCH_MT(MT)                                                                            \
   do {                                                                                              \
-    auto kern = sampled_gemm_tc<MT, kDx, kInj, kTf32>;                                              \
+    auto kern = sampled_gemm_tc<MT, kDx, kInj, kTf32, kSplit>;                                      \
     PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
-                                 TcCfg<MT>::kSmemBytes));                                           \
-    kern<<<grid, kTcThreads, TcCfg<MT>::kSmemBytes, st>>>(tm, p);                                    \
+                                 TcCfg<MT, kSplit>::kSmemBytes));                                   \
+    kern<<<grid, kTcThreads, TcCfg<MT, kSplit>::kSmemBytes, st>>>(tm, tmb, p);                       \
   } while (0)
   if (mt_rows == 512) PL_LAUNCH_MT(4);
   else if (mt_rows == 256) PL_LAUNCH_MT(2);
   else PL_LAUNCH_MT(1);
 #undef PL_LAUNCH_MT
   PL_LAUNCH_CHECK("sampled_gemm_tc");
+  return PL_OK;
+}
+
+// tensor map of the mean operand of the split kernels over mu_rounded [rows = I][pitch] (bf16, pitch = O rounded up to
+// 8; or fp32 with tf32-rounded values, pitch = O): forward reads MN-major boxes [kBKe weight rows] x [128 B of columns],
+// dX reads one K-major box [128 weight rows] x [128 B of columns]
+static int make_tmap_mean(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, bool dx,
+                          bool f32) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return PL_ERR_CUDA;
+  }
+  const uint64_t es = f32 ? 4 : 2;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {pitch * es};
+  const cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : 64), (cuuint32_t)(dx ? 128 : (f32 ? 32 : 64))};
+  const cuuint32_t estr[2] = {1, 1};
+  // MN-major fp32 (tf32) operands use the 32-byte-atom flavour of the 128-byte swizzle (see make_tmap_3d)
+  const CUtensorMapSwizzle sw = (f32 && !dx) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(mean operand) failed with CUresult %d (rows %llu cols %llu)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols);
+    return PL_ERR_CUDA;
+  }
+  return PL_OK;
+}
+
+// split-operand parameters: bf16 -> mu16 | sig16 (split16_bytes each), tf32 -> mu_hi | sigma (fp32 each)
+static inline int prep_params_split(const float* mu, const float* rho, void* mean_buf, void* sig_buf, int64_t rows,
+                                    int64_t cols, bool tf32, cudaStream_t st) {
+  if (tf32) {
+    split_tf32_kernel<<<ew_grid(rows * cols, 1024), 256, 0, st>>>(mu, rho, (float*)mean_buf, (float*)sig_buf, rows * cols);
+    PL_LAUNCH_CHECK("split_tf32_kernel");
+  } else {
+    split_bf16_kernel<<<ew_grid(rows * ((cols + 7) / 8), 512), 256, 0, st>>>(mu, rho, (uint4*)mean_buf, (uint4*)sig_buf,
+                                                                              (int)rows, (int)cols);
+    PL_LAUNCH_CHECK("split_bf16_kernel");
+  }
   return PL_OK;
 }
 

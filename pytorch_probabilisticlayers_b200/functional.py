@@ -193,7 +193,7 @@ class _BayesLinearFn(torch.autograd.Function):
             _timed(f"linear_fwd[{mc}x{batch}x{fin}x{fout}]",
                    lambda: _cabi.check(lib.pl_linear_fwd(C.byref(a)), "pl_linear_fwd"),
                    ("flops", 2.0 * mc * batch * fin * fout))
-        keep_x = state is None or spec.precision != _cabi.PREC_BF16   # bf16: the state holds x as bf16
+        keep_x = state is None or spec.precision not in _cabi.BF16_CLASS   # bf16: the state holds x as bf16
         ctx.save_for_backward(xb if keep_x else None, w_mu_c, w_rho_c, b_mu_c, b_rho_c,
                               eps_w_c, eps_b_c, state)
         ctx.meta = (spec, param_mode, x_stride, mc, batch, fin, fout, tuple(x.shape))
@@ -391,15 +391,16 @@ def kl_and_entropy(mu, rho, prior_scale=1.0, prior_scale_elem=None):
     return _KLFn.apply(mu, rho, prior_scale, prior_scale_elem)
 
 
-def eps_dump(seed, stream_id, mc_global_offset, num_mc, rows, cols, device, raw=False):
-    """The on-chip eps stream, materialised (test bridge for src/ProbabilisticLayers.py:835)."""
+def eps_dump(seed, stream_id, mc_global_offset, num_mc, rows, cols, device, raw=False, seed_dev=None):
+    """The on-chip eps stream, materialised (test bridge for src/ProbabilisticLayers.py:835).  ``seed_dev``: device
+    address of a uint64 added to the seed on the device (CUDA-graph replays)."""
     lib = _cabi.lib()
     if raw:
         out = torch.empty((num_mc, rows, 4 * ((cols + 7) // 8)), dtype=torch.int32, device=device)
     else:
         out = torch.empty((num_mc, rows, cols), dtype=torch.float32, device=device)
     with torch.cuda.device(device):
-        _cabi.check(lib.pl_eps_dump(int(seed), int(stream_id), int(mc_global_offset), num_mc, rows,
-                                    cols, _cabi.ptr(out), 1 if raw else 0,
-                                    _cabi.current_stream(out.device)), "pl_eps_dump")
+        _cabi.check(lib.pl_eps_dump_dev(int(seed), seed_dev or None, int(stream_id), int(mc_global_offset), num_mc, rows,
+                                        cols, _cabi.ptr(out), 1 if raw else 0,
+                                        _cabi.current_stream(out.device)), "pl_eps_dump")
     return out

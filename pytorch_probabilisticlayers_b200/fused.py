@@ -41,7 +41,7 @@ class _FusedMLPFn(torch.autograd.Function):
                 last = li == nl - 1
                 a = _cabi.LinearArgs()
                 a.mc, a.batch, a.in_features, a.out_features = mc, batch, fin, fout
-                a.precision, a.param_mode = _cabi.PREC_BF16, _cabi.PARAM_SHARED_RHO
+                a.precision, a.param_mode = specs[li].precision, _cabi.PARAM_SHARED_RHO
                 if li == 0:
                     a.x, a.x_mc_stride = _cabi.ptr(xb), x_stride
                 else:
@@ -92,7 +92,7 @@ class _FusedMLPFn(torch.autograd.Function):
                 fin, fout = w_mu.shape
                 a = _cabi.LinearArgs()
                 a.mc, a.batch, a.in_features, a.out_features = mc, batch, fin, fout
-                a.precision, a.param_mode = _cabi.PREC_BF16, _cabi.PARAM_SHARED_RHO
+                a.precision, a.param_mode = specs[li].precision, _cabi.PARAM_SHARED_RHO
                 a.w_mu, a.w_rho = _cabi.ptr(w_mu), _cabi.ptr(w_rho)
                 a.b_mu, a.b_rho = _cabi.ptr(b_mu), _cabi.ptr(b_rho)
                 sp = specs[li]
@@ -157,8 +157,11 @@ class FusedBayesMLP(torch.nn.Module):
 
     @staticmethod
     def supported(layers, batch) -> bool:
+        """The chain hands bf16 activations from layer to layer, so every layer must resolve to a bf16 tensor-core
+        precision ('auto', 'auto_fast', 'bf16', 'bf16_fast'): a user who configured fp32 / tf32 is never downgraded."""
         return all(l.bias is not None and l._tc_ok(0, batch) and l._injected is None
-                   and not isinstance(l.prior, LaplacePrior) for l in layers)
+                   and not isinstance(l.prior, LaplacePrior)
+                   and l._precision_code(True, True) in _cabi.BF16_CLASS for l in layers)
 
     def forward(self, x):
         assert x.dim() == 3, f"Input tensor not of shape [N_MC, BatchSize, Features] but is {x.shape=}"
@@ -169,7 +172,9 @@ class FusedBayesMLP(torch.nn.Module):
             if eps_w is not None:
                 raise RuntimeError("FusedBayesMLP runs the on-chip Philox sampler only; use the unfused "
                                    "layers for injected eps")
-            spec.precision = _cabi.PREC_BF16
+            if spec.precision not in _cabi.BF16_CLASS:
+                raise RuntimeError("FusedBayesMLP chains bf16 activations: set_precision('auto' | 'bf16' | '*_fast') "
+                                   "or run the layers unfused")
             specs.append(spec)
             l._remember(mc, None, None, spec)
             params += [l.weight.loc, l.weight.logscale, l.bias.loc, l.bias.logscale]

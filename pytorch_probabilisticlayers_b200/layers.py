@@ -32,7 +32,7 @@ from . import functional as PF
 # ------------------------------------------------------------------------------------------------
 _STATE = {
     "seed": 0x5EEDB200,          # base Philox key; combined with a per-layer call counter
-    "precision": "auto",         # 'fp32' | 'bf16' | 'auto' (bf16 tensor cores when the shape tiles)
+    "precision": "auto",         # see set_precision
     "eps_source": "philox",      # 'philox' | 'torch_cpu'
     "mc_global_offset": 0,       # first global MC index of this rank (MC sharding)
     "next_layer_id": 0,
@@ -46,9 +46,22 @@ def manual_seed(seed: int):
     _STATE["seed"] = int(seed) & 0xFFFFFFFFFFFFFFFF
 
 
+_PRECISION_NAMES = ("fp32", "tf32", "bf16", "auto", "auto_tf32", "bf16_fast", "tf32_fast", "auto_fast")
+
+
 def set_precision(precision: str):
-    if precision not in ("fp32", "tf32", "bf16", "auto", "auto_tf32"):
-        raise ValueError(f"precision must be 'fp32', 'tf32', 'bf16', 'auto' or 'auto_tf32', got {precision!r}")
+    """Arithmetic of the fused layers.
+      'fp32'       exact FFMA kernels (any shape)
+      'bf16'       tcgen05 bf16 operands, fp32 accumulate, mean and noise in SEPARATE operands
+                   (Y = X.bf16(mu) + X.bf16(sigma*eps)): the Monte-Carlo noise survives however small sigma is
+      'tf32'       the same with tf32 operands read straight from the fp32 tensors (primary-tolerance mode, rel 2e-3)
+      'bf16_fast' / 'tf32_fast'   one rounded operand round(mu + sigma*eps), half the MMAs: only faithful once
+                   sigma >~ ulp(mu) (NOT at the reference's initialisation, src/ProbabilisticLayers.py:881)
+      'auto' / 'auto_tf32' / 'auto_fast'   the bf16 / tf32 / bf16_fast kernels where the layer shape tiles, fp32 elsewhere
+    A forced tensor-core mode also falls back to fp32 for layers the tensor-core kernels cannot tile (odd widths,
+    per-MC parameters); BayesConv2d has no tf32 kernel and runs 'tf32*' requests in fp32."""
+    if precision not in _PRECISION_NAMES:
+        raise ValueError(f"precision must be one of {_PRECISION_NAMES}, got {precision!r}")
     _STATE["precision"] = precision
 
 
@@ -195,21 +208,27 @@ class _FusedBayesLayer(torch.nn.Module):
         ``inject_eps(None)`` returns to the configured source."""
         self._injected = None if eps_w is None else (eps_w, eps_b)
 
-    def _precision_code(self, shape_ok_for_tc: bool):
+    def _precision_code(self, shape_ok_for_tc: bool, tc_possible: bool = None, conv: bool = False):
+        """Resolves the configured precision for this call.  ``shape_ok_for_tc``: the tensor-core kernels pay off
+        (the 'auto*' modes); ``tc_possible``: they can run at all (forced modes fall back to fp32 otherwise)."""
         p = self.precision or _STATE["precision"]
-        if p == "auto":
-            p = "bf16" if shape_ok_for_tc else "fp32"
-        elif p == "auto_tf32":
-            p = "tf32" if shape_ok_for_tc else "fp32"
+        if tc_possible is None:
+            tc_possible = shape_ok_for_tc
+        if p.startswith("auto"):
+            p = {"auto": "bf16", "auto_tf32": "tf32", "auto_fast": "bf16_fast"}[p] if shape_ok_for_tc else "fp32"
+        elif p != "fp32" and not tc_possible:
+            p = "fp32"
+        if conv and p.startswith("tf32"):
+            p = "fp32"          # no tf32 conv kernel: keep the tolerance class (rel 2e-3) rather than drop to bf16
         return _cabi.PRECISIONS[p]
 
-    def _draw(self, mc, device, tc_ok):
+    def _draw(self, mc, device, tc_ok, tc_possible=None, conv=False):
         """Returns (eps_w, eps_b, SampleSpec) for this call."""
         self._calls += 1
         seed = (_STATE["seed"] + self._calls * _GOLDEN) & 0xFFFFFFFFFFFFFFFF
         spec = PF.SampleSpec(seed=seed, layer_id=self.layer_id,
                              mc_global_offset=_STATE["mc_global_offset"],
-                             precision=self._precision_code(tc_ok))
+                             precision=self._precision_code(tc_ok, tc_possible, conv))
         if _STATE["seed_dev"] is not None:
             if self._injected is not None or (self.eps_source or _STATE["eps_source"]) != "philox":
                 raise RuntimeError("a device-side seed offset (CUDA-graph mode) needs the on-chip Philox sampler")
@@ -316,10 +335,14 @@ class BayesLinear(_FusedBayesLayer):
         return (self.dim_input % 8 == 0 and self.dim_output % 8 == 0 and batch >= 128
                 and self.dim_input >= 128 and self.dim_output >= 128)
 
+    def _tc_possible(self):
+        # hard limits of the tcgen05 kernels: 16-byte aligned bf16 rows in both weight dimensions
+        return self.dim_input % 8 == 0 and self.dim_output % 8 == 0 and self.dim_input >= 8 and self.dim_output >= 8
+
     def forward(self, x: torch.Tensor, prior=None, stochastic=True):
         assert x.dim() == 3, f"Input tensor not of shape [N_MC, BatchSize, Features] but is {x.shape=}"
         mc = x.shape[0]
-        eps_w, eps_b, spec = self._draw(mc, x.device, self._tc_ok(mc, x.shape[1]))
+        eps_w, eps_b, spec = self._draw(mc, x.device, self._tc_ok(mc, x.shape[1]), self._tc_possible())
         out = PF.bayes_linear(x, self.weight.loc, self.weight.logscale,
                               None if self.bias is None else self.bias.loc,
                               None if self.bias is None else self.bias.logscale,
@@ -393,7 +416,7 @@ class BayesConv2d(_FusedBayesLayer):
         wo = (x.shape[4] + 2 * self.padding - self.dilation * (k - 1) - 1) // self.stride + 1
         tc_ok = (x.shape[1] * ho * wo >= 512 and self.out_channels >= 32
                  and self.in_channels * k * k >= 32)
-        eps_w, eps_b, spec = self._draw(mc, x.device, tc_ok)
+        eps_w, eps_b, spec = self._draw(mc, x.device, tc_ok, True, conv=True)
         out = PF.bayes_conv2d(x, self.weight.loc, self.weight.logscale, self.bias.loc,
                               self.bias.logscale, self.kernel_size, self.stride, self.padding,
                               self.dilation, eps_w, eps_b, spec)
@@ -463,9 +486,12 @@ class SIVILayer(torch.nn.Module):
             eps_b = torch.randn(num_MC, self.dim_output).to(dev)
         else:
             seed = (_STATE["seed"] + self._calls * _GOLDEN) & 0xFFFFFFFFFFFFFFFF
-            # hyper-net noise from the same counter stream (bias stream id + 2^16 keeps it disjoint)
+            # hyper-net noise from the same counter stream (bias stream id + 2^16 keeps it disjoint), drawn on the
+            # device: with a device-side seed offset the draw can be captured in a CUDA graph
+            sd = _STATE["seed_dev"]
             noise = PF.eps_dump(seed, 2 * self.layer_id + (1 << 16), _STATE["mc_global_offset"],
-                                num_MC, 1, self.dim_noise_input, dev).reshape(num_MC, -1)
+                                num_MC, 1, self.dim_noise_input, dev,
+                                seed_dev=sd.data_ptr() if sd is not None else None).reshape(num_MC, -1)
         sivi_out = self.sivi_net(noise)
         nw = self.dim_input * self.dim_output
         w_mu, w_logsigma = sivi_out[:, :nw], sivi_out[:, nw:2 * nw]
@@ -478,6 +504,10 @@ class SIVILayer(torch.nn.Module):
         spec = PF.SampleSpec(seed=seed, layer_id=self.layer_id,
                              mc_global_offset=_STATE["mc_global_offset"],
                              precision=_cabi.PREC_FP32)
+        if _STATE["seed_dev"] is not None:
+            if eps_w is not None:
+                raise RuntimeError("a device-side seed offset (CUDA-graph mode) needs the on-chip Philox sampler")
+            spec.seed_dev = _STATE["seed_dev"].data_ptr()
         out = PF.bayes_linear(x, self.w_mu, self.w_std, self.b_mu, self.b_std, eps_w, eps_b, spec,
                               param_mode=_cabi.PARAM_PER_MC_SIGMA)
         # KL(N(mu_mc, std_mc) || N(0,1)).mean(0).sum(), weights only (:330-333): [MC*I*O] elements,

@@ -56,9 +56,17 @@ class ELBOTrainStep:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        if mc_coupled_loss and self.world > 1:
-            # MC_NLL / MC_BatchNorm couple samples across MC (SURVEY.md 8e caveats): replicas only
-            raise ValueError("this criterion couples MC samples; run it unsharded (replicas only)")
+        if self.world > 1:
+            # MC_NLL / MC_BatchNorm couple samples across MC, LaplacePrior's EMA hooks see the local pre-reduction
+            # gradient (SURVEY.md 8e caveats): such nets only run unsharded ("replicas only")
+            from .loss import MC_NLL
+            coupled = [type(m).__name__ for m in net.modules()
+                       if isinstance(m, (layers._MCBatchNorm, layers.LaplacePrior))]
+            if mc_coupled_loss or isinstance(criterion, MC_NLL) or coupled:
+                raise ValueError("MC sharding over %d ranks needs samples that are independent given (mu, rho); this "
+                                 "configuration couples them (%s): run it unsharded (replicas only)"
+                                 % (self.world, ", ".join(["criterion"] * bool(mc_coupled_loss or isinstance(criterion, MC_NLL))
+                                                          + coupled)))
         self.params = [p for p in net.parameters() if p.requires_grad]
         dev = self.params[0].device
         n = sum(p.numel() for p in self.params)
@@ -195,8 +203,6 @@ class ELBOTrainStep:
         dev = self.flat.device
         if not (self.fused_opt and dev.type == "cuda"):
             raise RuntimeError("CUDA-graph mode needs the fused optimiser pass on a CUDA device")
-        if any(isinstance(m, SIVILayer) for m in self.net.modules()):
-            raise RuntimeError("CUDA-graph mode does not support SIVILayer (its hyper-net noise is drawn per call)")
         self._gx, self._gy = x.clone(), y.clone()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))

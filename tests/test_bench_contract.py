@@ -1,5 +1,5 @@
-"""bench.py's reference arm (the CPU port of the reference's path, no GPU needed) prints ONE JSON line with the
-keys the driver reads."""
+"""bench.py's reference arm (the reference's own CPU path -- the unmodified modules staged in oracle/_ref, else the
+op-for-op port; no GPU needed) prints ONE JSON line with the keys the driver reads and honours --steps / --warmup."""
 import json
 import os
 import subprocess
@@ -20,6 +20,10 @@ def test_reference_arm_prints_one_contract_line():
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["steps"] == 1 and d["warmup"] == 1          # the driver's arguments are honoured, not clamped
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(bench.WORKLOADS["c2"])      # same `config` object as this repo's arm
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]

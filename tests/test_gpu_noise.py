@@ -1,0 +1,168 @@
+"""The Monte-Carlo noise of the tensor-core forward at the REFERENCE'S OWN initialisation, and fp64-oracle parity of the
+tcgen05 kernels at BASELINE.json's shapes.
+
+src/ProbabilisticLayers.py:881 initialises sigma_w = sqrt(2/(I+O))/O: 3.8e-6 for 4096x4096 and 2.6e-5 for 784x1200, next
+to |mu| ~ 1e-2 (U(+-1/sqrt(O)), :880) whose bf16 ulp is 6e-5-1.2e-4 and tf32 ulp 8e-6-1.5e-5.  A single rounded operand
+round(mu + sigma*eps) is then the same number for every MC sample.  'bf16' / 'tf32' keep the noise in its own MMA operand
+(PL_PREC_BF16 / PL_PREC_TF32); these tests compare Y[mc] - mean_mc(Y) and the across-MC variance with the fp64 oracle
+evaluated on the eps the kernels drew, WITHOUT inflating sigma.  Tolerance: rel 2e-2 (north_star's bf16 bar) for both.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import closed_form as cf
+
+pytestmark = pytest.mark.gpu
+
+NOISE_TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def plb():
+    import pytorch_probabilisticlayers_b200 as p
+    assert torch.cuda.is_available()
+    p.set_precision("fp32")
+    p.set_eps_source("philox")
+    return p
+
+
+def n(t):
+    return t.detach().cpu().numpy()
+
+
+def l2_rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _noise_case(plb, precision, i, o, mc, b, broadcast):
+    torch.manual_seed(i + o)
+    plb.manual_seed(777 + i)
+    layer = plb.BayesLinear(i, o).cuda()           # reset_parameters(): the reference's init, untouched
+    layer.precision = precision
+    if broadcast:
+        x = torch.randn(b, i, device="cuda").unsqueeze(0).expand(mc, b, i)
+    else:
+        x = torch.randn(mc, b, i, device="cuda")
+    with torch.no_grad():
+        y = layer(x)
+    eps_w, eps_b = n(layer.weight.eps), n(layer.bias.eps)
+    want = cf.linear_fwd(n(x), n(layer.weight.loc), n(layer.weight.logscale), eps_w, n(layer.bias.loc),
+                         n(layer.bias.logscale), eps_b)
+    # the weight noise alone (the bias noise is O(0.02), sampled in fp32, and would mask it): subtract the sampled bias
+    sb = cf.rsample(n(layer.bias.loc), n(layer.bias.logscale), eps_b)[:, None, :]
+    got_w, want_w = n(y).astype(np.float64) - sb, want - sb
+    return got_w, want_w, layer
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("i,o,mc,b", [(4096, 4096, 4, 128), (784, 1200, 8, 256)])
+def test_mc_noise_survives_reference_init(plb, precision, i, o, mc, b):
+    """MC-broadcast input (layer 1 of the reference's nets): Y[mc] - mean_mc(Y) is the weight noise alone."""
+    got, want, _ = _noise_case(plb, precision, i, o, mc, b, broadcast=True)
+    d_got, d_want = got - got.mean(0, keepdims=True), want - want.mean(0, keepdims=True)
+    assert np.abs(d_want).max() > 0
+    assert l2_rel(d_got, d_want) < NOISE_TOL, (precision, i, o)
+    v_got, v_want = got.var(0), want.var(0)                      # across-MC variance per (batch, out) element
+    assert abs(v_got.sum() - v_want.sum()) / v_want.sum() < NOISE_TOL
+    assert l2_rel(v_got, v_want) < 2 * NOISE_TOL
+    # and the output itself within the mode's tolerance
+    assert rel_err(got, want) < (2e-2 if precision == "bf16" else 2e-3)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_mc_noise_survives_reference_init_per_mc_input(plb, precision):
+    """Hidden layer (per-MC input): the noise term X[mc].(sigma*eps[mc]) against the oracle's, isolated by running the same
+    layer on the same eps with the mean operand removed (mu = 0)."""
+    i, o, mc, b = 1024, 1024, 4, 128
+    torch.manual_seed(5)
+    plb.manual_seed(31)
+    layer = plb.BayesLinear(i, o).cuda()
+    layer.precision = precision
+    x = torch.randn(mc, b, i, device="cuda")
+    with torch.no_grad():
+        layer._calls = 0
+        y_full = layer(x)
+        mu = layer.weight.loc.clone()
+        layer.weight.loc.zero_()
+        layer._calls = 0                     # same seed -> same eps
+        y_noise = layer(x)
+        layer.weight.loc.copy_(mu)
+    eps_w = n(layer.weight.eps)
+    sig = cf.softplus(n(layer.weight.logscale))
+    want_noise = np.matmul(n(x).astype(np.float64), sig[None] * eps_w)
+    sb = cf.rsample(n(layer.bias.loc), n(layer.bias.logscale), n(layer.bias.eps))[:, None, :]
+    assert l2_rel(n(y_noise).astype(np.float64) - sb, want_noise) < NOISE_TOL
+    # with the mean present the noise is still there: (full - mean part) correlates with the oracle noise
+    want_mean = np.matmul(n(x).astype(np.float64), n(mu).astype(np.float64)[None])
+    resid = n(y_full).astype(np.float64) - sb - want_mean      # noise + rounding error of the mean part
+    corr = float((resid * want_noise).sum() / (np.linalg.norm(resid) * np.linalg.norm(want_noise)))
+    assert corr > (0.2 if precision == "bf16" else 0.9), corr   # bf16: X's own rounding (2^-9 |y|) exceeds the init noise
+
+
+def test_single_operand_modes_lose_the_noise_at_reference_init(plb):
+    """Documents WHY the split operand exists: 'bf16_fast' (one operand bf16(mu + sigma*eps)) at the reference's
+    4096x4096 initialisation produces MC samples that are (almost) all equal."""
+    got, want, _ = _noise_case(plb, "bf16_fast", 4096, 4096, 4, 128, broadcast=True)
+    d_got, d_want = got - got.mean(0, keepdims=True), want - want.mean(0, keepdims=True)
+    assert l2_rel(d_got, d_want) > 0.5
+    assert rel_err(got, want) < 2e-2          # ... while the plain output tolerance does not notice
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", 2e-2), ("tf32", 2e-3), ("bf16_fast", 2e-2), ("tf32_fast", 2e-3)])
+@pytest.mark.parametrize("mc,b,i,o", [(2, 256, 784, 1200), (2, 256, 1200, 1200), (1, 512, 4096, 4096), (2, 512, 4096, 1000)])
+def test_tc_matches_fp64_oracle_at_baseline_shapes(plb, precision, tol, mc, b, i, o):
+    """C2 / C4 layer shapes, reference init (+ a second pass with trained-size sigma), forward, dX, dmu, drho against
+    oracle/closed_form.py in fp64 on the dumped eps."""
+    if precision.endswith("_fast") and (i, o) != (4096, 4096) and (i, o) != (784, 1200):
+        pytest.skip("fast modes: one C2 and one C4 shape")
+    for trained in (False, True):
+        torch.manual_seed(mc + i)
+        plb.manual_seed(1000 + o + trained)
+        layer = plb.BayesLinear(i, o).cuda()
+        layer.precision = precision
+        if trained:
+            with torch.no_grad():
+                layer.weight.logscale.uniform_(-6, -3)       # sigma 2.5e-3 .. 5e-2
+        x = torch.randn(mc, b, i, device="cuda", requires_grad=True)
+        gy = torch.randn(mc, b, o, device="cuda")
+        out = layer(x)
+        (out * gy).sum().backward()
+        eps_w, eps_b = n(layer.weight.eps), n(layer.bias.eps)
+        want = cf.linear_fwd(n(x), n(layer.weight.loc), n(layer.weight.logscale), eps_w, n(layer.bias.loc),
+                             n(layer.bias.logscale), eps_b)
+        assert rel_err(n(out), want) < tol, ("fwd", trained)
+        bw = cf.linear_bwd(n(gy), n(x), n(layer.weight.loc), n(layer.weight.logscale), eps_w, n(layer.bias.logscale), eps_b)
+        assert rel_err(n(x.grad), bw["dx"]) < tol, ("dx", trained)
+        assert rel_err(n(layer.weight.loc.grad), bw["dw_mu"]) < tol, ("dmu", trained)
+        assert rel_err(n(layer.weight.logscale.grad), bw["dw_rho"]) < tol, ("drho", trained)
+        assert rel_err(n(layer.bias.loc.grad), bw["db_mu"]) < 1e-4
+        assert rel_err(n(layer.bias.logscale.grad), bw["db_rho"]) < 1e-4
+        del layer, x, gy, out
+        torch.cuda.empty_cache()
+
+
+def test_fused_chain_uses_split_operand_by_default(plb):
+    """fuse_bayes_mlp under 'auto' runs PL_PREC_BF16 (split); the chain's first layer keeps the MC noise at init."""
+    from pytorch_probabilisticlayers_b200 import _cabi
+    from pytorch_probabilisticlayers_b200.fused import FusedBayesMLP, fuse_bayes_mlp
+    plb.set_precision("auto")
+    try:
+        torch.manual_seed(3)
+        mc, b = 4, 128
+        net = torch.nn.Sequential(plb.MC_ExpansionLayer(mc, 2), plb.BayesLinear(512, 512), torch.nn.LeakyReLU(),
+                                  plb.BayesLinear(512, 256)).cuda()
+        fused = fuse_bayes_mlp(net, b)
+        assert any(isinstance(m, FusedBayesMLP) for m in fused)
+        x = torch.randn(b, 512, device="cuda")
+        with torch.no_grad():
+            y = fused(x)
+        l0 = [m for m in net if isinstance(m, plb.BayesLinear)][0]
+        assert l0._last[3].precision == _cabi.PREC_BF16
+        assert float(y.var(0).mean()) > 0
+        plb.set_precision("fp32")
+        assert not any(isinstance(m, FusedBayesMLP) for m in fuse_bayes_mlp(net, b)), "fp32 must not be downgraded to bf16"
+    finally:
+        plb.set_precision("fp32")

@@ -60,6 +60,16 @@ def test_eps_stream_matches_oracle(plb):
     assert abs(big.mean().item()) < 5e-3 and abs(big.std().item() - 1) < 5e-3
 
 
+def test_eps_stream_statistics(plb):
+    """Statistical gate of the sampler on 1.7e7 draws of the on-chip stream: moments, KS vs N(0,1),
+    chi-square on |z| bins to the tail, correlation within a Box-Muller pair, across the 8 normals of one Philox call,
+    across column groups, rows and MC samples (tests/sampler_stats.py)."""
+    from sampler_stats import check_normal_stream
+    from pytorch_probabilisticlayers_b200.functional import eps_dump
+    eps = eps_dump(0xC0FFEE1234, 6, 3, 8, 1024, 2048, "cuda").cpu().numpy()
+    check_normal_stream(eps, "pl_eps_dump")
+
+
 # ---------------------------------------------------------------------------------------------
 # KL / entropy
 # ---------------------------------------------------------------------------------------------

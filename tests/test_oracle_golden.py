@@ -246,3 +246,11 @@ def test_laplace_prior_kl_and_ema_restatement(name, clamp):
         corr = 1.0 - 0.99 ** (s + 1)
         ema = 0.99 * ema + 0.01 * (1.0 / g[f"s{s}_g_w_mu"].astype(np.float64) ** 2) / (corr + 1e-8)
         assert rel_err(ema, g[f"s{s}_ema"]) < 1e-4
+
+
+def test_eps_stream_statistics_oracle():
+    """Statistical gate of the 8-normals-per-call sampler contract on the CPU restatement (2.1e6 draws); the GPU test
+    runs the same checks on 1.7e7 draws of pl_eps_dump."""
+    from sampler_stats import check_normal_stream
+    from oracle import philox
+    check_normal_stream(philox.eps_normal(0xC0FFEE1234, 6, 3, 4, 512, 1024), "oracle")
