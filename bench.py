@@ -389,12 +389,14 @@ def run_b200(args, wl):
         return PF.profile_stop(), n
 
     # launch-bound configurations replay the step from a CUDA graph by default (host enqueue >= GPU time)
-    use_graph = args.cuda_graph if args.cuda_graph is not None else bool(wl.get("regression"))
+    # (and so does the peer-exchange multi-GPU step, which is one stream of this library's kernels: no NCCL inside)
+    use_graph = args.cuda_graph if args.cuda_graph is not None else bool(
+        wl.get("regression") or (world > 1 and trainer.exchange == "peer"))
     prof = None
     launches_per_step = None
     eager_us = None
     if use_graph:
-        assert world == 1, "--cuda-graph is a single-GPU option"
+        assert world == 1 or trainer.exchange == "peer", "--cuda-graph at N > 1 needs the peer exchange (no NCCL in the step)"
         # a replayed graph hides the individual launches: take the roofline leg (and the launch count) first
         prof, prof_steps = roofline_leg()
         l1 = lib.pl_launch_count()
@@ -433,6 +435,8 @@ def run_b200(args, wl):
         net_w = build_net(plb, wl, mc_total, dev, args.precision, args.fuse, world)
         trainer_w = make_trainer(plb, wl, net_w)
         assert trainer_w.set_shard(mc_total * world) == mc_total
+        if use_graph and trainer_w.exchange == "peer":
+            trainer_w.enable_cuda_graph(x_dev, y_dev)
 
         def step_weak():
             return trainer_w.step(x_dev, y_dev)

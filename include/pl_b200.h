@@ -71,6 +71,9 @@ const char* pl_last_error(void);
 uint64_t pl_launch_count(void);
 /* 1 if the tcgen05 path can run on the current device (compute capability 10.x), else 0. */
 int pl_device_supported(void);
+/* sizeof of the argument structs, for bindings to check their mirrors: 0 pl_linear_args, 1 pl_conv2d_args, 2 pl_ce_args,
+ * 3 pl_bnpool_args, 4 pl_shard_seg, 5 pl_shard_ctx. */
+size_t pl_struct_size(int32_t which);
 
 /* ---- eps stream (test bridge; replaces torch.distributions.utils._standard_normal as used at
  *      src/ProbabilisticLayers.py:835) -----------------------------------------------------
@@ -228,6 +231,13 @@ typedef struct pl_linear_args {
   const uint64_t* seed_dev; /* optional device pointer: the eps stream uses seed + *seed_dev (mod 2^64).  A captured
                                CUDA graph replays fixed launch parameters, so the per-step part of the seed lives in
                                device memory and is advanced inside the graph; NULL = seed as given. */
+  /* MC-sharded training (pl_shard_*): the weight operand arrives ready-made from the owners' optimiser pass, and the
+     rho gradient leaves un-scaled so that the owner applies sigmoid(rho) once after the cross-rank sum. */
+  const void* w_lp;    /* tensor-core precisions: the weight in operand form (PL_PREC_BF16: mu16 [in*out] bf16 followed,
+                          w_lp_half bytes later, by sig16; PL_PREC_BF16_FAST: packed {8 mu | 8 sigma} groups); replaces the
+                          per-call parameter pre-pass, w_mu / w_rho are then not read by forward / dX.  NULL = pack here. */
+  int64_t w_lp_half;
+  int32_t dw_rho_raw;  /* != 0: dw_rho = sum_mc dW * eps (no sigmoid(rho) factor; w_rho is not read by the dW kernel) */
 } pl_linear_args;
 
 size_t pl_linear_workspace_bytes(const pl_linear_args* a);
@@ -276,6 +286,67 @@ size_t pl_conv2d_workspace_bytes(const pl_conv2d_args* a);
 size_t pl_conv2d_state_bytes(const pl_conv2d_args* a);
 int pl_conv2d_fwd(const pl_conv2d_args* a);
 int pl_conv2d_bwd(const pl_conv2d_args* a);
+
+/* ---- MC-sharded train step over NVLink peer memory (replaces, for the N-GPU step, Lightning DDP's gradient
+ *      all-reduce + the replicated torch.optim.Adam.step: experiments/BNN.py:349, :399-400) --------------------------
+ * Every rank owns an ARENA of identical layout (one device allocation, exported with pl_ipc_export and mapped by the
+ * peers with pl_ipc_open): fp32 parameters | gradient staging | low-precision operand area | statistics | flags.
+ * Rank r owns elements [r*chunk, (r+1)*chunk) of every parameter tensor (chunk a multiple of 8).  All *_off fields are
+ * BYTE offsets from the arena base and are the same on every rank.
+ *   pl_shard_push    scatters the local gradients (a flat fp32 buffer laid out like the arena's parameter area) into the
+ *                    owners' staging:  peers[owner].staging[tensor][this rank][...]  (+ the 4 local statistics)
+ *   pl_shard_barrier cross-GPU barrier (device-side epoch; graph-replayable; times out after ~4 s into the status word)
+ *   pl_shard_adam    owner-side: sum of the staged partials in rank order (deterministic), sigmoid(rho) on raw drho sums,
+ *                    analytic KL gradient, Adam on the shard (m, v hold only the shard), KL value, then the updated
+ *                    parameters written into EVERY rank's arena in the form the forward consumes (gather below)
+ *   pl_shard_finish  shares the KL partials, second barrier, stats_out4 = [LL, KL, ACC, LL+KL] summed over ranks
+ * No NCCL call and no host synchronisation anywhere on this path. */
+#define PL_SHARD_MAX_RANKS 8
+#define PL_SHARD_MAX_SEGS 48
+
+typedef struct pl_shard_seg {
+  int32_t kind;      /* 0: plain Adam tensor; 1: (posterior mean, posterior rho) pair of one weight                   */
+  int32_t gather;    /* 0: fp32 values into every rank's parameter area; 1: pair -> bf16 mu16 | sig16 (split operand,
+                        PL_PREC_BF16) at lp_off / lp_off + lp_half; 2: pair -> packed {8 mu | 8 sigma} bf16 groups
+                        (PL_PREC_BF16_FAST) at lp_off.  With 1 / 2 the fp32 values stay on the owner only.            */
+  int32_t rho_raw;   /* pair: the staged rho gradient is sum_mc dW*eps; the owner multiplies by sigmoid(rho)          */
+  float prior_scale; /* pair: scale of the N(0, scale) prior                                                          */
+  int64_t numel;     /* elements of the tensor (of each tensor of a pair)                                             */
+  int64_t chunk;     /* elements per rank, multiple of 8                                                              */
+  int64_t p_off;     /* parameter (pair: mean) tensor in the arena's fp32 parameter area                              */
+  int64_t p2_off;    /* pair: rho tensor                                                                              */
+  int64_t g_off;     /* staging [world][chunk] floats of the tensor (pair: of the mean)                               */
+  int64_t g2_off;    /* pair: staging of rho                                                                          */
+  int64_t s_off;     /* ELEMENT offset into the shard's m / v state (pair: rho follows at s_off + chunk)              */
+  int64_t lp_off;    /* gather 1 / 2: low-precision operand area of this weight                                       */
+  int64_t lp_half;   /* gather 1: byte distance from mu16 to sig16                                                    */
+} pl_shard_seg;
+
+typedef struct pl_shard_ctx {
+  int32_t rank, world, num_segs, _pad;
+  void* peers[PL_SHARD_MAX_RANKS];   /* arena base of every rank as mapped in THIS process (peers[rank] = own arena)   */
+  const pl_shard_seg* segs;          /* DEVICE pointer: num_segs entries                                               */
+  int64_t stats_off;                 /* float [world][4]: per-rank LL, -, ACC, -                                       */
+  int64_t kl_off;                    /* double [world]: per-rank KL partial                                            */
+  int64_t flags_off;                 /* uint32 [8 + world]: epoch, status, -, ..., then one arrival flag per rank      */
+  int64_t push_units, adam_units;    /* totals of the two prefix arrays                                                */
+  int64_t push_prefix[2 * PL_SHARD_MAX_SEGS + 1]; /* 8-element units of every tensor (2 slots per segment)            */
+  int64_t adam_prefix[PL_SHARD_MAX_SEGS + 1];     /* 8-element units of THIS rank's chunk of every segment            */
+} pl_shard_ctx;
+
+/* CUDA IPC: handle (64 bytes) + byte offset of `ptr` inside its device allocation; pl_ipc_open maps a peer's allocation
+ * into this process (peer access enabled lazily) and returns the pointer corresponding to `ptr`. */
+int pl_ipc_export(const void* ptr, void* handle64, int64_t* offset_out);
+int pl_ipc_open(const void* handle64, int64_t offset, void** ptr_out);
+int pl_ipc_close(void* ptr, int64_t offset);
+
+int pl_shard_push(const pl_shard_ctx* c, const float* grads, const float* stats4, void* stream);
+int pl_shard_barrier(const pl_shard_ctx* c, void* stream);
+/* sched_dev (optional, device): [lr/(1-beta1^t), 1/sqrt(1-beta2^t)] for CUDA-graph replays, else `step` (1-based). */
+int pl_shard_adam(const pl_shard_ctx* c, float* m, float* v, float kl_scale, float lr, float beta1, float beta2, float eps,
+                  int32_t step, const float* sched_dev, double* kl_value, void* stream);
+int pl_shard_finish(const pl_shard_ctx* c, const double* kl_acc, double kl_const, double inv_num_samples,
+                    float* stats_out4, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,12 +24,15 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32, "bf16_fas
 BF16_CLASS = (PREC_BF16, PREC_BF16_FAST)       # bf16 MMA operands (activation chaining, bf16 x kept as backward state)
 
 EXPORTS = (
-    "pl_version", "pl_last_error", "pl_launch_count", "pl_device_supported", "pl_eps_dump", "pl_eps_dump_dev",
+    "pl_version", "pl_last_error", "pl_launch_count", "pl_device_supported", "pl_struct_size", "pl_eps_dump",
+    "pl_eps_dump_dev",
     "pl_kl_workspace_bytes", "pl_kl_fwd", "pl_kl_bwd", "pl_adam_kl_step", "pl_adam_kl_step_dev",
     "pl_mc_cross_entropy_workspace_bytes", "pl_mc_cross_entropy",
     "pl_bn_stats", "pl_bn_act_pool_workspace_bytes", "pl_bn_act_pool_fwd", "pl_bn_act_pool_bwd",
     "pl_linear_workspace_bytes", "pl_linear_state_bytes", "pl_linear_fwd", "pl_linear_bwd",
     "pl_conv2d_workspace_bytes", "pl_conv2d_state_bytes", "pl_conv2d_fwd", "pl_conv2d_bwd",
+    "pl_ipc_export", "pl_ipc_open", "pl_ipc_close",
+    "pl_shard_push", "pl_shard_barrier", "pl_shard_adam", "pl_shard_finish",
 )
 
 
@@ -48,6 +51,7 @@ class LinearArgs(C.Structure):
         ("x_lp", C.c_void_p), ("y_lp", C.c_void_p), ("y_act", C.c_int32), ("y_act_slope", C.c_float),
         ("dy_lp", C.c_void_p), ("dx_lp", C.c_void_p), ("x_act_slope", C.c_float),
         ("seed_dev", C.c_void_p),
+        ("w_lp", C.c_void_p), ("w_lp_half", C.c_int64), ("dw_rho_raw", C.c_int32),
     ]
 
 
@@ -107,6 +111,8 @@ def lib():
                 l.pl_last_error.restype = C.c_char_p
                 l.pl_device_supported.restype = C.c_int
                 l.pl_launch_count.restype = C.c_uint64
+                l.pl_struct_size.restype = C.c_size_t
+                l.pl_struct_size.argtypes = [C.c_int32]
                 l.pl_eps_dump.restype = C.c_int
                 l.pl_eps_dump.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32,
                                           C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
@@ -153,6 +159,17 @@ def lib():
                 for name in ("pl_conv2d_fwd", "pl_conv2d_bwd"):
                     getattr(l, name).restype = C.c_int
                     getattr(l, name).argtypes = [C.POINTER(Conv2dArgs)]
+                for name in ("pl_ipc_export", "pl_ipc_open", "pl_ipc_close", "pl_shard_push", "pl_shard_barrier",
+                             "pl_shard_adam", "pl_shard_finish"):
+                    getattr(l, name).restype = C.c_int
+                l.pl_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+                l.pl_ipc_open.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+                l.pl_ipc_close.argtypes = [C.c_void_p, C.c_int64]
+                l.pl_shard_push.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                l.pl_shard_barrier.argtypes = [C.c_void_p, C.c_void_p]
+                l.pl_shard_adam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
+                                            C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+                l.pl_shard_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
                 _lib = l
     return _lib
 

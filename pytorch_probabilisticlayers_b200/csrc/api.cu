@@ -58,6 +58,18 @@ extern "C" const char* pl_last_error(void) { return pl::g_err; }
 
 extern "C" uint64_t pl_launch_count(void) { return pl::g_launches.load(std::memory_order_relaxed); }
 
+extern "C" size_t pl_struct_size(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(pl_linear_args);
+    case 1: return sizeof(pl_conv2d_args);
+    case 2: return sizeof(pl_ce_args);
+    case 3: return sizeof(pl_bnpool_args);
+    case 4: return sizeof(pl_shard_seg);
+    case 5: return sizeof(pl_shard_ctx);
+    default: return 0;
+  }
+}
+
 extern "C" int pl_device_supported(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;

@@ -1,0 +1,405 @@
+// MC-sharded train step without NCCL on the data path: gradient reduce-scatter, sharded Adam + KL, and the all-gather
+// of the updated parameters as plain loads / stores over NVLink peer mappings (CUDA IPC), fused into the kernels
+// that produce and consume the data.
+//
+// Every rank owns one ARENA with the same layout (symmetric): [fp32 parameters | gradient staging G | low-precision
+// operand area | statistics staging | flags].  Rank r owns elements [r*chunk, (r+1)*chunk) of every parameter tensor.
+//   push     each rank scatters its local gradient of tensor t, owner o's part, into  peers[o].G[t][rank][...]
+//            (reduce-scatter by peer stores: the owner later sums the N staged partials in a FIXED order, so the
+//            result is deterministic and the same for every N-way launch)
+//   barrier  flags in peer memory, st.release.sys / ld.acquire.sys, epoch counter on the device (graph-replayable)
+//   adam     the owner sums the staged partials, applies sigmoid(rho) to raw drho sums, adds the analytic KL gradient,
+//            does the Adam update on ITS shard only (m, v exist only for the shard), accumulates its part of the KL
+//            value, and writes the updated parameters in the form the forward consumes -- the bf16 {mu | sigma}
+//            operand of the tcgen05 kernels (4 B/weight) or fp32 for small tensors -- straight into EVERY rank's arena
+//            (all-gather by peer stores)
+//   finish   shares the KL partials, second barrier, sums the statistics
+// Replaces ncclAllReduce(301 MB fp32) + a replicated optimiser pass over all 75 M parameters (r01: ~1.5 ms of a 3.2 ms
+// step at N = 8).  Reference being matched: Lightning DDP's bucketed all-reduce + Adam, experiments/BNN.py:349,399-400.
+#include <cuda.h>
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace pl {
+
+using tc::pack_bf16x2;
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// One cross-GPU barrier, executed by the first `world` threads of ONE block.  epoch = ++(*epoch_dev) (thread 0).
+// Never hangs: after ~4 s of spinning it raises status[0] and proceeds (the caller checks the status word).
+__device__ void grid_barrier_block(const pl_shard_ctx& c, uint32_t* s_epoch) {
+  uint8_t* base = (uint8_t*)c.peers[c.rank];
+  uint32_t* epoch_dev = (uint32_t*)(base + c.flags_off);          // [0] epoch, [1] status, [8 + q] flag of rank q
+  if (threadIdx.x == 0) *s_epoch = ++(*epoch_dev);
+  __syncthreads();
+  const uint32_t e = *s_epoch;
+  if ((int)threadIdx.x < c.world) {
+    __threadfence_system();       // everything this GPU wrote before (this and earlier kernels) is ordered before the flag
+    uint32_t* remote = (uint32_t*)((uint8_t*)c.peers[threadIdx.x] + c.flags_off) + 8 + c.rank;
+    st_release_sys(remote, e);
+    const uint32_t* mine = epoch_dev + 8 + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
+      if (clock64() - t0 > (1ll << 33)) {
+        epoch_dev[1] = 1u;        // timeout: a peer never arrived
+        break;
+      }
+      __nanosleep(64);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
+__global__ void shard_barrier_kernel(const pl_shard_ctx c) {
+  __shared__ uint32_t s_epoch;
+  grid_barrier_block(c, &s_epoch);
+}
+
+// ---- push: local gradients -> owners' staging --------------------------------------------------------------------
+// unit = 8 consecutive elements of one tensor; push_prefix[s] = first unit of tensor-slot s (2 slots per pair segment)
+__global__ void __launch_bounds__(256) shard_push_kernel(const pl_shard_ctx c, const float* __restrict__ grads,
+                                                         const float* __restrict__ stats4) {
+  const pl_shard_seg* segs = c.segs;
+  const int64_t total = c.push_units;
+  int slot = 0;
+  for (int64_t u = (int64_t)blockIdx.x * 256 + threadIdx.x; u < total; u += (int64_t)gridDim.x * 256) {
+    while (u >= c.push_prefix[slot + 1]) ++slot;
+    const pl_shard_seg& sg = segs[slot >> 1];
+    const bool second = slot & 1;
+    const int64_t f0 = (u - c.push_prefix[slot]) * 8;
+    const int64_t numel = sg.numel, chunk = sg.chunk;
+    const int owner = (int)(f0 / chunk);
+    const int64_t j = f0 - (int64_t)owner * chunk;
+    const float* src = grads + (second ? sg.p2_off : sg.p_off) / 4 + f0;
+    float* dst = (float*)((uint8_t*)c.peers[owner] + (second ? sg.g2_off : sg.g_off)) + (int64_t)c.rank * chunk + j;
+    if (f0 + 8 <= numel) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      reinterpret_cast<float4*>(dst)[0] = a;
+      reinterpret_cast<float4*>(dst)[1] = b;
+    } else {
+      for (int t = 0; t < 8 && f0 + t < numel; ++t) dst[t] = __ldg(src + t);
+    }
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < c.world && stats4) {
+    float* dst = (float*)((uint8_t*)c.peers[threadIdx.x] + c.stats_off) + 4 * c.rank;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) dst[t] = stats4[t];
+  }
+}
+
+// ---- sharded Adam + KL + all-gather -------------------------------------------------------------------------------
+__device__ __forceinline__ void sigma_parts2(float rho, float& sigma, float& logsigma, float& sig) {
+  const float e = __expf(fminf(rho, 20.f));
+  const float poly = e * fmaf(e, fmaf(e, fmaf(e, fmaf(e, 0.2f, -0.25f), 0.33333334f), -0.5f), 1.0f);
+  sigma = e < 0.0625f ? poly : __logf(1.0f + e);
+  sigma = rho > 20.f ? rho : sigma;
+  logsigma = __logf(sigma);
+  sig = rho > 20.f ? 1.f : __fdividef(e, 1.f + e);
+}
+
+struct AdamHyper {
+  float kl_scale, step_size, inv_sqrt_bc2, beta1, beta2, eps;
+  const float* sched_dev;
+};
+
+__device__ __forceinline__ float adam_update(float w, float grad, float& m, float& v, const AdamHyper& h) {
+  m = fmaf(h.beta1, m, (1.f - h.beta1) * grad);
+  v = fmaf(h.beta2, v, (1.f - h.beta2) * grad * grad);
+  return w - h.step_size * __fdividef(m, fmaf(sqrtf(v), h.inv_sqrt_bc2, h.eps));
+}
+
+// unit = 8 consecutive elements of this rank's chunk of one segment (both tensors of a pair); adam_prefix[s] = first unit
+__global__ void __launch_bounds__(256) shard_adam_kernel(const pl_shard_ctx c, float* __restrict__ mstate,
+                                                         float* __restrict__ vstate, AdamHyper h,
+                                                         double* __restrict__ kl_out) {
+  if (h.sched_dev) {
+    h.step_size = __ldg(h.sched_dev);
+    h.inv_sqrt_bc2 = __ldg(h.sched_dev + 1);
+  }
+  uint8_t* base = (uint8_t*)c.peers[c.rank];
+  const int world = c.world, rank = c.rank;
+  const int64_t total = c.adam_units;
+  float kl = 0.f;
+  int si = 0;
+  for (int64_t u = (int64_t)blockIdx.x * 256 + threadIdx.x; u < total; u += (int64_t)gridDim.x * 256) {
+    while (u >= c.adam_prefix[si + 1]) ++si;
+    const pl_shard_seg sg = c.segs[si];
+    const int64_t j = (u - c.adam_prefix[si]) * 8;            // offset inside this rank's chunk
+    const int64_t f0 = (int64_t)rank * sg.chunk + j;          // element index inside the tensor
+    const int nval = (int)min((int64_t)8, sg.numel - f0);     // >= 1 by construction of the prefix
+    const float ip2 = sg.kind ? 1.f / (sg.prior_scale * sg.prior_scale) : 0.f;
+    float w[8], g[8], m[8], v[8];
+    // ---- first tensor (plain parameter, or the posterior mean of a pair) ----
+    {
+      const float* G = (const float*)(base + sg.g_off) + j;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) g[t] = 0.f;
+      for (int s = 0; s < world; ++s) {                       // fixed order: deterministic
+        const float4 a = *reinterpret_cast<const float4*>(G + (int64_t)s * sg.chunk);
+        const float4 b = *reinterpret_cast<const float4*>(G + (int64_t)s * sg.chunk + 4);
+        g[0] += a.x; g[1] += a.y; g[2] += a.z; g[3] += a.w; g[4] += b.x; g[5] += b.y; g[6] += b.z; g[7] += b.w;
+      }
+      float* P = (float*)(base + sg.p_off) + f0;
+      float* M = mstate + sg.s_off + j;
+      float* V = vstate + sg.s_off + j;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const bool ok = t < nval;
+        w[t] = ok ? P[t] : 0.f;
+        m[t] = ok ? M[t] : 0.f;
+        v[t] = ok ? V[t] : 0.f;
+        float grad = g[t];
+        if (sg.kind == 1) {
+          grad = fmaf(h.kl_scale * ip2, w[t], grad);
+          if (ok) kl = fmaf(0.5f * ip2 * w[t], w[t], kl);
+        }
+        w[t] = adam_update(w[t], grad, m[t], v[t], h);
+        if (ok) {
+          P[t] = w[t];
+          M[t] = m[t];
+          V[t] = v[t];
+        }
+      }
+      if (sg.gather == 0) {        // fp32 all-gather: the updated values into every other rank's parameter area
+        for (int q = 0; q < world; ++q) {
+          if (q == rank) continue;
+          float* R = (float*)((uint8_t*)c.peers[q] + sg.p_off) + f0;
+          if (nval == 8) {
+            reinterpret_cast<float4*>(R)[0] = make_float4(w[0], w[1], w[2], w[3]);
+            reinterpret_cast<float4*>(R)[1] = make_float4(w[4], w[5], w[6], w[7]);
+          } else {
+            for (int t = 0; t < nval; ++t) R[t] = w[t];
+          }
+        }
+      }
+    }
+    if (sg.kind != 1) continue;
+    // ---- second tensor: the posterior rho of the pair ----
+    const uint4 mu16 = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]),
+                                  pack_bf16x2(w[6], w[7]));
+    float sg8[8];
+    {
+      const float* G = (const float*)(base + sg.g2_off) + j;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) g[t] = 0.f;
+      for (int s = 0; s < world; ++s) {
+        const float4 a = *reinterpret_cast<const float4*>(G + (int64_t)s * sg.chunk);
+        const float4 b = *reinterpret_cast<const float4*>(G + (int64_t)s * sg.chunk + 4);
+        g[0] += a.x; g[1] += a.y; g[2] += a.z; g[3] += a.w; g[4] += b.x; g[5] += b.y; g[6] += b.z; g[7] += b.w;
+      }
+      float* P = (float*)(base + sg.p2_off) + f0;
+      float* M = mstate + sg.s_off + sg.chunk + j;
+      float* V = vstate + sg.s_off + sg.chunk + j;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const bool ok = t < nval;
+        const float rho = ok ? P[t] : 0.f;
+        m[t] = ok ? M[t] : 0.f;
+        v[t] = ok ? V[t] : 0.f;
+        float sigma, ls, sig;
+        sigma_parts2(rho, sigma, ls, sig);
+        float grad = sg.rho_raw ? g[t] * sig : g[t];
+        grad = fmaf(h.kl_scale * sig, fmaf(sigma, ip2, -__fdividef(1.f, sigma)), grad);
+        if (ok) kl += fmaf(0.5f * ip2 * sigma, sigma, -ls);
+        w[t] = adam_update(rho, grad, m[t], v[t], h);
+        if (ok) {
+          P[t] = w[t];
+          M[t] = m[t];
+          V[t] = v[t];
+        }
+        sg8[t] = ok ? softplus_f(w[t]) : 0.f;
+      }
+    }
+    if (sg.gather == 0) {
+      for (int q = 0; q < world; ++q) {
+        if (q == rank) continue;
+        float* R = (float*)((uint8_t*)c.peers[q] + sg.p2_off) + f0;
+        if (nval == 8) {
+          reinterpret_cast<float4*>(R)[0] = make_float4(w[0], w[1], w[2], w[3]);
+          reinterpret_cast<float4*>(R)[1] = make_float4(w[4], w[5], w[6], w[7]);
+        } else {
+          for (int t = 0; t < nval; ++t) R[t] = w[t];
+        }
+      }
+    } else {
+      // the tcgen05 kernels' operand form, 4 B/weight, into EVERY rank's arena (the owner's own included):
+      //   gather 1 (split):  mu16 [numel] bf16 at lp_off, sig16 [numel] bf16 at lp_off + lp_half
+      //   gather 2 (packed): {8 mu bf16 | 8 sigma bf16} groups of 32 bytes at lp_off
+      const uint4 s16 = make_uint4(pack_bf16x2(sg8[0], sg8[1]), pack_bf16x2(sg8[2], sg8[3]), pack_bf16x2(sg8[4], sg8[5]),
+                                   pack_bf16x2(sg8[6], sg8[7]));
+      const int64_t grp = f0 >> 3;
+      for (int q = 0; q < world; ++q) {
+        uint8_t* L = (uint8_t*)c.peers[q] + sg.lp_off;
+        if (sg.gather == 1) {
+          reinterpret_cast<uint4*>(L)[grp] = mu16;
+          reinterpret_cast<uint4*>(L + sg.lp_half)[grp] = s16;
+        } else {
+          reinterpret_cast<uint4*>(L)[2 * grp] = mu16;
+          reinterpret_cast<uint4*>(L)[2 * grp + 1] = s16;
+        }
+      }
+    }
+  }
+  if (kl_out) {
+    double d = warp_sum((double)kl);
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      d = 0.0;
+      for (int k = 0; k < 8; ++k) d += sm[k];
+      if (d != 0.0) atomicAdd(kl_out, d);
+    }
+  }
+}
+
+// ---- finish: share the KL partials, barrier, sum the statistics ---------------------------------------------------
+// stats_out[0] = sum_r LL_r, [1] = (sum_r kl_r + kl_const) * inv_ns, [2] = sum_r ACC_r, [3] = [0] + [1]
+__global__ void shard_finish_kernel(const pl_shard_ctx c, const double* __restrict__ kl_acc, double kl_const, double inv_ns,
+                                    float* __restrict__ stats_out) {
+  __shared__ uint32_t s_epoch;
+  if ((int)threadIdx.x < c.world) {
+    double* dst = (double*)((uint8_t*)c.peers[threadIdx.x] + c.kl_off) + c.rank;
+    *dst = kl_acc ? *kl_acc : 0.0;
+  }
+  grid_barrier_block(c, &s_epoch);
+  if (threadIdx.x == 0 && stats_out) {
+    const uint8_t* base = (const uint8_t*)c.peers[c.rank];
+    const float* st = (const float*)(base + c.stats_off);
+    const double* kls = (const double*)(base + c.kl_off);
+    float ll = 0.f, acc = 0.f;
+    double kl = 0.0;
+    for (int r = 0; r < c.world; ++r) {       // fixed order
+      ll += st[4 * r];
+      acc += st[4 * r + 2];
+      kl += kls[r];
+    }
+    const float klv = (float)((kl + kl_const) * inv_ns);
+    stats_out[0] = ll;
+    stats_out[1] = klv;
+    stats_out[2] = acc;
+    stats_out[3] = ll + klv;
+  }
+}
+
+static int check_ctx(const pl_shard_ctx* c, const char* who) {
+  PL_CHECK_ARG(c, "%s: NULL context", who);
+  PL_CHECK_ARG(c->world >= 1 && c->world <= PL_SHARD_MAX_RANKS && c->rank >= 0 && c->rank < c->world,
+               "%s: bad rank / world (%d / %d)", who, c->rank, c->world);
+  PL_CHECK_ARG(c->num_segs >= 0 && c->num_segs <= PL_SHARD_MAX_SEGS, "%s: too many segments (%d)", who, c->num_segs);
+  for (int r = 0; r < c->world; ++r) PL_CHECK_ARG(c->peers[r], "%s: NULL arena pointer of rank %d", who, r);
+  PL_CHECK_ARG(c->segs || c->num_segs == 0, "%s: NULL segment table", who);
+  return PL_OK;
+}
+
+}  // namespace pl
+
+// ---- CUDA IPC plumbing ------------------------------------------------------------------------------------------
+extern "C" int pl_ipc_export(const void* ptr, void* handle64, int64_t* offset_out) {
+  using namespace pl;
+  PL_CHECK_ARG(ptr && handle64 && offset_out, "pl_ipc_export: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+    set_error("pl_ipc_export: cuMemGetAddressRange entry point not available");
+    return PL_ERR_CUDA;
+  }
+  if (((RangeFn)fn)(&base, &size, (CUdeviceptr)ptr) != CUDA_SUCCESS) {
+    set_error("pl_ipc_export: cuMemGetAddressRange failed (not a device allocation?)");
+    return PL_ERR_CUDA;
+  }
+  cudaIpcMemHandle_t h;
+  PL_CUDA(cudaIpcGetMemHandle(&h, (void*)base));
+  memcpy(handle64, &h, 64);
+  *offset_out = (int64_t)((CUdeviceptr)ptr - base);
+  return PL_OK;
+}
+
+extern "C" int pl_ipc_open(const void* handle64, int64_t offset, void** ptr_out) {
+  using namespace pl;
+  PL_CHECK_ARG(handle64 && ptr_out, "pl_ipc_open: NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* base = nullptr;
+  PL_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr_out = (uint8_t*)base + offset;
+  return PL_OK;
+}
+
+extern "C" int pl_ipc_close(void* ptr, int64_t offset) {
+  using namespace pl;
+  if (!ptr) return PL_OK;
+  PL_CUDA(cudaIpcCloseMemHandle((uint8_t*)ptr - offset));
+  return PL_OK;
+}
+
+// ---- sharded step ----------------------------------------------------------------------------------------------
+extern "C" int pl_shard_push(const pl_shard_ctx* c, const float* grads, const float* stats4, void* stream) {
+  using namespace pl;
+  int rc = check_ctx(c, "pl_shard_push");
+  if (rc != PL_OK) return rc;
+  PL_CHECK_ARG(grads, "pl_shard_push: NULL gradients");
+  int64_t blocks = ceil_div64(c->push_units > 0 ? c->push_units : 1, 256 * 2);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  shard_push_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(*c, grads, stats4);
+  PL_LAUNCH_CHECK("shard_push_kernel");
+  return PL_OK;
+}
+
+extern "C" int pl_shard_barrier(const pl_shard_ctx* c, void* stream) {
+  using namespace pl;
+  int rc = check_ctx(c, "pl_shard_barrier");
+  if (rc != PL_OK) return rc;
+  shard_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*c);
+  PL_LAUNCH_CHECK("shard_barrier_kernel");
+  return PL_OK;
+}
+
+extern "C" int pl_shard_adam(const pl_shard_ctx* c, float* m, float* v, float kl_scale, float lr, float beta1, float beta2,
+                             float eps, int32_t step, const float* sched_dev, double* kl_value, void* stream) {
+  using namespace pl;
+  int rc = check_ctx(c, "pl_shard_adam");
+  if (rc != PL_OK) return rc;
+  PL_CHECK_ARG(m && v, "pl_shard_adam: NULL optimiser state");
+  PL_CHECK_ARG(sched_dev || step >= 1, "pl_shard_adam: step must be >= 1");
+  if (c->adam_units == 0) return PL_OK;
+  AdamHyper h;
+  if (sched_dev) step = 1;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  h.kl_scale = kl_scale;
+  h.step_size = (float)((double)lr / bc1);
+  h.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  h.beta1 = beta1; h.beta2 = beta2; h.eps = eps;
+  h.sched_dev = sched_dev;
+  int64_t blocks = ceil_div64(c->adam_units, 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  shard_adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(*c, m, v, h, kl_value);
+  PL_LAUNCH_CHECK("shard_adam_kernel");
+  return PL_OK;
+}
+
+extern "C" int pl_shard_finish(const pl_shard_ctx* c, const double* kl_acc, double kl_const, double inv_num_samples,
+                               float* stats_out4, void* stream) {
+  using namespace pl;
+  int rc = check_ctx(c, "pl_shard_finish");
+  if (rc != PL_OK) return rc;
+  shard_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*c, kl_acc, kl_const, inv_num_samples, stats_out4);
+  PL_LAUNCH_CHECK("shard_finish_kernel");
+  return PL_OK;
+}

@@ -113,6 +113,19 @@ static int tc_shape_ok(const pl_linear_args* a, const char* who) {
 
 int linear_bwd_simt_launch(const pl_linear_args* a);
 
+// the caller hands the weight in operand form (pl_linear_args.w_lp): point the state's parameter views at it
+static bool use_prepacked(const pl_linear_args* a, TcState& s) {
+  if (!a->w_lp || prec_tf32(a->precision)) return false;
+  if (prec_split(a->precision)) {
+    s.mean = (float*)a->w_lp;
+    s.sigma = (float*)((uint8_t*)a->w_lp + a->w_lp_half);
+  } else {
+    s.mean = nullptr;
+    s.sigma = (float*)a->w_lp;
+  }
+  return true;
+}
+
 // picks the sampled_gemm_tc instantiation for (injected eps, tf32, split operand); `mean` = the rounded-mean matrix
 // [w_rows][pitch] of the split kernels
 template <bool kDx>
@@ -155,14 +168,16 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   if (rc != PL_OK) return rc;
   cudaStream_t st = (cudaStream_t)a->stream;
   TcScratch w = carve_scratch(&fa, a->workspace, a->fwd_state == nullptr, false);
-  const TcState state = a->fwd_state ? carve_state(a, a->fwd_state) : w.st;
+  TcState state = a->fwd_state ? carve_state(a, a->fwd_state) : w.st;
   const int64_t I = a->in_features, O = a->out_features, MC = a->mc, B = a->batch;
   const int64_t x_rows = a->x_mc_stride == 0 ? B : MC * B;
   const bool tf32 = prec_tf32(a->precision);   // fp32 operands straight from the caller's tensors
   const bool split = prec_split(a->precision);
-  rc = split ? prep_params_split(a->w_mu, a->w_rho, state.mean, state.sigma, I, O, tf32, st)
-             : prep_params(a->w_mu, a->w_rho, state.sigma, I, O, tf32, st);
-  if (rc != PL_OK) return rc;
+  if (!use_prepacked(a, state)) {
+    rc = split ? prep_params_split(a->w_mu, a->w_rho, state.mean, state.sigma, I, O, tf32, st)
+               : prep_params(a->w_mu, a->w_rho, state.sigma, I, O, tf32, st);
+    if (rc != PL_OK) return rc;
+  }
   PL_CHECK_ARG(!tf32 || !(a->x_lp || a->y_lp), "pl_linear_fwd: bf16 activation chaining needs PL_PREC_BF16");
   if (!tf32 && !a->x_lp) {
     cast_bf16_kernel<<<ew_grid(x_rows * I / 8, 1024), 256, 0, st>>>(a->x, state.x_bf16, x_rows * I / 8);
@@ -214,11 +229,12 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
   if (rc != PL_OK) return rc;
   cudaStream_t st = (cudaStream_t)a->stream;
   TcScratch w = carve_scratch(a, a->workspace, !have_state, true);
-  const TcState state = have_state ? carve_state(a, a->fwd_state) : w.st;
+  TcState state = have_state ? carve_state(a, a->fwd_state) : w.st;
   const int64_t I = a->in_features, O = a->out_features, MC = a->mc, B = a->batch;
   const int64_t x_rows = a->x_mc_stride == 0 ? B : MC * B;
+  const bool prepacked = use_prepacked(a, state);
   if (!have_state) {
-    if (a->dx || a->dx_lp) {
+    if ((a->dx || a->dx_lp) && !prepacked) {
       rc = split ? prep_params_split(a->w_mu, a->w_rho, state.mean, state.sigma, I, O, tf32, st)
                  : prep_params(a->w_mu, a->w_rho, state.sigma, I, O, tf32, st);
       if (rc != PL_OK) return rc;
@@ -293,7 +309,7 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
     p.x_broadcast = a->x_mc_stride == 0;
     p.dy_broadcast = 0;
     p.w_aligned = 1;
-    p.w_rho = a->w_rho; p.eps_w = a->eps_w;
+    p.w_rho = a->dw_rho_raw ? nullptr : a->w_rho; p.eps_w = a->eps_w;
     p.sw = make_sampler(a->seed, a->layer_id, false, a->mc_global_offset, a->seed_dev);
     p.dw_mu = a->dw_mu; p.dw_rho = a->dw_rho;
     const int tiles = (int)(((I + 127) / 128) * ((O + 127) / 128));

@@ -986,7 +986,7 @@ struct TcDwParams {
   int atomic_out;          // several MC splits add into zero-initialised outputs
   int dy_broadcast;        // the second operand has no MC axis (conv: im2col of an MC-broadcast input)
   int w_aligned;           // w_out % 4 == 0: 128-bit eps / rho loads and gradient stores
-  const float* w_rho;      // [I, O]
+  const float* w_rho;      // [I, O]; NULL: leave drho un-scaled (sum dW*eps; the caller applies sigmoid(rho) later)
   const float* eps_w;      // optional injected eps [mc, I, O]
   Sampler sw;
   float* dw_mu;
@@ -1147,7 +1147,7 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
             for (int t = 0; t < 4; ++t)
               if (col + t < p.w_out) {
                 const float gmv = acc_mu[j + t];
-                const float grv = acc_rho[j + t] * sigmoid_f(__ldg(p.w_rho + idx + t));
+                const float grv = acc_rho[j + t] * (p.w_rho ? sigmoid_f(__ldg(p.w_rho + idx + t)) : 1.f);
                 if (p.atomic_out) {
                   atomicAdd(p.dw_mu + idx + t, gmv);
                   atomicAdd(p.dw_rho + idx + t, grv);
@@ -1158,10 +1158,12 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
               }
             continue;
           }
-          const float4 r = __ldg(reinterpret_cast<const float4*>(p.w_rho + idx));
           float4 gm = make_float4(acc_mu[j], acc_mu[j + 1], acc_mu[j + 2], acc_mu[j + 3]);
-          float4 gr = make_float4(acc_rho[j] * sigmoid_f(r.x), acc_rho[j + 1] * sigmoid_f(r.y),
-                                  acc_rho[j + 2] * sigmoid_f(r.z), acc_rho[j + 3] * sigmoid_f(r.w));
+          float4 gr = make_float4(acc_rho[j], acc_rho[j + 1], acc_rho[j + 2], acc_rho[j + 3]);
+          if (p.w_rho) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(p.w_rho + idx));
+            gr.x *= sigmoid_f(r.x); gr.y *= sigmoid_f(r.y); gr.z *= sigmoid_f(r.z); gr.w *= sigmoid_f(r.w);
+          }
           if (p.atomic_out) {
             atomicAdd(p.dw_mu + idx + 0, gm.x); atomicAdd(p.dw_mu + idx + 1, gm.y);
             atomicAdd(p.dw_mu + idx + 2, gm.z); atomicAdd(p.dw_mu + idx + 3, gm.w);

@@ -24,6 +24,11 @@ class SampleSpec:
     mc_global_offset: int = 0          # first global MC index owned by this rank
     precision: int = _cabi.PREC_FP32
     seed_dev: int = 0                  # device address of a uint64 added to ``seed`` by the kernels (CUDA graphs)
+    # MC-sharded training over peer memory (train.ELBOTrainStep, shard.PeerShard); used by the fused chain only
+    w_lp: int = 0                      # device address of the weight in operand form (0: pack per call)
+    w_lp_half: int = 0
+    dw_rho_raw: int = 0                # drho leaves the dW kernel as sum dW*eps (the shard owner applies sigmoid(rho))
+    grad_out: Optional[tuple] = None   # (dw_mu, dw_rho, db_mu, db_rho) tensors the backward writes straight into
 
 
 # ---- optional per-call CUDA-event timing (bench.py's roofline leg) -----------------------------

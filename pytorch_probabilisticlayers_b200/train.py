@@ -16,6 +16,11 @@ slices: a layer's slice is handed to NCCL (async, on NCCL's own stream) from a
 post-accumulate-grad hook as soon as that layer's backward kernels have been enqueued, so the
 transfer of layer L runs under the backward of layer L-1 and only the first layer's slice is
 exposed (SURVEY.md hard part H3).
+
+``exchange='peer'`` (the default on CUDA when every rank can map every other rank's memory) replaces the
+all-reduce + replicated optimiser pass by the NCCL-free sharded step of shard.py / csrc/comm.cu: reduce-scatter by
+peer stores, Adam + KL on the rank's 1/N shard, all-gather of the bf16 operand the forward consumes, two device-side
+barriers; the whole step is then a single stream of this library's kernels (CUDA-graph capturable at any N).
 """
 from __future__ import annotations
 
@@ -49,7 +54,7 @@ class ELBOTrainStep:
                  kl_kinds: Iterable = (BayesLinear, SIVILayer), with_accuracy: bool = True,
                  group: Optional[dist.ProcessGroup] = None, mc_coupled_loss: bool = False,
                  overlap: bool = True, fused_optimizer: bool = True,
-                 betas=(0.9, 0.999), eps: float = 1e-8):
+                 betas=(0.9, 0.999), eps: float = 1e-8, exchange: str = "auto"):
         self.net, self.criterion, self.num_samples = net, criterion, int(num_samples)
         self.kl_kinds = tuple(kl_kinds)
         self.with_accuracy = with_accuracy
@@ -114,8 +119,24 @@ class ELBOTrainStep:
                 kind, prior = kinds.get(id(p), (0, 1.0))
                 self._adam_plan.append((p, off, p.numel(), kind, prior))
                 off += p.numel()
+        # ---- gradient exchange for world > 1: 'peer' (shard.PeerShard) or 'nccl' (flat all-reduce) ----
+        self.shard = None
+        self.exchange = None if self.world == 1 else "nccl"
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        if self.world > 1 and exchange in ("auto", "peer") and self.fused_opt:
+            try:
+                self._setup_peer_exchange()
+                self.exchange = "peer"
+            except Exception as e:           # no peer mapping on this machine (or an unsupported net): NCCL path
+                if exchange == "peer":
+                    raise
+                self.exchange_fallback_reason = f"{type(e).__name__}: {e}"[:300]
+                self.shard = None
+        if self.world == 1 and self.fused_opt:
+            self._direct_grads()
         # per-layer slices of the flat buffer for the overlapped all-reduce
-        self.overlap = overlap and self.world > 1
+        self.overlap = overlap and self.world > 1 and self.shard is None
         self._handles = []
         self._graph = None         # CUDA-graph mode (enable_cuda_graph)
         self._capturing = False
@@ -149,6 +170,79 @@ class ELBOTrainStep:
                 cur = hi
             rest.append((cur, n + 4))
             self._rest = rest
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _fused_chains(self):
+        from .fused import FusedBayesMLP
+        return [m for m in self.net.modules() if isinstance(m, FusedBayesMLP)]
+
+    def _direct_grads(self):
+        """Fused chains write their parameter gradients straight into the flat buffer (no autograd accumulate pass)."""
+        for chain in self._fused_chains():
+            for l in chain.layers:
+                ps = (l.weight.loc, l.weight.logscale, l.bias.loc, l.bias.logscale)
+                if all(p.requires_grad and p.grad is not None for p in ps):
+                    sh = getattr(l, "_shard", None) or {}
+                    sh["grad_out"] = tuple(p.grad for p in ps)
+                    l._shard = sh
+
+    def _setup_peer_exchange(self):
+        """Builds the shard plan (shard.ShardPlan), moves parameters and gradients to its layout, maps the peers."""
+        from . import shard as S
+        if any(isinstance(m, SIVILayer) for m in self.net.modules()):
+            raise RuntimeError("SIVILayer's KL needs autograd through its hyper-network: NCCL exchange")
+        index = {id(p): i for i, p in enumerate(self.params)}
+        chained = {}
+        for chain in self._fused_chains():
+            for l in chain.layers:
+                chained[id(l)] = l._precision_code(True, True)
+        segs, used = [], set()
+        for m in self.kl_layers:
+            gaussian = not (isinstance(m, BayesLinear) and isinstance(m.prior, layers.LaplacePrior))
+            if not gaussian:
+                raise RuntimeError("LaplacePrior needs the autograd KL path: NCCL exchange")
+            prior = float(m.prior.scale if isinstance(m, BayesLinear) else m.prior_scale)
+            prec = chained.get(id(m))
+            gather = {_cabi.PREC_BF16: 1, _cabi.PREC_BF16_FAST: 2}.get(prec, 0)
+            if m.weight.loc.numel() % 8:
+                gather = 0
+            i1, i2 = index[id(m.weight.loc)], index[id(m.weight.logscale)]
+            segs.append(S.SegSpec(kind=1, numel=m.weight.loc.numel(), p_index=i1, p2_index=i2, gather=gather,
+                                  rho_raw=1 if gather else 0, prior_scale=prior))
+            used.update((i1, i2))
+        for i, p in enumerate(self.params):
+            if i not in used:
+                segs.append(S.SegSpec(kind=0, numel=p.numel(), p_index=i))
+        plan = S.ShardPlan(self.world, [p.numel() for p in self.params], segs)
+        dev = self.params[0].device
+        # flat gradient buffer in the arena's parameter layout (+ the 4 statistics)
+        n4 = plan.param_bytes // 4
+        self.flat = torch.zeros(n4 + 4, dtype=torch.float32, device=dev)
+        for p, off in zip(self.params, plan.param_offs):
+            p.grad = self.flat[off // 4:off // 4 + p.numel()].view_as(p)
+        self.stats = self.flat[n4:n4 + 4]
+        self.shard = S.PeerShard(plan, self.params, self.group)
+        self.shard_out = torch.zeros(4, dtype=torch.float32, device=dev)
+        by_index = {s.p_index: s for s in segs if s.kind == 1}
+        for chain in self._fused_chains():
+            for l in chain.layers:
+                s = by_index.get(index[id(l.weight.loc)])
+                sh = {}
+                if s is not None and s.gather:
+                    ptr, half = self.shard.lp_pointers(s)
+                    sh.update(w_lp=ptr, w_lp_half=half, dw_rho_raw=1)
+                l._shard = sh
+        self._direct_grads()
+        self.shard.initial_gather()
+        torch.cuda.synchronize(dev)
+        if self.shard.status() != 0:
+            raise RuntimeError("peer barrier timed out during set-up")
+
+    def sync_full_params(self):
+        """Peer exchange keeps the fp32 values of operand-gathered weights current on their owners only; this brings
+        them to every rank (checkpoints, evaluation, tests).  No-op otherwise."""
+        if self.shard is not None:
+            self.shard.sync_full_params(self.params)
 
     def _kl_backward(self, m):
         """Stream the analytic KL gradient of layer m (scaled 1/(N*num_samples)) into its .grad."""
@@ -265,6 +359,8 @@ class ELBOTrainStep:
         else:
             loss = ll if kl_graph is None else ll + kl_graph * inv
             loss.backward()
+        if self.shard is not None:
+            return self._peer_finish()
         if not self.overlap:
             for m in self.kl_layers:
                 self._kl_backward(m)
@@ -287,6 +383,24 @@ class ELBOTrainStep:
         out = self.stats.clone()
         out[3] = out[0] + out[1]
         return out
+
+    def _peer_finish(self):
+        """Gradient reduce-scatter (peer stores), sharded Adam + KL, operand all-gather (peer stores): csrc/comm.cu."""
+        sh = self.shard
+        self.adam_t += 1
+        sched = None
+        if self._capturing:
+            self._t_dev.add_(1.0)
+            bc1 = 1.0 - torch.pow(torch.full_like(self._t_dev, self.betas[0]), self._t_dev)
+            bc2 = 1.0 - torch.pow(torch.full_like(self._t_dev, self.betas[1]), self._t_dev)
+            self._sched.copy_(torch.cat([self.lr / bc1, torch.rsqrt(bc2)]).float())
+            sched = self._sched
+        PF._timed("shard_push", lambda: sh.push(self.flat, self.stats), ("bytes", 4.0 * (self.flat.numel() - 4)))
+        PF._timed("shard_barrier", sh.barrier)
+        PF._timed("shard_adam", lambda: sh.adam(1.0 / self.num_samples, self.lr, self.betas, self.eps, self.adam_t, sched),
+                  ("bytes", 4.0 * (self.flat.numel() - 4) + 28.0 * sh.plan.state_elems))
+        PF._timed("shard_finish", lambda: sh.finish(self.kl_const, 1.0 / self.num_samples, self.shard_out))
+        return self.shard_out.clone()
 
     def _fused_step(self):
         """Adam + KL gradient + KL value, one streaming kernel per parameter tensor."""

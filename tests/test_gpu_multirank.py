@@ -1,0 +1,54 @@
+"""Multi-GPU parity on the REAL kernels (SURVEY.md section 4 pin iv, "1-GPU vs N-GPU invariance"): the MC-sharded step on 2
+ranks -- NCCL-free peer exchange (csrc/comm.cu), eager and CUDA-graph replay, and the NCCL all-reduce path -- follows the
+single-GPU trajectory.  Needs >= 2 GPUs (gpurun --gpus 2); skipped on a single-GPU box."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WORKER = os.path.join(ROOT, "tests", "multirank_worker.py")
+
+
+def _run(n, out, *extra, port=29731):
+    if n == 1:
+        cmd = [sys.executable, WORKER, "--out", out, *extra]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+               "127.0.0.1", "--master-port", str(port), WORKER, "--out", out, *extra]
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    env.pop("WORLD_SIZE", None)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    return np.load(out + ".npz" if not out.endswith(".npz") else out)
+
+
+@pytest.fixture(scope="module")
+def single(tmp_path_factory):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d = tmp_path_factory.mktemp("mr")
+    return _run(1, str(d / "n1.npz")), d
+
+
+@pytest.mark.parametrize("exchange,graph", [("peer", 0), ("peer", 1), ("nccl", 0)])
+def test_two_ranks_follow_the_single_gpu_trajectory(single, exchange, graph):
+    ref, d = single
+    got = _run(2, str(d / f"n2_{exchange}_{graph}.npz"), "--exchange", exchange, "--graph", str(graph),
+               port=29731 + 7 * graph + (3 if exchange == "nccl" else 0))
+    assert str(got["exchange"]) == exchange and int(got["status"]) == 0, (got["exchange"], got["fallback"])
+    s1, s2 = ref["stats"], got["stats"]
+    for t in range(len(s1)):
+        if np.isnan(s2[t]).any():
+            continue
+        for k in (0, 1, 3):                 # LL, KL, loss (ACC is a count ratio)
+            assert abs(s2[t][k] - s1[t][k]) <= 1e-5 * max(abs(s1[t][k]), 1e-6), (t, k, s1[t], s2[t])
+    p1, p2 = ref["params"], got["params"]
+    # Adam turns last-bit gradient differences of near-zero gradients into O(lr) steps: compare in the max norm
+    assert np.abs(p1 - p2).max() <= 5e-3 * np.abs(p1).max()
+    assert np.linalg.norm(p1 - p2) <= 1e-4 * np.linalg.norm(p1)

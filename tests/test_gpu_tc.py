@@ -129,13 +129,18 @@ def test_tc_full_size_properties(plb):
 
 
 def test_tc_rejects_unsupported_shapes_loudly(plb):
+    """The C ABI refuses shapes the tensor-core kernels cannot tile (no silent wrong answer); the layer resolves a forced
+    tensor-core precision to fp32 for such shapes up front instead of failing inside autograd."""
+    from pytorch_probabilisticlayers_b200 import _cabi, functional as PF
     layer = plb.BayesLinear(30, 20).cuda()
-    layer.precision = "bf16"
+    spec = PF.SampleSpec(seed=1, layer_id=0, precision=_cabi.PREC_BF16)
     with pytest.raises(RuntimeError, match="multiples of 8"):
-        layer(torch.zeros(2, 4, 30, device="cuda"))
-    auto = plb.BayesLinear(30, 20).cuda()
-    auto.precision = "auto"                      # auto falls back to the fp32 kernels by shape
-    assert auto(torch.zeros(2, 4, 30, device="cuda")).shape == (2, 4, 20)
+        PF.bayes_linear(torch.zeros(2, 4, 30, device="cuda"), layer.weight.loc, layer.weight.logscale, layer.bias.loc,
+                        layer.bias.logscale, None, None, spec)
+    for prec in ("bf16", "tf32", "bf16_fast", "auto"):
+        layer.precision = prec                   # forced and auto modes fall back to the fp32 kernels by shape
+        assert layer(torch.zeros(2, 4, 30, device="cuda")).shape == (2, 4, 20)
+        assert layer._last[3].precision == _cabi.PREC_FP32
 
 
 # ---------------------------------------------------------------------------------------------
