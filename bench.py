@@ -367,9 +367,28 @@ def run_b200(args, wl):
     def step_resident():
         return trainer.step(x_dev, y_dev)
 
+    # e2e: every step's inputs come from pinned host memory and its [LL, KL, ACC, loss] is read back to the host.  The
+    # loader is double-buffered like any input pipeline: the H2D copy of step k+1 is issued on a copy stream before step k
+    # is launched, so it runs under step k's kernels; one H2D copy per step stays inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [(torch.empty_like(x_dev), torch.empty_like(y_dev)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    e2e_i = [0]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            bufs[i % 2][0].copy_(x_host, non_blocking=True)
+            bufs[i % 2][1].copy_(y_host, non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
     def step_e2e():
-        xs = x_host.to(dev, non_blocking=True)
-        ys = y_host.to(dev, non_blocking=True)
+        i = e2e_i[0]
+        if i == 0:
+            prefetch(0)
+        torch.cuda.current_stream(dev).wait_event(ready[i % 2])
+        prefetch(i + 1)                         # buffer (i+1)%2 was last read by step i-1, which the .cpu() below completed
+        e2e_i[0] = i + 1
+        xs, ys = bufs[i % 2]
         return trainer.step(xs, ys).cpu()        # D2H read of [LL, KL, ACC, loss] every step
 
     # clocks are sampled from before the warm-up to the end of the timed region (steps are ~10 ms:
@@ -632,7 +651,9 @@ def run_b200(args, wl):
                         "grad_exchange": exchange},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size(),
-                "d2h_bytes_per_step": 16},
+                "d2h_bytes_per_step": 16,
+                "loader": "double-buffered: the pinned-host -> device copy of step k+1 is issued on a copy stream when "
+                          "step k is launched; the result of every step is read back before the next one starts"},
         "gpu_launches": int(launches),
         "us_per_step": ms_step * 1e3,
         "eager_us_per_step": eager_us,

@@ -341,6 +341,10 @@ int pl_ipc_open(const void* handle64, int64_t offset, void** ptr_out);
 int pl_ipc_close(void* ptr, int64_t offset);
 
 int pl_shard_push(const pl_shard_ctx* c, const float* grads, const float* stats4, void* stream);
+/* The same for the 8-element units [unit_begin, unit_end) of push_prefix only (one layer's tensors, so that its transfer
+ * can run on a side stream under the backward of the layers before it); stats4 may be NULL. */
+int pl_shard_push_range(const pl_shard_ctx* c, const float* grads, const float* stats4, int64_t unit_begin,
+                        int64_t unit_end, void* stream);
 int pl_shard_barrier(const pl_shard_ctx* c, void* stream);
 /* sched_dev (optional, device): [lr/(1-beta1^t), 1/sqrt(1-beta2^t)] for CUDA-graph replays, else `step` (1-based). */
 int pl_shard_adam(const pl_shard_ctx* c, float* m, float* v, float kl_scale, float lr, float beta1, float beta2, float eps,

@@ -72,11 +72,11 @@ __global__ void shard_barrier_kernel(const pl_shard_ctx c) {
 // bytes (full 32-byte sectors -- partial-sector stores become separate byte-enabled NVLink packets).
 // push_prefix[s] = first 8-element unit of tensor slot s (2 slots per segment: [mean | rho]); 2 float4 per unit.
 __global__ void __launch_bounds__(256) shard_push_kernel(const pl_shard_ctx c, const float* __restrict__ grads,
-                                                         const float* __restrict__ stats4) {
+                                                         const float* __restrict__ stats4, int64_t u0, int64_t u1) {
   const pl_shard_seg* segs = c.segs;
-  const int64_t total = 2 * c.push_units;
+  const int64_t total = 2 * u1;
   int slot = 0;
-  for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < total; q += (int64_t)gridDim.x * 256) {
+  for (int64_t q = 2 * u0 + (int64_t)blockIdx.x * 256 + threadIdx.x; q < total; q += (int64_t)gridDim.x * 256) {
     const int64_t u = q >> 1;
     while (u >= c.push_prefix[slot + 1]) ++slot;
     const pl_shard_seg& sg = segs[slot >> 1];
@@ -379,16 +379,27 @@ extern "C" int pl_ipc_close(void* ptr, int64_t offset) {
 }
 
 // ---- sharded step ----------------------------------------------------------------------------------------------
-extern "C" int pl_shard_push(const pl_shard_ctx* c, const float* grads, const float* stats4, void* stream) {
+extern "C" int pl_shard_push_range(const pl_shard_ctx* c, const float* grads, const float* stats4, int64_t unit_begin,
+                                   int64_t unit_end, void* stream) {
   using namespace pl;
   int rc = check_ctx(c, "pl_shard_push");
   if (rc != PL_OK) return rc;
   PL_CHECK_ARG(grads, "pl_shard_push: NULL gradients");
-  int64_t blocks = ceil_div64(c->push_units > 0 ? 2 * c->push_units : 1, 256 * 4);
+  PL_CHECK_ARG(unit_begin >= 0 && unit_begin <= unit_end && unit_end <= c->push_units, "pl_shard_push: bad unit range");
+  if (unit_begin == unit_end && !stats4) return PL_OK;
+  int64_t blocks = ceil_div64(unit_end > unit_begin ? 2 * (unit_end - unit_begin) : 1, 256 * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  shard_push_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(*c, grads, stats4);
+  shard_push_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(*c, grads, stats4, unit_begin, unit_end);
   PL_LAUNCH_CHECK("shard_push_kernel");
   return PL_OK;
+}
+
+extern "C" int pl_shard_push(const pl_shard_ctx* c, const float* grads, const float* stats4, void* stream) {
+  if (!c) {
+    pl::set_error("pl_shard_push: NULL context");
+    return PL_ERR_BAD_ARG;
+  }
+  return pl_shard_push_range(c, grads, stats4, 0, c->push_units, stream);
 }
 
 extern "C" int pl_shard_barrier(const pl_shard_ctx* c, void* stream) {

@@ -29,6 +29,7 @@ class SampleSpec:
     w_lp_half: int = 0
     dw_rho_raw: int = 0                # drho leaves the dW kernel as sum dW*eps (the shard owner applies sigmoid(rho))
     grad_out: Optional[tuple] = None   # (dw_mu, dw_rho, db_mu, db_rho) tensors the backward writes straight into
+    after_bwd: Optional[object] = None  # callable run right after this layer's backward kernels are enqueued
 
 
 # ---- optional per-call CUDA-event timing (bench.py's roofline leg) -----------------------------

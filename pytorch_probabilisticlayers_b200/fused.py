@@ -142,6 +142,8 @@ class _FusedMLPFn(torch.autograd.Function):
                     a.dx_lp, a.dw_mu, a.dw_rho, a.db_mu, a.db_rho, a.dx = outs
                 if sp.grad_out is None:
                     grads[4 * li:4 * li + 4] = [dw_mu, dw_rho, db_mu, db_rho]
+                elif sp.after_bwd is not None:          # e.g. start this layer's gradient transfer on a side stream
+                    sp.after_bwd()
                 dy_lp = dx_lp
         return (dx0, None, None, *grads)
 
@@ -185,6 +187,7 @@ class FusedBayesMLP(torch.nn.Module):
             if sh is not None:                          # set by train.ELBOTrainStep (flat gradients / peer-sharded step)
                 spec.w_lp, spec.w_lp_half, spec.dw_rho_raw = sh.get("w_lp", 0), sh.get("w_lp_half", 0), sh.get("dw_rho_raw", 0)
                 spec.grad_out = sh.get("grad_out")
+                spec.after_bwd = sh.get("after_bwd")
             specs.append(spec)
             l._remember(mc, None, None, spec)
             params += [l.weight.loc, l.weight.logscale, l.bias.loc, l.bias.logscale]

@@ -250,11 +250,19 @@ class PeerShard:
         """(device pointer of the operand-form weight in OUR arena, byte distance to its sigma half)."""
         return self.arena.data_ptr() + seg.lp_off, seg.lp_half
 
-    def push(self, grads_flat, stats4):
+    def push(self, grads_flat, stats4, units=None):
+        """Scatter the local gradients to their owners; ``units`` = (begin, end) restricts it to a range of push units."""
+        u0, u1 = units if units is not None else (0, int(self.ctx.push_units))
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.pl_shard_push(C.byref(self.ctx), C.c_void_p(grads_flat.data_ptr()),
-                                               C.c_void_p(stats4.data_ptr() if stats4 is not None else None),
-                                               C.c_void_p(self._stream())), "pl_shard_push")
+            _cabi.check(self.lib.pl_shard_push_range(C.byref(self.ctx), C.c_void_p(grads_flat.data_ptr()),
+                                                     C.c_void_p(stats4.data_ptr() if stats4 is not None else None),
+                                                     C.c_int64(u0), C.c_int64(u1), C.c_void_p(self._stream())),
+                        "pl_shard_push")
+
+    def seg_units(self, seg_index):
+        """Push-unit range of segment ``seg_index`` (both tensors of a pair)."""
+        pp = self.plan.push_prefix()
+        return pp[2 * seg_index], pp[2 * seg_index + 2]
 
     def barrier(self):
         with torch.cuda.device(self.device):

@@ -186,7 +186,7 @@ class ELBOTrainStep:
                     sh["grad_out"] = tuple(p.grad for p in ps)
                     l._shard = sh
 
-    def _setup_peer_exchange(self):
+    def _setup_peer_exchange(self, overlap_push=True):
         """Builds the shard plan (shard.ShardPlan), moves parameters and gradients to its layout, maps the peers."""
         from . import shard as S
         if any(isinstance(m, SIVILayer) for m in self.net.modules()):
@@ -223,20 +223,38 @@ class ELBOTrainStep:
         self.stats = self.flat[n4:n4 + 4]
         self.shard = S.PeerShard(plan, self.params, self.group)
         self.shard_out = torch.zeros(4, dtype=torch.float32, device=dev)
-        by_index = {s.p_index: s for s in segs if s.kind == 1}
+        by_index = {s.p_index: (k, s) for k, s in enumerate(segs) if s.kind == 1}
+        # a chained layer's weight gradients leave for their owners on a side stream as soon as its backward kernels are
+        # enqueued: the transfer of layer L runs under the backward of layer L-1 (the push blocks fit next to the one
+        # tcgen05 CTA per SM); only the first layer's transfer and the small tensors stay on the critical path
+        self._side = torch.cuda.Stream(device=dev)
+        self._pushed = []                  # unit ranges already handed to the side stream in this step
         for chain in self._fused_chains():
             for l in chain.layers:
-                s = by_index.get(index[id(l.weight.loc)])
+                k, s = by_index.get(index[id(l.weight.loc)], (None, None))
                 sh = {}
                 if s is not None and s.gather:
                     ptr, half = self.shard.lp_pointers(s)
                     sh.update(w_lp=ptr, w_lp_half=half, dw_rho_raw=1)
+                if s is not None and overlap_push:
+                    sh["after_bwd"] = self._make_push_hook(self.shard.seg_units(k))
                 l._shard = sh
         self._direct_grads()
         self.shard.initial_gather()
         torch.cuda.synchronize(dev)
         if self.shard.status() != 0:
             raise RuntimeError("peer barrier timed out during set-up")
+
+    def _make_push_hook(self, units):
+        def hook():
+            main = torch.cuda.current_stream(self.flat.device)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self._side.wait_event(ev)
+            with torch.cuda.stream(self._side):
+                self.shard.push(self.flat, None, units)
+            self._pushed.append(units)
+        return hook
 
     def sync_full_params(self):
         """Peer exchange keeps the fp32 values of operand-gathered weights current on their owners only; this brings
@@ -395,7 +413,28 @@ class ELBOTrainStep:
             bc2 = 1.0 - torch.pow(torch.full_like(self._t_dev, self.betas[1]), self._t_dev)
             self._sched.copy_(torch.cat([self.lr / bc1, torch.rsqrt(bc2)]).float())
             sched = self._sched
-        PF._timed("shard_push", lambda: sh.push(self.flat, self.stats), ("bytes", 4.0 * (self.flat.numel() - 4)))
+        # what the side stream has not taken already (+ the statistics), then join it
+        done = sorted(self._pushed)
+        self._pushed = []
+        cur, rest = 0, []
+        for lo, hi in done:
+            if lo > cur:
+                rest.append((cur, lo))
+            cur = max(cur, hi)
+        total = int(sh.ctx.push_units)
+        if cur < total:
+            rest.append((cur, total))
+        if not rest:
+            rest = [(total, total)]
+
+        def push_rest():
+            for i, r in enumerate(rest):
+                sh.push(self.flat, self.stats if i == 0 else None, r)
+            if done:
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+                torch.cuda.current_stream(self.flat.device).wait_event(ev)
+        PF._timed("shard_push", push_rest, ("bytes", 4.0 * (self.flat.numel() - 4)))
         PF._timed("shard_barrier", sh.barrier)
         PF._timed("shard_adam", lambda: sh.adam(1.0 / self.num_samples, self.lr, self.betas, self.eps, self.adam_t, sched),
                   ("bytes", 4.0 * (self.flat.numel() - 4) + 28.0 * sh.plan.state_elems))
