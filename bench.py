@@ -407,10 +407,13 @@ def run_b200(args, wl):
             trainer._eager_step(x_dev, y_dev) if trainer._graph is not None else step_resident()
         return PF.profile_stop(), n
 
-    # launch-bound configurations replay the step from a CUDA graph by default (host enqueue >= GPU time)
-    # (and so does the peer-exchange multi-GPU step, which is one stream of this library's kernels: no NCCL inside)
+    # launch-bound configurations replay the step from a CUDA graph by default: the regression configs, any workload
+    # whose host enqueue time is >= 80 % of its GPU time (probed here), and the peer-exchange multi-GPU step (one
+    # stream of this library's kernels, no NCCL inside)
+    probe_ms = timed(step_resident, 5) / 5
+    host_bound = host_ms.get("step_resident", 0.0) >= 0.8 * probe_ms and world == 1
     use_graph = args.cuda_graph if args.cuda_graph is not None else bool(
-        wl.get("regression") or (world > 1 and trainer.exchange == "peer"))
+        wl.get("regression") or host_bound or (world > 1 and trainer.exchange == "peer"))
     prof = None
     launches_per_step = None
     eager_us = None

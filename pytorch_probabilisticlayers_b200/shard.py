@@ -186,8 +186,9 @@ class PeerShard:
     def __init__(self, plan: ShardPlan, params, group=None):
         self.plan = plan
         self.group = group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
+        multi = plan.world > 1
+        self.rank = dist.get_rank(group) if multi else 0
+        self.world = dist.get_world_size(group) if multi else 1
         assert self.world == plan.world
         self.lib = _cabi.lib()
         dev = params[0].device
@@ -201,18 +202,22 @@ class PeerShard:
                 view.copy_(p.data)
                 p.data = view
             torch.cuda.synchronize(dev)
-            handle = (C.c_uint8 * 64)()
-            offset = C.c_int64(0)
-            _cabi.check(self.lib.pl_ipc_export(C.c_void_p(self.arena.data_ptr()), handle, C.byref(offset)), "pl_ipc_export")
-            mine = (bytes(handle), int(offset.value))
-            everyone = [None] * self.world
-            dist.all_gather_object(everyone, mine, group=group)
             self._opened = []
             peers = []
-            for r, (h, off) in enumerate(everyone):
+            everyone = [None]
+            if multi:
+                handle = (C.c_uint8 * 64)()
+                offset = C.c_int64(0)
+                _cabi.check(self.lib.pl_ipc_export(C.c_void_p(self.arena.data_ptr()), handle, C.byref(offset)),
+                            "pl_ipc_export")
+                mine = (bytes(handle), int(offset.value))
+                everyone = [None] * self.world
+                dist.all_gather_object(everyone, mine, group=group)
+            for r, item in enumerate(everyone):
                 if r == self.rank:
                     peers.append(self.arena.data_ptr())
                     continue
+                h, off = item
                 out = C.c_void_p()
                 buf = (C.c_uint8 * 64).from_buffer_copy(h)
                 _cabi.check(self.lib.pl_ipc_open(buf, C.c_int64(off), C.byref(out)), "pl_ipc_open")
@@ -241,10 +246,16 @@ class PeerShard:
             self.m = torch.zeros(max(plan.state_elems, 8), dtype=torch.float32, device=dev)
             self.v = torch.zeros(max(plan.state_elems, 8), dtype=torch.float32, device=dev)
             self.kl_acc = torch.zeros(1, dtype=torch.float64, device=dev)
-        dist.barrier(group=group)      # every rank has mapped every arena before anyone stores into a peer
+        if multi:
+            dist.barrier(group=group)  # every rank has mapped every arena before anyone stores into a peer
 
     def _stream(self):
         return _cabi.current_stream(self.device)
+
+    def staging_view(self, seg: SegSpec, second=False):
+        """fp32 view of this rank's own staging row of a segment (world == 1: the gradient buffer itself)."""
+        off = (seg.g2_off if second else seg.g_off) + self.rank * seg.chunk * 4
+        return self.arena[off:off + seg.numel * 4].view(torch.float32)
 
     def lp_pointers(self, seg: SegSpec):
         """(device pointer of the operand-form weight in OUR arena, byte distance to its sigma half)."""

@@ -134,6 +134,13 @@ class ELBOTrainStep:
                 self.exchange_fallback_reason = f"{type(e).__name__}: {e}"[:300]
                 self.shard = None
         if self.world == 1 and self.fused_opt:
+            # single GPU: the same kernel as ONE multi-tensor launch over all parameter tensors (segment table) instead of
+            # one launch per tensor; the gradient buffer is the shard arena's staging area, so nothing is copied
+            try:
+                self._setup_peer_exchange()
+            except Exception as e:
+                self.exchange_fallback_reason = f"{type(e).__name__}: {e}"[:300]
+                self.shard = None
             self._direct_grads()
         # per-layer slices of the flat buffer for the overlapped all-reduce
         self.overlap = overlap and self.world > 1 and self.shard is None
@@ -189,7 +196,7 @@ class ELBOTrainStep:
     def _setup_peer_exchange(self, overlap_push=True):
         """Builds the shard plan (shard.ShardPlan), moves parameters and gradients to its layout, maps the peers."""
         from . import shard as S
-        if any(isinstance(m, SIVILayer) for m in self.net.modules()):
+        if self.world > 1 and any(isinstance(m, SIVILayer) for m in self.net.modules()):
             raise RuntimeError("SIVILayer's KL needs autograd through its hyper-network: NCCL exchange")
         index = {id(p): i for i, p in enumerate(self.params)}
         chained = {}
@@ -200,12 +207,14 @@ class ELBOTrainStep:
         for m in self.kl_layers:
             gaussian = not (isinstance(m, BayesLinear) and isinstance(m.prior, layers.LaplacePrior))
             if not gaussian:
-                raise RuntimeError("LaplacePrior needs the autograd KL path: NCCL exchange")
+                if self.world > 1:
+                    raise RuntimeError("LaplacePrior needs the autograd KL path: NCCL exchange")
+                continue                          # per-element prior: plain Adam tensors, KL through autograd
             prior = float(m.prior.scale if isinstance(m, BayesLinear) else m.prior_scale)
             prec = chained.get(id(m))
             gather = {_cabi.PREC_BF16: 1, _cabi.PREC_BF16_FAST: 2}.get(prec, 0)
-            if m.weight.loc.numel() % 8:
-                gather = 0
+            if m.weight.loc.numel() % 8 or self.world == 1:
+                gather = 0                        # single GPU: the layers pack their operand per call as before
             i1, i2 = index[id(m.weight.loc)], index[id(m.weight.logscale)]
             segs.append(S.SegSpec(kind=1, numel=m.weight.loc.numel(), p_index=i1, p2_index=i2, gather=gather,
                                   rho_raw=1 if gather else 0, prior_scale=prior))
@@ -213,16 +222,29 @@ class ELBOTrainStep:
         for i, p in enumerate(self.params):
             if i not in used:
                 segs.append(S.SegSpec(kind=0, numel=p.numel(), p_index=i))
+        if len(segs) > S.MAX_SEGS:
+            raise RuntimeError(f"{len(segs)} optimiser segments > {S.MAX_SEGS}")
         plan = S.ShardPlan(self.world, [p.numel() for p in self.params], segs)
         dev = self.params[0].device
+        self.shard = S.PeerShard(plan, self.params, self.group)
+        self.shard_out = torch.zeros(4, dtype=torch.float32, device=dev)
+        if self.world == 1:
+            # the gradients live directly in the (single-row) staging area the optimiser kernel reads: no push
+            lo = min(s.g_off for s in segs)
+            self.flat = self.shard.arena[lo:plan.stats_off].view(torch.float32)
+            for s in segs:
+                self.params[s.p_index].grad = self.shard.staging_view(s).view_as(self.params[s.p_index])
+                if s.kind == 1:
+                    self.params[s.p2_index].grad = self.shard.staging_view(s, True).view_as(self.params[s.p2_index])
+            self.stats = torch.zeros(4, dtype=torch.float32, device=dev)
+            self.adam_m = self.adam_v = None          # the shard owns the optimiser state
+            return
         # flat gradient buffer in the arena's parameter layout (+ the 4 statistics)
         n4 = plan.param_bytes // 4
         self.flat = torch.zeros(n4 + 4, dtype=torch.float32, device=dev)
         for p, off in zip(self.params, plan.param_offs):
             p.grad = self.flat[off // 4:off // 4 + p.numel()].view_as(p)
         self.stats = self.flat[n4:n4 + 4]
-        self.shard = S.PeerShard(plan, self.params, self.group)
-        self.shard_out = torch.zeros(4, dtype=torch.float32, device=dev)
         by_index = {s.p_index: (k, s) for k, s in enumerate(segs) if s.kind == 1}
         # a chained layer's weight gradients leave for their owners on a side stream as soon as its backward kernels are
         # enqueued: the transfer of layer L runs under the backward of layer L-1 (the push blocks fit next to the one
@@ -328,8 +350,11 @@ class ELBOTrainStep:
         layers.set_seed_device_offset(self._seed_dev)
         graph = torch.cuda.CUDAGraph()
         self._capturing = True
+        torch.cuda.synchronize(dev)
         try:
-            with torch.cuda.graph(graph):
+            # capture on the stream the warm-up ran on: layers that keep last-forward tensors (SIVILayer's w_mu / kl_div,
+            # hence the AccumulateGrad nodes of its hyper-net) must not tie the capture to the legacy default stream
+            with torch.cuda.graph(graph, stream=side):
                 self._gout = self._eager_step(self._gx, self._gy)
                 # advance the device-side step state for the NEXT replay
                 self._seed_dev.add_(_GOLDEN_SIGNED)
@@ -413,6 +438,14 @@ class ELBOTrainStep:
             bc2 = 1.0 - torch.pow(torch.full_like(self._t_dev, self.betas[1]), self._t_dev)
             self._sched.copy_(torch.cat([self.lr / bc1, torch.rsqrt(bc2)]).float())
             sched = self._sched
+        if self.world == 1:
+            # one multi-tensor launch: Adam + KL gradient + KL value over every parameter tensor
+            PF._timed("adam_kl_multi", lambda: sh.adam(1.0 / self.num_samples, self.lr, self.betas, self.eps, self.adam_t, sched),
+                      ("bytes", 28.0 * sh.plan.state_elems))
+            self.stats[1] += ((sh.kl_acc[0] + self.kl_const) / self.num_samples).float()
+            out = self.stats.clone()
+            out[3] = out[0] + out[1]
+            return out
         # what the side stream has not taken already (+ the statistics), then join it
         done = sorted(self._pushed)
         self._pushed = []
