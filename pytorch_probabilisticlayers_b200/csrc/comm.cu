@@ -152,16 +152,18 @@ __device__ __forceinline__ void store8(float* P, float* M, float* V, int nval, c
     reinterpret_cast<float4*>(V)[0] = make_float4(v[0], v[1], v[2], v[3]);
     reinterpret_cast<float4*>(V)[1] = make_float4(v[4], v[5], v[6], v[7]);
   } else {
-    for (int t = 0; t < nval; ++t) {
-      P[t] = w[t];
-      M[t] = m[t];
-      V[t] = v[t];
-    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t)       // fully unrolled + predicated: the arrays must stay in registers
+      if (t < nval) {
+        P[t] = w[t];
+        M[t] = m[t];
+        V[t] = v[t];
+      }
   }
 }
 
 // unit = 8 consecutive elements of this rank's chunk of one segment (both tensors of a pair); adam_prefix[s] = first unit
-__global__ void __launch_bounds__(256) shard_adam_kernel(const pl_shard_ctx c, float* __restrict__ mstate,
+__global__ void __launch_bounds__(256, 2) shard_adam_kernel(const pl_shard_ctx c, float* __restrict__ mstate,
                                                          float* __restrict__ vstate, AdamHyper h,
                                                          double* __restrict__ kl_out) {
   if (h.sched_dev) {
@@ -171,11 +173,16 @@ __global__ void __launch_bounds__(256) shard_adam_kernel(const pl_shard_ctx c, f
   uint8_t* base = (uint8_t*)c.peers[c.rank];
   const int world = c.world, rank = c.rank;
   const int64_t total = c.adam_units;
+  // the segment table is read once per 8 elements: keep it in shared memory
+  __shared__ pl_shard_seg s_segs[PL_SHARD_MAX_SEGS];
+  for (int i = threadIdx.x; i < c.num_segs * (int)(sizeof(pl_shard_seg) / 8); i += 256)
+    reinterpret_cast<int64_t*>(s_segs)[i] = reinterpret_cast<const int64_t*>(c.segs)[i];
+  __syncthreads();
   float kl = 0.f;
   int si = 0;
   for (int64_t u = (int64_t)blockIdx.x * 256 + threadIdx.x; u < total; u += (int64_t)gridDim.x * 256) {
     while (u >= c.adam_prefix[si + 1]) ++si;
-    const pl_shard_seg sg = c.segs[si];
+    const pl_shard_seg& sg = s_segs[si];
     const int64_t j = (u - c.adam_prefix[si]) * 8;            // offset inside this rank's chunk
     const int64_t f0 = (int64_t)rank * sg.chunk + j;          // element index inside the tensor
     const int nval = (int)min((int64_t)8, sg.numel - f0);     // >= 1 by construction of the prefix
@@ -214,7 +221,9 @@ __global__ void __launch_bounds__(256) shard_adam_kernel(const pl_shard_ctx c, f
             reinterpret_cast<float4*>(R)[0] = make_float4(w[0], w[1], w[2], w[3]);
             reinterpret_cast<float4*>(R)[1] = make_float4(w[4], w[5], w[6], w[7]);
           } else {
-            for (int t = 0; t < nval; ++t) R[t] = w[t];
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+              if (t < nval) R[t] = w[t];
           }
         }
       }
@@ -259,7 +268,9 @@ __global__ void __launch_bounds__(256) shard_adam_kernel(const pl_shard_ctx c, f
           reinterpret_cast<float4*>(R)[0] = make_float4(w[0], w[1], w[2], w[3]);
           reinterpret_cast<float4*>(R)[1] = make_float4(w[4], w[5], w[6], w[7]);
         } else {
-          for (int t = 0; t < nval; ++t) R[t] = w[t];
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            if (t < nval) R[t] = w[t];
         }
       }
     } else {
@@ -428,7 +439,7 @@ extern "C" int pl_shard_adam(const pl_shard_ctx* c, float* m, float* v, float kl
   h.beta1 = beta1; h.beta2 = beta2; h.eps = eps;
   h.sched_dev = sched_dev;
   int64_t blocks = ceil_div64(c->adam_units, 256);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > 148 * 8) blocks = 148 * 8;
   shard_adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(*c, m, v, h, kl_value);
   PL_LAUNCH_CHECK("shard_adam_kernel");
   return PL_OK;

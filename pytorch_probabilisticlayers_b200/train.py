@@ -338,6 +338,14 @@ class ELBOTrainStep:
         if not (self.fused_opt and dev.type == "cuda"):
             raise RuntimeError("CUDA-graph mode needs the fused optimiser pass on a CUDA device")
         self._gx, self._gy = x.clone(), y.clone()
+        # Layers keep tensors of their last forward (kl_div, SIVILayer's w_mu / w_std ...).  Those keep the previous
+        # iteration's autograd graph -- and with it the AccumulateGrad nodes of the leaf parameters, which remember the
+        # stream they were created on -- alive.  Detach them so that the warm-up below recreates the nodes on the capture
+        # stream (otherwise autograd synchronises the capture with the legacy default stream: illegal during capture).
+        for m in self.net.modules():
+            for name, val in list(vars(m).items()):
+                if isinstance(val, torch.Tensor) and val.grad_fn is not None:
+                    setattr(m, name, val.detach())
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
