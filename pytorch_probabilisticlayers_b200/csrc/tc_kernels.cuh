@@ -783,26 +783,30 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 //   full barriers live in the leader CTA (peer producers arrive remotely, TMA bytes of both CTAs
 //   are credited to it); empty / accumulator barriers are multicast to both CTAs by tcgen05.commit.
 // ---------------------------------------------------------------------------------------------
-template <int MT2>
+template <int MT2, bool kSplit = false>
 struct Tc2Cfg {
-  static constexpr int kStagesA = 4;
-  static constexpr int kStagesB = 4;
+  // split: every B stage = this CTA's generated noise tile + its TMA-loaded mean tile (2 x 16 KB)
+  static constexpr int kStagesA = kSplit ? 3 : 4;
+  static constexpr int kStagesB = kSplit ? 3 : 4;
   static constexpr int kABytes = MT2 * kSubTileBytes;          // this CTA's rows of one k-block
-  static constexpr int kSmemBytes = kStagesA * kABytes + kStagesB * kSubTileBytes + 2048 + 1024;
+  static constexpr int kBBytes = (kSplit ? 2 : 1) * kSubTileBytes;
+  static constexpr int kSmemBytes = kStagesA * kABytes + kStagesB * kBBytes + 2048 + 1024;
   static constexpr int kTmemCols = MT2 * 256;                   // 256 or 512
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 };
 
-template <int MT2, bool kDx, bool kInjected>
+template <int MT2, bool kDx, bool kInjected, bool kSplit>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
-sampled_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams p) {
-  using Cfg = Tc2Cfg<MT2>;
+sampled_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const TcGemmParams p) {
+  using Cfg = Tc2Cfg<MT2, kSplit>;
   constexpr int kTileN = 256;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + Cfg::kStagesA * Cfg::kABytes;
-  const uint32_t sMisc = sB + Cfg::kStagesB * kSubTileBytes;
+  const uint32_t sMisc = sB + Cfg::kStagesB * Cfg::kBBytes;
   float* bias_s = reinterpret_cast<float*>(smem + (sMisc - smem_base));  // 256 floats
   const uint32_t bar0 = sMisc + 1024;
   auto a_full = [&](int s) { return bar0 + 8u * s; };
@@ -827,12 +831,14 @@ sampled_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams 
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < Cfg::kStagesB; ++s) {
-      mbar_init(b_full(s), 2 * kGenWarps);        // one elected arrival per generator warp, both CTAs
+      // one elected arrival per generator warp of both CTAs (+ split: the two mean-tile producers, like a_full)
+      mbar_init(b_full(s), 2 * kGenWarps + (kSplit ? 2 : 0));
       mbar_init(b_empty(s), 1);
     }
     mbar_init(acc_full, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmap_a);
+    if (kSplit) tma_prefetch_desc(&tmap_b);
   }
   if (warp == 1) tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
   if (warp >= 2) {
@@ -846,10 +852,25 @@ sampled_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams 
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs, own rows) =====================
+    // ===================== TMA producer (both CTAs, own rows / own weight columns) =====================
     if (lane == 0) {
       const int row0 = (int)(mc * p.a_mc_rows) + m0 + (int)rank * 128;
       for (int kb = 0; kb < num_kb; ++kb) {
+        if (kSplit) {
+          // this CTA's half of the mean tile, credited to the leader's b_full like the activation bytes
+          const int sb = kb % Cfg::kStagesB, pb = (kb / Cfg::kStagesB) & 1;
+          mbar_wait(b_empty(sb), pb ^ 1);
+          if (rank == 0) mbar_expect_tx(b_full(sb), 2 * kSubTileBytes);
+          else mbar_arrive_cluster(b_full(sb), 0);
+          const uint32_t dst = sB + sb * Cfg::kBBytes + kSubTileBytes;
+          if (kDx) {
+            tma_load_2d_2cta(dst, &tmap_b, b_full(sb), kb * kBK, nb0);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+              tma_load_2d_2cta(dst + g * (kSubTileBytes / 2), &tmap_b, b_full(sb), nb0 + g * 64, kb * kBK);
+          }
+        }
         const int s = kb % Cfg::kStagesA, ph = (kb / Cfg::kStagesA) & 1;
         mbar_wait(a_empty(s), ph ^ 1);
         if (rank == 0) mbar_expect_tx(a_full(s), 2 * Cfg::kABytes);
@@ -872,15 +893,25 @@ sampled_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams 
         mbar_wait_cluster(b_full(sb), pb);
         tc_fence_after_sync();
         const uint32_t a_addr = sA + sa * Cfg::kABytes;
-        const uint32_t b_addr = sB + sb * kSubTileBytes;
+        const uint32_t b_addr = sB + sb * Cfg::kBBytes;
 #pragma unroll
         for (int ks = 0; ks < kBK / 16; ++ks) {
-          const uint64_t b_desc = kDx ? smem_desc_sw128(b_addr + ks * 32, 16, 1024)
-                                      : smem_desc_sw128(b_addr + ks * 2048, 8192, 1024);
+          auto b_desc_at = [&](uint32_t base) {
+            return kDx ? smem_desc_sw128(base + ks * 32, 16, 1024) : smem_desc_sw128(base + ks * 2048, 8192, 1024);
+          };
+          const uint64_t b_desc = b_desc_at(b_addr);
 #pragma unroll
           for (int t = 0; t < MT2; ++t) {
             const uint64_t a_desc = smem_desc_sw128(a_addr + t * kSubTileBytes + ks * 32, 16, 1024);
             mma_bf16_ss_2cta(tmem_base + t * kTileN, a_desc, b_desc, idesc, (kb | ks) != 0);
+          }
+          if (kSplit) {   // the mean tiles of both CTAs into the same accumulators
+            const uint64_t m_desc = b_desc_at(b_addr + kSubTileBytes);
+#pragma unroll
+            for (int t = 0; t < MT2; ++t) {
+              const uint64_t a_desc = smem_desc_sw128(a_addr + t * kSubTileBytes + ks * 32, 16, 1024);
+              mma_bf16_ss_2cta(tmem_base + t * kTileN, a_desc, m_desc, idesc, 1u);
+            }
           }
         }
         mma_commit_2cta(a_empty(sa));
@@ -893,7 +924,7 @@ sampled_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams 
     // ===================== W-tile generators (both CTAs, own 128 columns) =====================
     const int gw = warp - 2;  // 0..15
     const Sampler sw = live(p.sw);
-    WGen<kDx, kInjected, false> gen;
+    WGen<kDx, kInjected, false, kSplit> gen;
     gen.init(gw, lane, nb0);
     const bool n_full = p.w_aligned && (kDx ? (nb0 + 128 <= p.w_in) : (nb0 + 128 <= p.w_out));
     const int k_extent = kDx ? p.w_out : p.w_in;
@@ -914,37 +945,64 @@ sampled_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const TcGemmParams 
         if (lane == 0) mbar_arrive_cluster(b_full((kb - 1) % Cfg::kStagesB), 0);   // the leader's barrier
       }
       mbar_wait(b_empty(s), ph ^ 1);
-      gen.store(sB + s * kSubTileBytes, lane);
+      gen.store(sB + s * Cfg::kBBytes, lane);
       if (kb + 1 < num_kb) load_block(kb + 1);
     }
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster(b_full((num_kb - 1) % Cfg::kStagesB), 0);
     // ===================== epilogue: this CTA's 128 rows of every sub-tile, all 256 columns ==========
+    const int q = warp & 3;
     mbar_wait(acc_full, 0);
     tc_fence_after_sync();
-    const int q = warp & 3;
 #pragma unroll 1
     for (int t = 0; t < MT2; ++t) {
       const int row = m0 + t * 256 + (int)rank * 128 + q * 32 + lane;
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
         const int col = (gw >> 2) * 64 + cc * 32;
+        uint4 mk[4];
+        if (p.mask_src) {   // chained dX: this lane's 64 bytes of the bf16 activation, in flight during the TMEM load
+          const __nv_bfloat16* src = p.mask_src + ((int64_t)mc * p.rows + row) * p.ndim + n0 + col;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            mk[c] = (row < p.rows && n0 + col + 8 * c < p.ndim) ? __ldg(reinterpret_cast<const uint4*>(src) + c)
+                                                                : make_uint4(0, 0, 0, 0);
+        }
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * kTileN + col), v);
         tmem_ld_wait();
         if (row < p.rows) {
           if (p.out_hw == 0) {
-            float* o = p.out + ((int64_t)mc * p.rows + row) * p.ndim + n0 + col;
+            const int64_t obase = ((int64_t)mc * p.rows + row) * p.ndim + n0 + col;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (n0 + col + j < p.ndim) {
-                float4 w;
-                w.x = __uint_as_float(v[j + 0]) + bias_s[col + j + 0];
-                w.y = __uint_as_float(v[j + 1]) + bias_s[col + j + 1];
-                w.z = __uint_as_float(v[j + 2]) + bias_s[col + j + 2];
-                w.w = __uint_as_float(v[j + 3]) + bias_s[col + j + 3];
-                *reinterpret_cast<float4*>(o + j) = w;
+            for (int j = 0; j < 32; j += 8) {
+              if (n0 + col + j < p.ndim) {   // ndim % 8 == 0 on this path
+                float w[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) w[e] = __uint_as_float(v[j + e]) + bias_s[col + j + e];
+                if (p.act) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) w[e] = w[e] > 0.f ? w[e] : p.act_slope * w[e];
+                }
+                if (p.mask_src) {
+                  const uint4 mkj = mk[j >> 3];
+                  const uint32_t mw[4] = {mkj.x, mkj.y, mkj.z, mkj.w};
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const uint32_t h = (e & 1) ? (mw[e >> 1] >> 16) : (mw[e >> 1] & 0xffffu);
+                    const bool pos = (h & 0x8000u) == 0 && (h & 0x7fffu) != 0;
+                    w[e] = pos ? w[e] : p.mask_slope * w[e];
+                  }
+                }
+                if (p.out) {
+                  *reinterpret_cast<float4*>(p.out + obase + j) = make_float4(w[0], w[1], w[2], w[3]);
+                  *reinterpret_cast<float4*>(p.out + obase + j + 4) = make_float4(w[4], w[5], w[6], w[7]);
+                }
+                if (p.out_lp)
+                  *reinterpret_cast<uint4*>(p.out_lp + obase + j) =
+                      make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]),
+                                 pack_bf16x2(w[6], w[7]));
               }
             }
           } else {
@@ -1287,34 +1345,38 @@ static inline int prep_params(const float* mu, const float* rho, float* buf, int
   return PL_OK;
 }
 
-// PL_TC_2CTA=1 selects the cta_group::2 kernels.  Measured on C4 (r01): 2.22 ms vs 1.78 ms per
-// 4096^2 forward for the 1-CTA kernel -- the kernels are bound by the sampler's issue rate, not by
-// shared-memory operand traffic, and pairing two SMs per stage hand-off costs more than it saves.
-// Kept (parity-tested) for when the sampler gets cheaper.
-static int g_force_1cta = -1;
+// Kernel choice between one CTA per tile and CTA pairs (cta_group::2): see launch_gemm.  r01 measured the pair kernel
+// equal to the 1-CTA kernel for the single rounded operand (sampler bound); the split-operand kernels issue twice the MMAs
+// and are bound by the shared-memory operand traffic of 128 x 128 MMAs, which the pair halves.  PL_TC_2CTA=0/1 overrides.
+static int g_tc_pairs = -2;     // -1: default policy, 0: never, 1: always (PL_TC_2CTA)
 
 template <bool kDx, bool kInj, bool kTf32 = false, bool kSplit = false>
 static int launch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_t st, const CUtensorMap* tm_b = nullptr) {
-  if (g_force_1cta < 0) {
+  if (g_tc_pairs == -2) {
     const char* e = getenv("PL_TC_2CTA");
-    g_force_1cta = (e && e[0] == '1') ? 0 : 1;
+    g_tc_pairs = !e ? -1 : (e[0] == '1' ? 1 : 0);
   }
   if (kSplit && !tm_b) {
     set_error("launch_gemm: the split-operand kernel needs the mean operand's tensor map");
     return PL_ERR_BAD_ARG;
   }
-  if (!kTf32 && !kSplit && !g_force_1cta && p.rows > 128 && p.ndim > 128 && p.out && !p.out_lp && !p.mask_src && !p.act) {
+  // CTA pairs (cta_group::2, M = 256 x N = 256 MMAs): halve the shared-memory operand traffic per MMA.  The split-operand
+  // kernels issue twice the MMAs and are bound by exactly that traffic with 128 x 128 MMAs, so pairs are their default;
+  // the single-operand kernels are bound by the sampler and gain nothing (r01).  PL_TC_2CTA=0 / 1 overrides.
+  const bool pair = kSplit ? g_tc_pairs != 0 : g_tc_pairs == 1;
+  if (!kTf32 && pair && p.rows > 128 && p.ndim > 128 && (p.out_hw == 0 || (p.out && !p.out_lp))) {
     const int pair_rows = p.rows > 256 ? 512 : 256;
     dim3 grid(2u * (unsigned)((p.ndim + 255) / 256), (unsigned)((p.rows + pair_rows - 1) / pair_rows),
               (unsigned)p.mc);
+    const CUtensorMap& tmb2 = tm_b ? *tm_b : tm;
     if (pair_rows == 512) {
-      auto kern = sampled_gemm_tc2<2, kDx, kInj>;
-      PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<2>::kSmemBytes));
-      kern<<<grid, kTcThreads, Tc2Cfg<2>::kSmemBytes, st>>>(tm, p);
+      auto kern = sampled_gemm_tc2<2, kDx, kInj, kSplit>;
+      PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<2, kSplit>::kSmemBytes));
+      kern<<<grid, kTcThreads, Tc2Cfg<2, kSplit>::kSmemBytes, st>>>(tm, tmb2, p);
     } else {
-      auto kern = sampled_gemm_tc2<1, kDx, kInj>;
-      PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<1>::kSmemBytes));
-      kern<<<grid, kTcThreads, Tc2Cfg<1>::kSmemBytes, st>>>(tm, p);
+      auto kern = sampled_gemm_tc2<1, kDx, kInj, kSplit>;
+      PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<1, kSplit>::kSmemBytes));
+      kern<<<grid, kTcThreads, Tc2Cfg<1, kSplit>::kSmemBytes, st>>>(tm, tmb2, p);
     }
     PL_LAUNCH_CHECK("sampled_gemm_tc2");
     return PL_OK;
