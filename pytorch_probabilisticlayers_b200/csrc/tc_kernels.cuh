@@ -1345,9 +1345,7 @@ static inline int prep_params(const float* mu, const float* rho, float* buf, int
   return PL_OK;
 }
 
-// Kernel choice between one CTA per tile and CTA pairs (cta_group::2): see launch_gemm.  r01 measured the pair kernel
-// equal to the 1-CTA kernel for the single rounded operand (sampler bound); the split-operand kernels issue twice the MMAs
-// and are bound by the shared-memory operand traffic of 128 x 128 MMAs, which the pair halves.  PL_TC_2CTA=0/1 overrides.
+// Kernel choice between one CTA per tile and CTA pairs (cta_group::2): see launch_gemm (PL_TC_2CTA=1 selects the pairs).
 static int g_tc_pairs = -2;     // -1: default policy, 0: never, 1: always (PL_TC_2CTA)
 
 template <bool kDx, bool kInj, bool kTf32 = false, bool kSplit = false>
@@ -1360,10 +1358,11 @@ static int launch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_
     set_error("launch_gemm: the split-operand kernel needs the mean operand's tensor map");
     return PL_ERR_BAD_ARG;
   }
-  // CTA pairs (cta_group::2, M = 256 x N = 256 MMAs): halve the shared-memory operand traffic per MMA.  The split-operand
-  // kernels issue twice the MMAs and are bound by exactly that traffic with 128 x 128 MMAs, so pairs are their default;
-  // the single-operand kernels are bound by the sampler and gain nothing (r01).  PL_TC_2CTA=0 / 1 overrides.
-  const bool pair = kSplit ? g_tc_pairs != 0 : g_tc_pairs == 1;
+  // CTA pairs (cta_group::2, M = 256 x N = 256 MMAs) halve the shared-memory operand traffic per MMA.  Measured equal to
+  // the 1-CTA kernels for both operand forms (r02 C4: 11.50 vs 11.59 ms/step, and slower on the 1000-wide layer): the
+  // fused kernels run at the board's power cap, where time follows the executed work, not its schedule.  Opt-in
+  // (PL_TC_2CTA=1), parity-tested.
+  const bool pair = g_tc_pairs == 1;
   if (!kTf32 && pair && p.rows > 128 && p.ndim > 128 && (p.out_hw == 0 || (p.out && !p.out_lp))) {
     const int pair_rows = p.rows > 256 ? 512 : 256;
     dim3 grid(2u * (unsigned)((p.ndim + 255) / 256), (unsigned)((p.rows + pair_rows - 1) / pair_rows),

@@ -166,3 +166,28 @@ def test_fused_chain_uses_split_operand_by_default(plb):
         assert not any(isinstance(m, FusedBayesMLP) for m in fuse_bayes_mlp(net, b)), "fp32 must not be downgraded to bf16"
     finally:
         plb.set_precision("fp32")
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", 2e-2), ("tf32", 2e-3), ("bf16_fast", 2e-2), ("tf32_fast", 2e-3)])
+@pytest.mark.parametrize("mc,b,i,o", [(2, 8, 2048, 136), (3, 40, 72, 264)])
+def test_tc_small_batch_and_ragged_widths_vs_oracle(plb, precision, tol, mc, b, i, o):
+    """Forced tensor-core modes on shapes 'auto' would leave to the fp32 kernels: batch far below one 128-row tile, K and N
+    tails, in every operand form."""
+    torch.manual_seed(b + o)
+    plb.manual_seed(555 + i)
+    layer = plb.BayesLinear(i, o).cuda()
+    layer.precision = precision
+    with torch.no_grad():
+        layer.weight.loc.normal_(0, 0.05)
+        layer.weight.logscale.fill_(-4.0)
+    x = torch.randn(mc, b, i, device="cuda", requires_grad=True)
+    gy = torch.randn(mc, b, o, device="cuda")
+    out = layer(x)
+    (out * gy).sum().backward()
+    eps_w, eps_b = n(layer.weight.eps), n(layer.bias.eps)
+    want = cf.linear_fwd(n(x), n(layer.weight.loc), n(layer.weight.logscale), eps_w, n(layer.bias.loc), n(layer.bias.logscale),
+                         eps_b)
+    bw = cf.linear_bwd(n(gy), n(x), n(layer.weight.loc), n(layer.weight.logscale), eps_w, n(layer.bias.logscale), eps_b)
+    errs = {"fwd": rel_err(n(out), want), "dx": rel_err(n(x.grad), bw["dx"]), "dmu": rel_err(n(layer.weight.loc.grad), bw["dw_mu"]),
+            "drho": rel_err(n(layer.weight.logscale.grad), bw["dw_rho"])}
+    assert all(e < tol for e in errs.values()), errs
