@@ -290,7 +290,11 @@ def make_inputs(torch, wl, pin=True):
     return (x.pin_memory(), y.pin_memory()) if pin else (x, y)
 
 
+GRAD_WIRE = ["fp32"]
+
+
 def make_trainer(plb, wl, net, **kw):
+    kw.setdefault("grad_wire", GRAD_WIRE[0])
     from pytorch_probabilisticlayers_b200.train import ELBOTrainStep
     ns = wl["num_samples"]
     crit = plb.MC_NLL(ns) if wl.get("regression") else plb.MC_CrossEntropyLoss(ns)
@@ -651,7 +655,7 @@ def run_b200(args, wl):
                                             and args.precision in FUSABLE),
                         "cuda_graph": bool(use_graph),
                         "parallelism": f"mc-shard x{world}" if world > 1 else "single",
-                        "grad_exchange": exchange},
+                        "grad_exchange": exchange, "grad_wire": args.grad_wire if exchange == "peer" else None},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size(),
                 "d2h_bytes_per_step": 16,
@@ -695,6 +699,8 @@ def main():
     ap.add_argument("--no-side-legs", action="store_true",
                     help="skip the secondary legs (tf32 / bf16_fast / gpu_eager_reference / cpu_baseline)")
     ap.add_argument("--no-weak", action="store_true", help="N>1: skip the report-only weak-scaling leg")
+    ap.add_argument("--grad-wire", choices=["fp32", "bf16"], default="fp32",
+                    help="N>1, peer exchange: format of the partial gradients on the wire (bf16 halves the reduce-scatter bytes)")
     ap.add_argument("--cuda-graph", dest="cuda_graph", action="store_true", default=None,
                     help="replay the whole step from a CUDA graph (default for the launch-bound c1 / c5)")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
@@ -702,6 +708,7 @@ def main():
                     help="run BayesLinear / LeakyReLU module by module instead of as a fused chain")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
+    GRAD_WIRE[0] = args.grad_wire
     if args.mc:
         wl["mc"] = args.mc
         wl["name"] = wl.get("name", args.workload) + f" [MC overridden to {args.mc}]"

@@ -323,7 +323,9 @@ typedef struct pl_shard_seg {
 } pl_shard_seg;
 
 typedef struct pl_shard_ctx {
-  int32_t rank, world, num_segs, _pad;
+  int32_t rank, world, num_segs;
+  int32_t wire_bf16;                 /* != 0: the partial gradients travel and are staged as bf16 (half the reduce-scatter
+                                        bytes; the owner still sums them in fp32, in rank order)                         */
   void* peers[PL_SHARD_MAX_RANKS];   /* arena base of every rank as mapped in THIS process (peers[rank] = own arena)   */
   const pl_shard_seg* segs;          /* DEVICE pointer: num_segs entries                                               */
   int64_t stats_off;                 /* float [world][4]: per-rank LL, -, ACC, -                                       */

@@ -76,6 +76,30 @@ __global__ void __launch_bounds__(256) shard_push_kernel(const pl_shard_ctx c, c
   const pl_shard_seg* segs = c.segs;
   const int64_t total = 2 * u1;
   int slot = 0;
+  if (c.wire_bf16) {
+    // bf16 wire format: one thread per 8-element unit, 16-byte stores of 8 bf16 partials (consecutive threads contiguous)
+    for (int64_t u = u0 + (int64_t)blockIdx.x * 256 + threadIdx.x; u < u1; u += (int64_t)gridDim.x * 256) {
+      while (u >= c.push_prefix[slot + 1]) ++slot;
+      const pl_shard_seg& sg = segs[slot >> 1];
+      const bool second = slot & 1;
+      const int64_t f0 = (u - c.push_prefix[slot]) * 8;
+      const int64_t numel = sg.numel, chunk = sg.chunk;
+      const int owner = (int)(f0 / chunk);
+      const int64_t j = f0 - (int64_t)owner * chunk;
+      const float* src = grads + (second ? sg.p2_off : sg.p_off) / 4 + f0;
+      float v[8];
+      if (f0 + 8 <= numel) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = f0 + t < numel ? __ldg(src + t) : 0.f;
+      }
+      uint16_t* dst = (uint16_t*)((uint8_t*)c.peers[owner] + (second ? sg.g2_off : sg.g_off)) + (int64_t)c.rank * chunk + j;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                                  pack_bf16x2(v[6], v[7]));
+    }
+  } else
   for (int64_t q = 2 * u0 + (int64_t)blockIdx.x * 256 + threadIdx.x; q < total; q += (int64_t)gridDim.x * 256) {
     const int64_t u = q >> 1;
     while (u >= c.push_prefix[slot + 1]) ++slot;
@@ -162,6 +186,31 @@ __device__ __forceinline__ void store8(float* P, float* M, float* V, int nval, c
   }
 }
 
+// sum over the ranks' staged partials of 8 consecutive elements, in rank order (deterministic); fp32 or bf16 wire format
+__device__ __forceinline__ void staged_sum8(const uint8_t* stage, int64_t chunk, int64_t j, int world, bool bf16, float (&g)[8]) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t) g[t] = 0.f;
+  if (bf16) {
+    const uint16_t* G = reinterpret_cast<const uint16_t*>(stage) + j;
+    for (int s = 0; s < world; ++s) {
+      const uint4 q = *reinterpret_cast<const uint4*>(G + (int64_t)s * chunk);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        g[2 * t] += __uint_as_float(w[t] << 16);
+        g[2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+      }
+    }
+  } else {
+    const float* G = reinterpret_cast<const float*>(stage) + j;
+    for (int s = 0; s < world; ++s) {
+      const float4 a = *reinterpret_cast<const float4*>(G + (int64_t)s * chunk);
+      const float4 b = *reinterpret_cast<const float4*>(G + (int64_t)s * chunk + 4);
+      g[0] += a.x; g[1] += a.y; g[2] += a.z; g[3] += a.w; g[4] += b.x; g[5] += b.y; g[6] += b.z; g[7] += b.w;
+    }
+  }
+}
+
 // unit = 8 consecutive elements of this rank's chunk of one segment (both tensors of a pair); adam_prefix[s] = first unit
 __global__ void __launch_bounds__(256, 2) shard_adam_kernel(const pl_shard_ctx c, float* __restrict__ mstate,
                                                          float* __restrict__ vstate, AdamHyper h,
@@ -190,14 +239,7 @@ __global__ void __launch_bounds__(256, 2) shard_adam_kernel(const pl_shard_ctx c
     float w[8], g[8], m[8], v[8];
     // ---- first tensor (plain parameter, or the posterior mean of a pair) ----
     {
-      const float* G = (const float*)(base + sg.g_off) + j;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) g[t] = 0.f;
-      for (int s = 0; s < world; ++s) {                       // fixed order: deterministic
-        const float4 a = *reinterpret_cast<const float4*>(G + (int64_t)s * sg.chunk);
-        const float4 b = *reinterpret_cast<const float4*>(G + (int64_t)s * sg.chunk + 4);
-        g[0] += a.x; g[1] += a.y; g[2] += a.z; g[3] += a.w; g[4] += b.x; g[5] += b.y; g[6] += b.z; g[7] += b.w;
-      }
+      staged_sum8(base + sg.g_off, sg.chunk, j, world, c.wire_bf16 != 0, g);
       float* P = (float*)(base + sg.p_off) + f0;
       float* M = mstate + sg.s_off + j;
       float* V = vstate + sg.s_off + j;
@@ -234,14 +276,7 @@ __global__ void __launch_bounds__(256, 2) shard_adam_kernel(const pl_shard_ctx c
                                   pack_bf16x2(w[6], w[7]));
     float sg8[8];
     {
-      const float* G = (const float*)(base + sg.g2_off) + j;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) g[t] = 0.f;
-      for (int s = 0; s < world; ++s) {
-        const float4 a = *reinterpret_cast<const float4*>(G + (int64_t)s * sg.chunk);
-        const float4 b = *reinterpret_cast<const float4*>(G + (int64_t)s * sg.chunk + 4);
-        g[0] += a.x; g[1] += a.y; g[2] += a.z; g[3] += a.w; g[4] += b.x; g[5] += b.y; g[6] += b.z; g[7] += b.w;
-      }
+      staged_sum8(base + sg.g2_off, sg.chunk, j, world, c.wire_bf16 != 0, g);
       float* P = (float*)(base + sg.p2_off) + f0;
       float* M = mstate + sg.s_off + sg.chunk + j;
       float* V = vstate + sg.s_off + sg.chunk + j;

@@ -36,7 +36,7 @@ class ShardSeg(C.Structure):
 
 
 class ShardCtx(C.Structure):
-    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("num_segs", C.c_int32), ("_pad", C.c_int32),
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("num_segs", C.c_int32), ("wire_bf16", C.c_int32),
                 ("peers", C.c_void_p * MAX_RANKS), ("segs", C.c_void_p),
                 ("stats_off", C.c_int64), ("kl_off", C.c_int64), ("flags_off", C.c_int64),
                 ("push_units", C.c_int64), ("adam_units", C.c_int64),
@@ -183,8 +183,9 @@ def emulate_step(plan: ShardPlan, params, grads_per_rank, m, v, lr, betas, eps, 
 class PeerShard:
     """Arena + peer mappings + C context of one rank.  ``params``: the trainer's parameters in flat-gradient order."""
 
-    def __init__(self, plan: ShardPlan, params, group=None):
+    def __init__(self, plan: ShardPlan, params, group=None, wire_bf16=False):
         self.plan = plan
+        self.wire_bf16 = bool(wire_bf16) and plan.world > 1
         self.group = group
         multi = plan.world > 1
         self.rank = dist.get_rank(group) if multi else 0
@@ -232,6 +233,7 @@ class PeerShard:
             self.segs_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
             ctx = ShardCtx()
             ctx.rank, ctx.world, ctx.num_segs = self.rank, self.world, len(plan.segs)
+            ctx.wire_bf16 = 1 if self.wire_bf16 else 0
             for r, ptr in enumerate(peers):
                 ctx.peers[r] = ptr
             ctx.segs = self.segs_dev.data_ptr()

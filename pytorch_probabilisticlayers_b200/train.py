@@ -54,7 +54,7 @@ class ELBOTrainStep:
                  kl_kinds: Iterable = (BayesLinear, SIVILayer), with_accuracy: bool = True,
                  group: Optional[dist.ProcessGroup] = None, mc_coupled_loss: bool = False,
                  overlap: bool = True, fused_optimizer: bool = True,
-                 betas=(0.9, 0.999), eps: float = 1e-8, exchange: str = "auto"):
+                 betas=(0.9, 0.999), eps: float = 1e-8, exchange: str = "auto", grad_wire: str = "fp32"):
         self.net, self.criterion, self.num_samples = net, criterion, int(num_samples)
         self.kl_kinds = tuple(kl_kinds)
         self.with_accuracy = with_accuracy
@@ -122,6 +122,13 @@ class ELBOTrainStep:
         # ---- gradient exchange for world > 1: 'peer' (shard.PeerShard) or 'nccl' (flat all-reduce) ----
         self.shard = None
         self.exchange = None if self.world == 1 else "nccl"
+        if grad_wire not in ("fp32", "bf16"):
+            raise ValueError("grad_wire must be 'fp32' or 'bf16'")
+        # peer exchange only: format of the partial gradients on the wire / in the owners' staging.  'bf16' halves the
+        # reduce-scatter bytes; every partial (a sum over MC/N samples) is rounded once to bf16 (rel 2^-9) and the owner sums
+        # the N partials in fp32 -- inside the tolerance class of the bf16 compute modes, outside the 1e-5 N-invariance of
+        # the default
+        self.grad_wire = grad_wire
         if exchange not in ("auto", "peer", "nccl"):
             raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
         if self.world > 1 and exchange in ("auto", "peer") and self.fused_opt:
@@ -226,7 +233,7 @@ class ELBOTrainStep:
             raise RuntimeError(f"{len(segs)} optimiser segments > {S.MAX_SEGS}")
         plan = S.ShardPlan(self.world, [p.numel() for p in self.params], segs)
         dev = self.params[0].device
-        self.shard = S.PeerShard(plan, self.params, self.group)
+        self.shard = S.PeerShard(plan, self.params, self.group, wire_bf16=self.grad_wire == "bf16")
         self.shard_out = torch.zeros(4, dtype=torch.float32, device=dev)
         if self.world == 1:
             # the gradients live directly in the (single-row) staging area the optimiser kernel reads: no push

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--graph", type=int, default=0)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--precision", default="auto")
+    ap.add_argument("--grad-wire", default="fp32")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -45,7 +46,7 @@ def main():
             if isinstance(m, plb.BayesLinear):
                 m.weight.logscale.fill_(-5.0)
     net = fuse_bayes_mlp(net, b)
-    tr = ELBOTrainStep(net, plb.MC_CrossEntropyLoss(ns), ns, lr=1e-3, exchange=args.exchange)
+    tr = ELBOTrainStep(net, plb.MC_CrossEntropyLoss(ns), ns, lr=1e-3, exchange=args.exchange, grad_wire=args.grad_wire)
     assert tr.set_shard(mc_total) == mc_total // world
     x = torch.randn(b, dims[0], device=dev)
     y = torch.randint(0, dims[-1], (b,), device=dev)

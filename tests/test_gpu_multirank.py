@@ -54,3 +54,17 @@ def test_two_ranks_follow_the_single_gpu_trajectory(single, exchange, graph):
     # Adam turns last-bit gradient differences of near-zero gradients into O(lr) steps: compare in the max norm
     assert np.abs(p1 - p2).max() <= 5e-3 * np.abs(p1).max()
     assert np.linalg.norm(p1 - p2) <= 1e-4 * np.linalg.norm(p1)
+
+
+def test_bf16_gradient_wire_stays_on_the_single_gpu_trajectory(single):
+    """Gate for grad_wire='bf16' (partial gradients rounded to bf16 on the wire, summed in fp32 by the owner): the 2-rank
+    trajectory stays within 1e-3 of the single-GPU loss -- the bf16 modes' tolerance class, not the 1e-5 of the fp32 wire."""
+    ref, d = single
+    got = _run(2, str(d / "n2_wire.npz"), "--exchange", "peer", "--grad-wire", "bf16", port=29771)
+    assert str(got["exchange"]) == "peer" and int(got["status"]) == 0
+    s1, s2 = ref["stats"], got["stats"]
+    for t in range(len(s1)):
+        for k, tol in ((0, 2e-2), (1, 1e-4), (3, 1e-4)):
+            assert abs(s2[t][k] - s1[t][k]) <= tol * max(abs(s1[t][k]), 1e-6), (t, k, s1[t], s2[t])
+    p1, p2 = ref["params"], got["params"]
+    assert np.linalg.norm(p1 - p2) <= 2e-3 * np.linalg.norm(p1)
