@@ -27,7 +27,13 @@ def run(prec):
         for l in lin:
             l.weight.loc.copy_(torch.randn_like(l.weight.loc) * 0.05)
     acts = {}
-    hooks = [m.register_forward_hook(lambda mod, i, o, n=n: (o.retain_grad(), acts.__setitem__(n, o))) for n, m in enumerate(net)]
+    def keep(n):
+        def hook(mod, i, o):
+            if o.requires_grad:
+                o.retain_grad()
+            acts[n] = o
+        return hook
+    hooks = [m.register_forward_hook(keep(n)) for n, m in enumerate(net)]
     y = net(x)
     y.square().sum().backward()
     out = {f"act{n}": a.detach().cpu().numpy() for n, a in acts.items()}
