@@ -456,6 +456,7 @@ def run_b200(args, wl):
     # total MC = MC x N); the headline above is the strong-scaling figure BASELINE.json's config names ----
     weak = None
     exchange = getattr(trainer, "exchange", None)
+    transport = getattr(trainer.shard, "transport", None) if trainer.shard is not None else None
     if world > 1 and not wl.get("conv") and not args.no_weak:
         if trainer.shard is not None:
             torch.cuda.synchronize()
@@ -655,7 +656,8 @@ def run_b200(args, wl):
                                             and args.precision in FUSABLE),
                         "cuda_graph": bool(use_graph),
                         "parallelism": f"mc-shard x{world}" if world > 1 else "single",
-                        "grad_exchange": exchange, "grad_wire": args.grad_wire if exchange == "peer" else None},
+                        "grad_exchange": exchange, "grad_wire": args.grad_wire if exchange == "peer" else None,
+                        "peer_transport": transport if world > 1 else None},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size(),
                 "d2h_bytes_per_step": 16,

@@ -328,6 +328,9 @@ typedef struct pl_shard_ctx {
                                         bytes; the owner still sums them in fp32, in rank order)                         */
   void* peers[PL_SHARD_MAX_RANKS];   /* arena base of every rank as mapped in THIS process (peers[rank] = own arena)   */
   const pl_shard_seg* segs;          /* DEVICE pointer: num_segs entries                                               */
+  void* mc_base;                     /* optional NVLS multicast mapping of the arenas (one store lands in every rank's
+                                        arena, replicated by the NVSwitch): the all-gather then leaves each GPU once
+                                        instead of once per peer; NULL = one store per peer                             */
   int64_t stats_off;                 /* float [world][4]: per-rank LL, -, ACC, -                                       */
   int64_t kl_off;                    /* double [world]: per-rank KL partial                                            */
   int64_t flags_off;                 /* uint32 [8 + world]: epoch, status, -, ..., then one arrival flag per rank      */

@@ -30,6 +30,12 @@ using tc::pack_bf16x2;
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// 16-byte store through the NVLS multicast mapping: the switch replicates it into every rank's arena
+__device__ __forceinline__ void multimem_st16(void* mc_addr, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -255,7 +261,11 @@ __global__ void __launch_bounds__(256, 2) shard_adam_kernel(const pl_shard_ctx c
         w[t] = adam_update(w[t], grad, m[t], v[t], h);
       }
       store8(P, M, V, nval, w, m, v);
-      if (sg.gather == 0) {        // fp32 all-gather: the updated values into every other rank's parameter area
+      if (sg.gather == 0 && c.mc_base && nval == 8 && world > 1) {
+        uint8_t* R = (uint8_t*)c.mc_base + sg.p_off + f0 * 4;
+        multimem_st16(R, make_uint4(__float_as_uint(w[0]), __float_as_uint(w[1]), __float_as_uint(w[2]), __float_as_uint(w[3])));
+        multimem_st16(R + 16, make_uint4(__float_as_uint(w[4]), __float_as_uint(w[5]), __float_as_uint(w[6]), __float_as_uint(w[7])));
+      } else if (sg.gather == 0) {        // fp32 all-gather: the updated values into every other rank's parameter area
         for (int q = 0; q < world; ++q) {
           if (q == rank) continue;
           float* R = (float*)((uint8_t*)c.peers[q] + sg.p_off) + f0;
@@ -295,7 +305,11 @@ __global__ void __launch_bounds__(256, 2) shard_adam_kernel(const pl_shard_ctx c
       }
       store8(P, M, V, nval, w, m, v);
     }
-    if (sg.gather == 0) {
+    if (sg.gather == 0 && c.mc_base && nval == 8 && world > 1) {
+      uint8_t* R = (uint8_t*)c.mc_base + sg.p2_off + f0 * 4;
+      multimem_st16(R, make_uint4(__float_as_uint(w[0]), __float_as_uint(w[1]), __float_as_uint(w[2]), __float_as_uint(w[3])));
+      multimem_st16(R + 16, make_uint4(__float_as_uint(w[4]), __float_as_uint(w[5]), __float_as_uint(w[6]), __float_as_uint(w[7])));
+    } else if (sg.gather == 0) {
       for (int q = 0; q < world; ++q) {
         if (q == rank) continue;
         float* R = (float*)((uint8_t*)c.peers[q] + sg.p2_off) + f0;
@@ -315,6 +329,16 @@ __global__ void __launch_bounds__(256, 2) shard_adam_kernel(const pl_shard_ctx c
       const uint4 s16 = make_uint4(pack_bf16x2(sg8[0], sg8[1]), pack_bf16x2(sg8[2], sg8[3]), pack_bf16x2(sg8[4], sg8[5]),
                                    pack_bf16x2(sg8[6], sg8[7]));
       const int64_t grp = f0 >> 3;
+      if (c.mc_base && world > 1) {       // one multicast store per 16 bytes: the NVSwitch fans it out to all arenas
+        uint8_t* L = (uint8_t*)c.mc_base + sg.lp_off;
+        if (sg.gather == 1) {
+          multimem_st16(L + grp * 16, mu16);
+          multimem_st16(L + sg.lp_half + grp * 16, s16);
+        } else {
+          multimem_st16(L + grp * 32, mu16);
+          multimem_st16(L + grp * 32 + 16, s16);
+        }
+      } else
       for (int q = 0; q < world; ++q) {
         uint8_t* L = (uint8_t*)c.peers[q] + sg.lp_off;
         if (sg.gather == 1) {

@@ -37,7 +37,7 @@ class ShardSeg(C.Structure):
 
 class ShardCtx(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("num_segs", C.c_int32), ("wire_bf16", C.c_int32),
-                ("peers", C.c_void_p * MAX_RANKS), ("segs", C.c_void_p),
+                ("peers", C.c_void_p * MAX_RANKS), ("segs", C.c_void_p), ("mc_base", C.c_void_p),
                 ("stats_off", C.c_int64), ("kl_off", C.c_int64), ("flags_off", C.c_int64),
                 ("push_units", C.c_int64), ("adam_units", C.c_int64),
                 ("push_prefix", C.c_int64 * (2 * MAX_SEGS + 1)), ("adam_prefix", C.c_int64 * (MAX_SEGS + 1))]
@@ -183,7 +183,7 @@ def emulate_step(plan: ShardPlan, params, grads_per_rank, m, v, lr, betas, eps, 
 class PeerShard:
     """Arena + peer mappings + C context of one rank.  ``params``: the trainer's parameters in flat-gradient order."""
 
-    def __init__(self, plan: ShardPlan, params, group=None, wire_bf16=False):
+    def __init__(self, plan: ShardPlan, params, group=None, wire_bf16=False, use_symmetric_memory=True):
         self.plan = plan
         self.wire_bf16 = bool(wire_bf16) and plan.world > 1
         self.group = group
@@ -194,8 +194,29 @@ class PeerShard:
         self.lib = _cabi.lib()
         dev = params[0].device
         self.device = dev
+        self.transport = "local"
+        self._symm = None
         with torch.cuda.device(dev):
-            self.arena = torch.zeros(plan.arena_bytes, dtype=torch.uint8, device=dev)
+            self.arena = None
+            import os
+            if multi and use_symmetric_memory and os.environ.get("PL_SHARD_NO_SYMM", "0") != "1":
+                # torch's symmetric memory: peer mappings + (on NVSwitch systems) an NVLS multicast mapping of the arenas
+                try:
+                    import torch.distributed._symmetric_memory as symm
+                    arena = symm.empty(plan.arena_bytes, dtype=torch.uint8, device=dev)
+                    arena.zero_()
+                    torch.cuda.synchronize(dev)
+                    name = (group or dist.group.WORLD).group_name
+                    self._symm = symm.rendezvous(arena, name)
+                    self.arena = arena
+                    self.transport = "symmetric_memory" + ("+multicast" if self._symm.multicast_ptr else "")
+                except Exception as e:      # older driver / no fabric support: CUDA IPC below
+                    self._symm = None
+                    self.symm_fallback_reason = f"{type(e).__name__}: {e}"[:200]
+            if self.arena is None:
+                self.arena = torch.zeros(plan.arena_bytes, dtype=torch.uint8, device=dev)
+                if multi:
+                    self.transport = "cuda_ipc"
             # parameters move into the arena's fp32 area (same values): the owners' optimiser pass writes the updated
             # small tensors straight into every rank's copy
             for p, off in zip(params, plan.param_offs):
@@ -206,7 +227,11 @@ class PeerShard:
             self._opened = []
             peers = []
             everyone = [None]
-            if multi:
+            if multi and self._symm is not None:
+                everyone = []
+                peers = [int(p) for p in self._symm.buffer_ptrs]
+                assert peers[self.rank] == self.arena.data_ptr()
+            elif multi:
                 handle = (C.c_uint8 * 64)()
                 offset = C.c_int64(0)
                 _cabi.check(self.lib.pl_ipc_export(C.c_void_p(self.arena.data_ptr()), handle, C.byref(offset)),
@@ -237,6 +262,7 @@ class PeerShard:
             for r, ptr in enumerate(peers):
                 ctx.peers[r] = ptr
             ctx.segs = self.segs_dev.data_ptr()
+            ctx.mc_base = int(self._symm.multicast_ptr) if (self._symm is not None and self._symm.multicast_ptr) else None
             ctx.stats_off, ctx.kl_off, ctx.flags_off = plan.stats_off, plan.kl_off, plan.flags_off
             pp, ap = plan.push_prefix(), plan.adam_prefix(self.rank)
             for i, vv in enumerate(pp):

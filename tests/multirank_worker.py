@@ -67,7 +67,7 @@ def main():
     if rank == 0:
         flat = torch.cat([p.detach().flatten() for p in net.parameters()]).cpu().numpy()
         np.savez(args.out, stats=np.array([s if s is not None else [np.nan] * 4 for s in stats], np.float64), params=flat,
-                 exchange=str(tr.exchange), status=status,
+                 exchange=str(tr.exchange), status=status, transport=str(getattr(tr.shard, "transport", "")),
                  fallback=str(getattr(tr, "exchange_fallback_reason", "")))
     if world > 1:
         dist.barrier()

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "multirank_worker.py")
 
 
-def _run(n, out, *extra, port=29731):
+def _run(n, out, *extra, port=29731, env_extra=None):
     if n == 1:
         cmd = [sys.executable, WORKER, "--out", out, *extra]
     else:
@@ -23,6 +23,7 @@ def _run(n, out, *extra, port=29731):
     env = dict(os.environ)
     env.pop("RANK", None)
     env.pop("WORLD_SIZE", None)
+    env.update(env_extra or {})
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
     return np.load(out + ".npz" if not out.endswith(".npz") else out)
@@ -36,12 +37,17 @@ def single(tmp_path_factory):
     return _run(1, str(d / "n1.npz")), d
 
 
-@pytest.mark.parametrize("exchange,graph", [("peer", 0), ("peer", 1), ("nccl", 0)])
-def test_two_ranks_follow_the_single_gpu_trajectory(single, exchange, graph):
+@pytest.mark.parametrize("exchange,graph,ipc", [("peer", 0, 0), ("peer", 1, 0), ("peer", 0, 1), ("nccl", 0, 0)])
+def test_two_ranks_follow_the_single_gpu_trajectory(single, exchange, graph, ipc):
+    """peer: arenas in torch symmetric memory (all-gather through the NVLS multicast mapping where the fabric offers one) or,
+    ipc=1, plain CUDA-IPC peer mappings (one store per peer)."""
     ref, d = single
-    got = _run(2, str(d / f"n2_{exchange}_{graph}.npz"), "--exchange", exchange, "--graph", str(graph),
-               port=29731 + 7 * graph + (3 if exchange == "nccl" else 0))
+    got = _run(2, str(d / f"n2_{exchange}_{graph}_{ipc}.npz"), "--exchange", exchange, "--graph", str(graph),
+               port=29731 + 7 * graph + (3 if exchange == "nccl" else 0) + 11 * ipc,
+               env_extra={"PL_SHARD_NO_SYMM": "1"} if ipc else None)
     assert str(got["exchange"]) == exchange and int(got["status"]) == 0, (got["exchange"], got["fallback"])
+    if exchange == "peer":
+        assert str(got["transport"]).startswith("cuda_ipc" if ipc else "symmetric_memory"), got["transport"]
     s1, s2 = ref["stats"], got["stats"]
     for t in range(len(s1)):
         if np.isnan(s2[t]).any():

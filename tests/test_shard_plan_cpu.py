@@ -62,7 +62,7 @@ def test_struct_mirrors_match_the_header():
     from pytorch_probabilisticlayers_b200 import _cabi
     lib = _cabi.lib()
     assert C.sizeof(S.ShardSeg) == 16 + 9 * 8
-    assert C.sizeof(S.ShardCtx) == 16 + 8 * 8 + 8 + 5 * 8 + (2 * 48 + 1) * 8 + (48 + 1) * 8
+    assert C.sizeof(S.ShardCtx) == 16 + 8 * 8 + 16 + 5 * 8 + (2 * 48 + 1) * 8 + (48 + 1) * 8
     for which, mirror in enumerate((_cabi.LinearArgs, _cabi.Conv2dArgs, _cabi.CeArgs, _cabi.BnPoolArgs, S.ShardSeg, S.ShardCtx)):
         assert lib.pl_struct_size(which) == C.sizeof(mirror), (which, mirror.__name__)
 
