@@ -480,6 +480,33 @@ def run_b200(args, wl):
                 "note": "report-only: per-GPU MC fixed at the config's MC, total MC grows with N"}
         net = net_w            # same layer shapes: the KL micro-benchmark below only needs the parameters
 
+    # ---- N > 1, peer exchange: the same step with the OTHER gradient wire format, for the record ----
+    other_wire = None
+    if world > 1 and exchange == "peer" and not wl.get("conv"):
+        try:
+            ow = "fp32" if args.grad_wire == "bf16" else "bf16"
+            torch.manual_seed(1234)
+            net_o = build_net(plb, wl, mc_local, dev, args.precision, args.fuse, world)
+            GRAD_WIRE[0] = ow
+            trainer_o = make_trainer(plb, wl, net_o)
+            GRAD_WIRE[0] = args.grad_wire
+            assert trainer_o.set_shard(mc_total) == mc_local
+
+            def step_other():
+                return trainer_o.step(x_dev, y_dev)
+            for _ in range(3):
+                step_other()
+            if use_graph:
+                trainer_o.enable_cuda_graph(x_dev, y_dev)
+            ms_o = timed(step_other, args.steps) / args.steps
+            other_wire = {"grad_wire": ow, "ms_per_step": ms_o, "value": mc_total * batch / (ms_o * 1e-3), "unit": UNIT}
+            torch.cuda.synchronize()
+            dist.barrier()
+            trainer_o.shard.close()
+            del trainer_o, net_o
+        except Exception as e:
+            other_wire = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -677,6 +704,7 @@ def run_b200(args, wl):
         "gpu_eager_reference": eager_ref,
         "cpu_baseline": cpu,
         "weak_scaling": weak,
+        "other_wire": other_wire,
         "final_stats": {"LL": final_stats[0], "KL": final_stats[1], "ACC": final_stats[2],
                         "loss": final_stats[3]},
     }
@@ -701,8 +729,11 @@ def main():
     ap.add_argument("--no-side-legs", action="store_true",
                     help="skip the secondary legs (tf32 / bf16_fast / gpu_eager_reference / cpu_baseline)")
     ap.add_argument("--no-weak", action="store_true", help="N>1: skip the report-only weak-scaling leg")
-    ap.add_argument("--grad-wire", choices=["fp32", "bf16"], default="fp32",
-                    help="N>1, peer exchange: format of the partial gradients on the wire (bf16 halves the reduce-scatter bytes)")
+    ap.add_argument("--grad-wire", choices=["auto", "fp32", "bf16"], default="auto",
+                    help="N>1, peer exchange: format of the partial gradients on the wire.  bf16 halves the reduce-scatter "
+                         "bytes (every partial rounded once to bf16, summed in fp32 by the owner; gated by "
+                         "tests/test_gpu_multirank.py); auto = bf16 when the layers compute with bf16 operands, else fp32.  "
+                         "The line also carries the other format's timing (`other_wire`).")
     ap.add_argument("--cuda-graph", dest="cuda_graph", action="store_true", default=None,
                     help="replay the whole step from a CUDA graph (default for the launch-bound c1 / c5)")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
@@ -710,6 +741,8 @@ def main():
                     help="run BayesLinear / LeakyReLU module by module instead of as a fused chain")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
+    if args.grad_wire == "auto":
+        args.grad_wire = "bf16" if DTYPES[args.precision] == "bf16" else "fp32"
     GRAD_WIRE[0] = args.grad_wire
     if args.mc:
         wl["mc"] = args.mc
