@@ -43,9 +43,14 @@ struct TcScratch {
   TcState st;
   float* bias;
   float* colsum;
+  float* mean_mat;            // [B, O] fp32: X.round(mu) of an MC-broadcast input (split modes, forward)
   __nv_bfloat16* dy_bf16;
   size_t total;
 };
+// the MC-shared mean part is hoisted out of the per-sample launches when the input has no MC axis
+static inline bool hoist_mean(const pl_linear_args* a) {
+  return prec_split(a->precision) && a->x_mc_stride == 0 && a->mc >= 4 && !a->eps_w;
+}
 
 static TcState carve_state(const pl_linear_args* a, void* base) {
   const size_t I = a->in_features, O = a->out_features, MC = a->mc, B = a->batch;
@@ -79,6 +84,8 @@ static TcScratch carve_scratch(const pl_linear_args* a, void* base, bool with_st
   }
   w.bias = (float*)(b + off); off += align256(MC * O * 4);
   w.colsum = (float*)(b + off); off += align256(MC * O * 4);
+  w.mean_mat = (float*)(b + off);
+  if (!backward && hoist_mean(a)) off += align256(B * O * 4);
   w.dy_bf16 = (__nv_bfloat16*)(b + off);
   if (backward) off += align256(MC * B * O * 2);
   w.total = off + 256;
@@ -208,6 +215,15 @@ int linear_fwd_tc_launch(const pl_linear_args* a) {
   p.out_lp = (__nv_bfloat16*)a->y_lp;
   p.act = a->y_act;
   p.act_slope = a->y_act_slope;
+  if (hoist_mean(a)) {
+    // X.round(mu) once (one "sample", no bias / activation), then the per-sample launches add it in their epilogue
+    TcGemmParams pm = p;
+    pm.mc = 1; pm.bias = nullptr; pm.out = w.mean_mat; pm.out_lp = nullptr; pm.act = 0; pm.mean_only = 1;
+    rc = dispatch_gemm<false>(tm, pm, st, state.mean, I, O, O, false, tf32, true);
+    if (rc != PL_OK) return rc;
+    p.noise_only = 1;
+    p.mean_mat = w.mean_mat;
+  }
   return dispatch_gemm<false>(tm, p, st, state.mean, I, O, O, a->eps_w != nullptr, tf32, split);
 }
 

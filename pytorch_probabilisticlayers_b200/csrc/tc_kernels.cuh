@@ -42,6 +42,12 @@ struct TcGemmParams {
   float act_slope;
   const __nv_bfloat16* mask_src;  // dX: multiply by act'(x): x > 0 ? 1 : mask_slope, x = mask_src[row][col]
   float mask_slope;
+  // split kernels, MC-broadcast input (layer 1 of the reference's nets): X.round(mu) is the same for every MC sample, so
+  // it is computed ONCE (mean_only launch, mc = 1) and the per-sample launches add it in the epilogue instead of
+  // re-running the mean MMA for all MC samples (noise_only + mean_mat)
+  int mean_only;                // generators idle, only the mean MMA: out = X.round(mu)
+  int noise_only;               // mean tile neither loaded nor multiplied
+  const float* mean_mat;        // [rows, ndim] fp32 added to every sample's result (row-major epilogue only)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -574,7 +580,12 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (lane == 0) {
       const int row0 = (int)(mc * p.a_mc_rows) + m0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        if (kSplit) {
+        if (kSplit && p.noise_only) {
+          // no mean tile: only this producer's arrival on the stage's full barrier
+          const int sb = kb % Cfg::kStagesB, pb = (kb / Cfg::kStagesB) & 1;
+          mbar_wait(b_empty(sb), pb ^ 1);
+          mbar_arrive(b_full(sb));
+        } else if (kSplit) {
           // mean tile of this k-block into the second half of B stage sb (freed by the same commit as the noise half)
           const int sb = kb % Cfg::kStagesB, pb = (kb / Cfg::kStagesB) & 1;
           mbar_wait(b_empty(sb), pb ^ 1);
@@ -625,18 +636,21 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                        : (kTf32 ? smem_desc_sw128_base32(base + ks * 1024, 4096, 512)
                                 : smem_desc_sw128(base + ks * 2048, 8192, 1024));
           };
-          const uint64_t b_desc = b_desc_at(b_addr);
+          const bool do_noise = !(kSplit && p.mean_only), do_mean = kSplit && !p.noise_only;
+          if (do_noise) {
+            const uint64_t b_desc = b_desc_at(b_addr);
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint64_t a_desc = smem_desc_sw128(a_addr + mt * kSubTileBytes + ks * 32, 16, 1024);
-            mma_ss<kTf32>(tmem_base + mt * kBN, a_desc, b_desc, idesc, (kb | ks) != 0);
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t a_desc = smem_desc_sw128(a_addr + mt * kSubTileBytes + ks * 32, 16, 1024);
+              mma_ss<kTf32>(tmem_base + mt * kBN, a_desc, b_desc, idesc, (kb | ks) != 0);
+            }
           }
-          if (kSplit) {   // the mean tile (same layout, second half of the stage) into the same accumulators
+          if (do_mean) {   // the mean tile (same layout, second half of the stage) into the same accumulators
             const uint64_t m_desc = b_desc_at(b_addr + kSubTileBytes);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
               const uint64_t a_desc = smem_desc_sw128(a_addr + mt * kSubTileBytes + ks * 32, 16, 1024);
-              mma_ss<kTf32>(tmem_base + mt * kBN, a_desc, m_desc, idesc, 1u);
+              mma_ss<kTf32>(tmem_base + mt * kBN, a_desc, m_desc, idesc, do_noise ? 1u : (uint32_t)((kb | ks) != 0));
             }
           }
         }
@@ -662,6 +676,15 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       else gen.template load<false>(p, mc, kb * kBKe);
 #endif
     };
+    if (kSplit && p.mean_only) {
+      // nothing to synthesise: keep the stage hand-shake alive (the MMA thread only multiplies the TMA-loaded mean tiles)
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::kStagesB, ph = (kb / Cfg::kStagesB) & 1;
+        mbar_wait(b_empty(s), ph ^ 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_full(s));
+      }
+    } else {
     gen.words(p, sw, mc, 0);
     load_block(0);
     for (int kb = 0; kb < num_kb; ++kb) {
@@ -688,6 +711,7 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(b_full((num_kb - 1) % Cfg::kStagesB));
+    }
     // ===================== epilogue: TMEM -> registers -> HBM =====================
     const int q = warp & 3;        // TMEM lane quadrant this warp may access
     const int col = (gw >> 2) * 32;  // which 32-column quarter of the tile
@@ -720,6 +744,12 @@ sampled_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               float w[8];
 #pragma unroll
               for (int t = 0; t < 8; ++t) w[t] = __uint_as_float(v[j + t]) + bias_s[col + j + t];
+              if (p.mean_mat) {   // the MC-shared mean part X.round(mu), computed once
+                const float4* mm = reinterpret_cast<const float4*>(p.mean_mat + (int64_t)row * p.ndim + n0 + col + j);
+                const float4 m0 = __ldg(mm), m1 = __ldg(mm + 1);
+                w[0] += m0.x; w[1] += m0.y; w[2] += m0.z; w[3] += m0.w;
+                w[4] += m1.x; w[5] += m1.y; w[6] += m1.z; w[7] += m1.w;
+              }
               if (p.act) {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) w[t] = w[t] > 0.f ? w[t] : p.act_slope * w[t];
@@ -1362,7 +1392,7 @@ static int launch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_
   // the 1-CTA kernels for both operand forms (r02 C4: 11.50 vs 11.59 ms/step, and slower on the 1000-wide layer): the
   // fused kernels run at the board's power cap, where time follows the executed work, not its schedule.  Opt-in
   // (PL_TC_2CTA=1), parity-tested.
-  const bool pair = g_tc_pairs == 1;
+  const bool pair = g_tc_pairs == 1 && !p.mean_only && !p.noise_only;   // the hoisted-mean launches exist in the 1-CTA kernel only
   if (!kTf32 && pair && p.rows > 128 && p.ndim > 128 && (p.out_hw == 0 || (p.out && !p.out_lp))) {
     const int pair_rows = p.rows > 256 ? 512 : 256;
     dim3 grid(2u * (unsigned)((p.ndim + 255) / 256), (unsigned)((p.rows + pair_rows - 1) / pair_rows),
