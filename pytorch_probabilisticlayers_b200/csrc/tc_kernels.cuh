@@ -1410,7 +1410,8 @@ static int launch_gemm(const CUtensorMap& tm, const TcGemmParams& p, cudaStream_
     PL_LAUNCH_CHECK("sampled_gemm_tc2");
     return PL_OK;
   }
-  const int mt_rows = p.rows > 256 ? 512 : (p.rows > 128 ? 256 : 128);
+  // the hoisted mean launch has a single "sample": 128-row tiles give it 4x the CTAs (it is latency bound per CTA)
+  const int mt_rows = p.mean_only ? 128 : (p.rows > 256 ? 512 : (p.rows > 128 ? 256 : 128));
   dim3 grid((unsigned)((p.ndim + kBN - 1) / kBN), (unsigned)((p.rows + mt_rows - 1) / mt_rows),
             (unsigned)p.mc);
   const CUtensorMap& tmb = tm_b ? *tm_b : tm;

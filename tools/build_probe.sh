@@ -6,7 +6,7 @@ set -e
 cd "$(dirname "$0")/../pytorch_probabilisticlayers_b200/csrc"
 name=$1; shift
 out=../lib/probe_$name; mkdir -p $out ../build/probe_$name
-for f in api adam bn_pool ce kl linear linear_simt linear_tc conv_simt conv_tc; do
+for f in api adam bn_pool ce comm kl linear linear_simt linear_tc conv_simt conv_tc; do
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
     --expt-relaxed-constexpr "$@" -c $f.cu -o ../build/probe_$name/$f.o &
 done
