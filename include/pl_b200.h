@@ -333,7 +333,7 @@ typedef struct pl_shard_ctx {
                                         instead of once per peer; NULL = one store per peer                             */
   int64_t stats_off;                 /* float [world][4]: per-rank LL, -, ACC, -                                       */
   int64_t kl_off;                    /* double [world]: per-rank KL partial                                            */
-  int64_t flags_off;                 /* uint32 [8 + world]: epoch, status, -, ..., then one arrival flag per rank      */
+  int64_t flags_off;                 /* 4 channels x uint32 [16]: epoch, status, -, ..., then one arrival flag per rank  */
   int64_t push_units, adam_units;    /* totals of the two prefix arrays                                                */
   int64_t push_prefix[2 * PL_SHARD_MAX_SEGS + 1]; /* 8-element units of every tensor (2 slots per segment)            */
   int64_t adam_prefix[PL_SHARD_MAX_SEGS + 1];     /* 8-element units of THIS rank's chunk of every segment            */
@@ -350,10 +350,16 @@ int pl_shard_push(const pl_shard_ctx* c, const float* grads, const float* stats4
  * can run on a side stream under the backward of the layers before it); stats4 may be NULL. */
 int pl_shard_push_range(const pl_shard_ctx* c, const float* grads, const float* stats4, int64_t unit_begin,
                         int64_t unit_end, void* stream);
-int pl_shard_barrier(const pl_shard_ctx* c, void* stream);
+/* channel 0..3: independent flag sets, one per stream that issues barriers (their epochs must not interleave). */
+int pl_shard_barrier(const pl_shard_ctx* c, int32_t channel, void* stream);
 /* sched_dev (optional, device): [lr/(1-beta1^t), 1/sqrt(1-beta2^t)] for CUDA-graph replays, else `step` (1-based). */
 int pl_shard_adam(const pl_shard_ctx* c, float* m, float* v, float kl_scale, float lr, float beta1, float beta2, float eps,
                   int32_t step, const float* sched_dev, double* kl_value, void* stream);
+/* The same for segments [seg_begin, seg_end) only: a layer's optimiser pass + operand gather can then run on a side
+ * stream (after its own push + barrier) under the backward of the layers before it.  kl_value accumulates. */
+int pl_shard_adam_range(const pl_shard_ctx* c, int32_t seg_begin, int32_t seg_end, float* m, float* v, float kl_scale,
+                        float lr, float beta1, float beta2, float eps, int32_t step, const float* sched_dev,
+                        double* kl_value, void* stream);
 int pl_shard_finish(const pl_shard_ctx* c, const double* kl_acc, double kl_const, double inv_num_samples,
                     float* stats_out4, void* stream);
 

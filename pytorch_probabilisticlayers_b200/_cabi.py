@@ -32,7 +32,7 @@ EXPORTS = (
     "pl_linear_workspace_bytes", "pl_linear_state_bytes", "pl_linear_fwd", "pl_linear_bwd",
     "pl_conv2d_workspace_bytes", "pl_conv2d_state_bytes", "pl_conv2d_fwd", "pl_conv2d_bwd",
     "pl_ipc_export", "pl_ipc_open", "pl_ipc_close",
-    "pl_shard_push", "pl_shard_push_range", "pl_shard_barrier", "pl_shard_adam", "pl_shard_finish",
+    "pl_shard_push", "pl_shard_push_range", "pl_shard_barrier", "pl_shard_adam", "pl_shard_adam_range", "pl_shard_finish",
 )
 
 
@@ -160,14 +160,16 @@ def lib():
                     getattr(l, name).restype = C.c_int
                     getattr(l, name).argtypes = [C.POINTER(Conv2dArgs)]
                 for name in ("pl_ipc_export", "pl_ipc_open", "pl_ipc_close", "pl_shard_push", "pl_shard_push_range", "pl_shard_barrier",
-                             "pl_shard_adam", "pl_shard_finish"):
+                             "pl_shard_adam", "pl_shard_adam_range", "pl_shard_finish"):
                     getattr(l, name).restype = C.c_int
                 l.pl_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
                 l.pl_ipc_open.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
                 l.pl_ipc_close.argtypes = [C.c_void_p, C.c_int64]
                 l.pl_shard_push.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
                 l.pl_shard_push_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
-                l.pl_shard_barrier.argtypes = [C.c_void_p, C.c_void_p]
+                l.pl_shard_barrier.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+                l.pl_shard_adam_range.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                                  C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
                 l.pl_shard_adam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
                                             C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
                 l.pl_shard_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]

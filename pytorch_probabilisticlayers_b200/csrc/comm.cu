@@ -44,21 +44,23 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 
 // One cross-GPU barrier, executed by the first `world` threads of ONE block.  epoch = ++(*epoch_dev) (thread 0).
 // Never hangs: after ~4 s of spinning it raises status[0] and proceeds (the caller checks the status word).
-__device__ void grid_barrier_block(const pl_shard_ctx& c, uint32_t* s_epoch) {
+// `channel` (0..3) selects an independent set of flags: barriers issued on different streams must not share an epoch counter.
+__device__ void grid_barrier_block(const pl_shard_ctx& c, uint32_t* s_epoch, int channel = 0) {
   uint8_t* base = (uint8_t*)c.peers[c.rank];
-  uint32_t* epoch_dev = (uint32_t*)(base + c.flags_off);          // [0] epoch, [1] status, [8 + q] flag of rank q
+  const int64_t foff = c.flags_off + 64 * channel;
+  uint32_t* epoch_dev = (uint32_t*)(base + foff);                 // [0] epoch, [1] status, [8 + q] flag of rank q
   if (threadIdx.x == 0) *s_epoch = ++(*epoch_dev);
   __syncthreads();
   const uint32_t e = *s_epoch;
   if ((int)threadIdx.x < c.world) {
     __threadfence_system();       // everything this GPU wrote before (this and earlier kernels) is ordered before the flag
-    uint32_t* remote = (uint32_t*)((uint8_t*)c.peers[threadIdx.x] + c.flags_off) + 8 + c.rank;
+    uint32_t* remote = (uint32_t*)((uint8_t*)c.peers[threadIdx.x] + foff) + 8 + c.rank;
     st_release_sys(remote, e);
     const uint32_t* mine = epoch_dev + 8 + threadIdx.x;
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
       if (clock64() - t0 > (1ll << 33)) {
-        epoch_dev[1] = 1u;        // timeout: a peer never arrived
+        ((uint32_t*)(base + c.flags_off))[1] = 1u;        // timeout: a peer never arrived (status word of channel 0)
         break;
       }
       __nanosleep(64);
@@ -68,9 +70,9 @@ __device__ void grid_barrier_block(const pl_shard_ctx& c, uint32_t* s_epoch) {
   __syncthreads();
 }
 
-__global__ void shard_barrier_kernel(const pl_shard_ctx c) {
+__global__ void shard_barrier_kernel(const pl_shard_ctx c, int channel) {
   __shared__ uint32_t s_epoch;
-  grid_barrier_block(c, &s_epoch);
+  grid_barrier_block(c, &s_epoch, channel);
 }
 
 // ---- push: local gradients -> owners' staging --------------------------------------------------------------------
@@ -220,14 +222,14 @@ __device__ __forceinline__ void staged_sum8(const uint8_t* stage, int64_t chunk,
 // unit = 8 consecutive elements of this rank's chunk of one segment (both tensors of a pair); adam_prefix[s] = first unit
 __global__ void __launch_bounds__(256, 2) shard_adam_kernel(const pl_shard_ctx c, float* __restrict__ mstate,
                                                          float* __restrict__ vstate, AdamHyper h,
-                                                         double* __restrict__ kl_out) {
+                                                         double* __restrict__ kl_out, int64_t unit_begin, int64_t unit_end) {
   if (h.sched_dev) {
     h.step_size = __ldg(h.sched_dev);
     h.inv_sqrt_bc2 = __ldg(h.sched_dev + 1);
   }
   uint8_t* base = (uint8_t*)c.peers[c.rank];
   const int world = c.world, rank = c.rank;
-  const int64_t total = c.adam_units;
+  const int64_t total = unit_end;
   // the segment table is read once per 8 elements: keep it in shared memory
   __shared__ pl_shard_seg s_segs[PL_SHARD_MAX_SEGS];
   for (int i = threadIdx.x; i < c.num_segs * (int)(sizeof(pl_shard_seg) / 8); i += 256)
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(256, 2) shard_adam_kernel(const pl_shard_ctx c
   __syncthreads();
   float kl = 0.f;
   int si = 0;
-  for (int64_t u = (int64_t)blockIdx.x * 256 + threadIdx.x; u < total; u += (int64_t)gridDim.x * 256) {
+  for (int64_t u = unit_begin + (int64_t)blockIdx.x * 256 + threadIdx.x; u < total; u += (int64_t)gridDim.x * 256) {
     while (u >= c.adam_prefix[si + 1]) ++si;
     const pl_shard_seg& sg = s_segs[si];
     const int64_t j = (u - c.adam_prefix[si]) * 8;            // offset inside this rank's chunk
@@ -472,23 +474,36 @@ extern "C" int pl_shard_push(const pl_shard_ctx* c, const float* grads, const fl
   return pl_shard_push_range(c, grads, stats4, 0, c->push_units, stream);
 }
 
-extern "C" int pl_shard_barrier(const pl_shard_ctx* c, void* stream) {
+extern "C" int pl_shard_barrier(const pl_shard_ctx* c, int32_t channel, void* stream) {
   using namespace pl;
   int rc = check_ctx(c, "pl_shard_barrier");
   if (rc != PL_OK) return rc;
-  shard_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*c);
+  PL_CHECK_ARG(channel >= 0 && channel < 4, "pl_shard_barrier: channel must be 0..3");
+  shard_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*c, channel);
   PL_LAUNCH_CHECK("shard_barrier_kernel");
   return PL_OK;
 }
 
 extern "C" int pl_shard_adam(const pl_shard_ctx* c, float* m, float* v, float kl_scale, float lr, float beta1, float beta2,
                              float eps, int32_t step, const float* sched_dev, double* kl_value, void* stream) {
+  if (!c) {
+    pl::set_error("pl_shard_adam: NULL context");
+    return PL_ERR_BAD_ARG;
+  }
+  return pl_shard_adam_range(c, 0, c->num_segs, m, v, kl_scale, lr, beta1, beta2, eps, step, sched_dev, kl_value, stream);
+}
+
+extern "C" int pl_shard_adam_range(const pl_shard_ctx* c, int32_t seg_begin, int32_t seg_end, float* m, float* v,
+                                   float kl_scale, float lr, float beta1, float beta2, float eps, int32_t step,
+                                   const float* sched_dev, double* kl_value, void* stream) {
   using namespace pl;
   int rc = check_ctx(c, "pl_shard_adam");
   if (rc != PL_OK) return rc;
   PL_CHECK_ARG(m && v, "pl_shard_adam: NULL optimiser state");
   PL_CHECK_ARG(sched_dev || step >= 1, "pl_shard_adam: step must be >= 1");
-  if (c->adam_units == 0) return PL_OK;
+  PL_CHECK_ARG(seg_begin >= 0 && seg_begin <= seg_end && seg_end <= c->num_segs, "pl_shard_adam: bad segment range");
+  const int64_t u0 = c->adam_prefix[seg_begin], u1 = c->adam_prefix[seg_end];
+  if (u1 == u0) return PL_OK;
   AdamHyper h;
   if (sched_dev) step = 1;
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
@@ -497,9 +512,9 @@ extern "C" int pl_shard_adam(const pl_shard_ctx* c, float* m, float* v, float kl
   h.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   h.beta1 = beta1; h.beta2 = beta2; h.eps = eps;
   h.sched_dev = sched_dev;
-  int64_t blocks = ceil_div64(c->adam_units, 256);
+  int64_t blocks = ceil_div64(u1 - u0, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  shard_adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(*c, m, v, h, kl_value);
+  shard_adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(*c, m, v, h, kl_value, u0, u1);
   PL_LAUNCH_CHECK("shard_adam_kernel");
   return PL_OK;
 }

@@ -120,7 +120,7 @@ class ShardPlan:
         self.kl_off = off
         off += _align(self.world * 8)
         self.flags_off = off
-        off += _align((8 + self.world) * 4)
+        off += _align(4 * 64)               # 4 barrier channels x 16 words
         self.arena_bytes = off
 
     # 8-element units ------------------------------------------------------------------------------------------
@@ -303,15 +303,21 @@ class PeerShard:
         pp = self.plan.push_prefix()
         return pp[2 * seg_index], pp[2 * seg_index + 2]
 
-    def barrier(self):
+    def barrier(self, channel=0):
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.pl_shard_barrier(C.byref(self.ctx), C.c_void_p(self._stream())), "pl_shard_barrier")
+            _cabi.check(self.lib.pl_shard_barrier(C.byref(self.ctx), C.c_int32(channel), C.c_void_p(self._stream())),
+                        "pl_shard_barrier")
 
-    def adam(self, kl_scale, lr, betas, eps, step, sched_dev=None, with_kl=True):
+    def adam(self, kl_scale, lr, betas, eps, step, sched_dev=None, with_kl=True, segs=None, zero_kl=True):
+        """Optimiser pass + gather over the segments ``segs`` = (begin, end) (default: all).  ``zero_kl``: clear the KL
+        accumulator first (once per step when the pass is issued in several pieces)."""
+        s0, s1 = segs if segs is not None else (0, len(self.plan.segs))
         with torch.cuda.device(self.device):
-            self.kl_acc.zero_()
-            _cabi.check(self.lib.pl_shard_adam(
-                C.byref(self.ctx), C.c_void_p(self.m.data_ptr()), C.c_void_p(self.v.data_ptr()), C.c_float(kl_scale),
+            if zero_kl:
+                self.kl_acc.zero_()
+            _cabi.check(self.lib.pl_shard_adam_range(
+                C.byref(self.ctx), C.c_int32(s0), C.c_int32(s1), C.c_void_p(self.m.data_ptr()),
+                C.c_void_p(self.v.data_ptr()), C.c_float(kl_scale),
                 C.c_float(lr), C.c_float(betas[0]), C.c_float(betas[1]), C.c_float(eps), C.c_int32(step),
                 C.c_void_p(sched_dev.data_ptr() if sched_dev is not None else None),
                 C.c_void_p(self.kl_acc.data_ptr() if with_kl else None), C.c_void_p(self._stream())), "pl_shard_adam")

@@ -258,6 +258,8 @@ class ELBOTrainStep:
         # tcgen05 CTA per SM); only the first layer's transfer and the small tensors stay on the critical path
         self._side = torch.cuda.Stream(device=dev)
         self._pushed = []                  # unit ranges already handed to the side stream in this step
+        self._overlap_adam = True          # per-layer optimiser pass + gather on the side stream as well
+        self._adam_done = []
         for chain in self._fused_chains():
             for l in chain.layers:
                 k, s = by_index.get(index[id(l.weight.loc)], (None, None))
@@ -266,7 +268,7 @@ class ELBOTrainStep:
                     ptr, half = self.shard.lp_pointers(s)
                     sh.update(w_lp=ptr, w_lp_half=half, dw_rho_raw=1)
                 if s is not None and overlap_push:
-                    sh["after_bwd"] = self._make_push_hook(self.shard.seg_units(k))
+                    sh["after_bwd"] = self._make_push_hook(self.shard.seg_units(k), k)
                 l._shard = sh
         self._direct_grads()
         self.shard.initial_gather()
@@ -274,7 +276,11 @@ class ELBOTrainStep:
         if self.shard.status() != 0:
             raise RuntimeError("peer barrier timed out during set-up")
 
-    def _make_push_hook(self, units):
+    def _make_push_hook(self, units, seg_index):
+        """Side-stream work of one chained layer, issued right after its backward kernels: push its gradients to their
+        owners, barrier (channel 1), then the owners' optimiser pass + operand gather of THIS layer -- all under the
+        backward of the layers before it.  (Nobody reads this layer's operands again before the next forward, and every
+        rank has finished its backward of the layer when it has pushed.)"""
         def hook():
             main = torch.cuda.current_stream(self.flat.device)
             ev = torch.cuda.Event()
@@ -282,8 +288,26 @@ class ELBOTrainStep:
             self._side.wait_event(ev)
             with torch.cuda.stream(self._side):
                 self.shard.push(self.flat, None, units)
+                if self._overlap_adam:
+                    self.shard.barrier(1)
+                    self.shard.adam(1.0 / self.num_samples, self.lr, self.betas, self.eps, self.adam_t, self._sched_cur,
+                                    segs=(seg_index, seg_index + 1), zero_kl=False)
+                    self._adam_done.append(seg_index)
             self._pushed.append(units)
         return hook
+
+    def _begin_opt_step(self):
+        """Start-of-step state of the shard optimiser (the per-layer passes may run before the backward has finished)."""
+        self.adam_t += 1
+        self.shard.kl_acc.zero_()
+        self._sched_cur = None
+        self._adam_done = []
+        if self._capturing:
+            self._t_dev.add_(1.0)
+            bc1 = 1.0 - torch.pow(torch.full_like(self._t_dev, self.betas[0]), self._t_dev)
+            bc2 = 1.0 - torch.pow(torch.full_like(self._t_dev, self.betas[1]), self._t_dev)
+            self._sched.copy_(torch.cat([self.lr / bc1, torch.rsqrt(bc2)]).float())
+            self._sched_cur = self._sched
 
     def sync_full_params(self):
         """Peer exchange keeps the fp32 values of operand-gathered weights current on their owners only; this brings
@@ -382,6 +406,8 @@ class ELBOTrainStep:
 
     def _eager_step(self, x, y):
         self.flat.zero_()
+        if self.shard is not None:
+            self._begin_opt_step()
         pred = self.net(x)
         inv = 1.0 / (self.num_samples * self.world)
         # cross entropy on CUDA: value, accuracy and d(loss)/d(pred) from one pass over the logits (csrc/ce.cu)
@@ -445,17 +471,11 @@ class ELBOTrainStep:
     def _peer_finish(self):
         """Gradient reduce-scatter (peer stores), sharded Adam + KL, operand all-gather (peer stores): csrc/comm.cu."""
         sh = self.shard
-        self.adam_t += 1
-        sched = None
-        if self._capturing:
-            self._t_dev.add_(1.0)
-            bc1 = 1.0 - torch.pow(torch.full_like(self._t_dev, self.betas[0]), self._t_dev)
-            bc2 = 1.0 - torch.pow(torch.full_like(self._t_dev, self.betas[1]), self._t_dev)
-            self._sched.copy_(torch.cat([self.lr / bc1, torch.rsqrt(bc2)]).float())
-            sched = self._sched
+        sched = self._sched_cur
         if self.world == 1:
             # one multi-tensor launch: Adam + KL gradient + KL value over every parameter tensor
-            PF._timed("adam_kl_multi", lambda: sh.adam(1.0 / self.num_samples, self.lr, self.betas, self.eps, self.adam_t, sched),
+            PF._timed("adam_kl_multi", lambda: sh.adam(1.0 / self.num_samples, self.lr, self.betas, self.eps, self.adam_t, sched,
+                                                       zero_kl=False),
                       ("bytes", 28.0 * sh.plan.state_elems))
             self.stats[1] += ((sh.kl_acc[0] + self.kl_const) / self.num_samples).float()
             out = self.stats.clone()
@@ -484,8 +504,23 @@ class ELBOTrainStep:
                 torch.cuda.current_stream(self.flat.device).wait_event(ev)
         PF._timed("shard_push", push_rest, ("bytes", 4.0 * (self.flat.numel() - 4)))
         PF._timed("shard_barrier", sh.barrier)
-        PF._timed("shard_adam", lambda: sh.adam(1.0 / self.num_samples, self.lr, self.betas, self.eps, self.adam_t, sched),
-                  ("bytes", 4.0 * (self.flat.numel() - 4) + 28.0 * sh.plan.state_elems))
+        # the segments whose optimiser pass did not already run on the side stream
+        done = set(self._adam_done)
+        todo, cur = [], None
+        for k in range(len(sh.plan.segs)):
+            if k in done:
+                if cur is not None:
+                    todo.append((cur, k))
+                    cur = None
+            elif cur is None:
+                cur = k
+        if cur is not None:
+            todo.append((cur, len(sh.plan.segs)))
+
+        def adam_rest():
+            for r in todo:
+                sh.adam(1.0 / self.num_samples, self.lr, self.betas, self.eps, self.adam_t, sched, segs=r, zero_kl=False)
+        PF._timed("shard_adam", adam_rest, ("bytes", 4.0 * (self.flat.numel() - 4) + 28.0 * sh.plan.state_elems))
         PF._timed("shard_finish", lambda: sh.finish(self.kl_const, 1.0 / self.num_samples, self.shard_out))
         return self.shard_out.clone()
 

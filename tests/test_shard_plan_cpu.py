@@ -43,7 +43,7 @@ def test_plan_partitions_every_tensor_once(world):
             spans.append((s.lp_off, s.lp_off + s.numel * 4))
             assert s.lp_half == s.numel * 2
     spans += [(plan.stats_off, plan.stats_off + world * 16), (plan.kl_off, plan.kl_off + world * 8),
-              (plan.flags_off, plan.flags_off + (8 + world) * 4)]
+              (plan.flags_off, plan.flags_off + 4 * 64)]
     spans.sort()
     for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
         assert a1 <= b0
