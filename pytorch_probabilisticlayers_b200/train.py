@@ -258,7 +258,10 @@ class ELBOTrainStep:
         # tcgen05 CTA per SM); only the first layer's transfer and the small tensors stay on the critical path
         self._side = torch.cuda.Stream(device=dev)
         self._pushed = []                  # unit ranges already handed to the side stream in this step
-        self._overlap_adam = True          # per-layer optimiser pass + gather on the side stream as well
+        # per-layer optimiser pass + operand gather on the side stream as well: implemented and parity-tested, but measured
+        # zero-sum at N = 8 (2.22 vs 2.18 ms/step): the gather competes with the backward kernels for the same HBM / NVLink
+        # ingress, so it stays off
+        self._overlap_adam = False
         self._adam_done = []
         for chain in self._fused_chains():
             for l in chain.layers:
