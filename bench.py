@@ -412,10 +412,10 @@ def run_b200(args, wl):
         return PF.profile_stop(), n
 
     # launch-bound configurations replay the step from a CUDA graph by default: the regression configs, any workload
-    # whose host enqueue time is >= 80 % of its GPU time (probed here), and the peer-exchange multi-GPU step (one
+    # whose host enqueue time is >= 70 % of its GPU time (probed here), and the peer-exchange multi-GPU step (one
     # stream of this library's kernels, no NCCL inside)
     probe_ms = timed(step_resident, 5) / 5
-    host_bound = host_ms.get("step_resident", 0.0) >= 0.8 * probe_ms and world == 1
+    host_bound = host_ms.get("step_resident", 0.0) >= 0.7 * probe_ms and world == 1
     use_graph = args.cuda_graph if args.cuda_graph is not None else bool(
         wl.get("regression") or host_bound or (world > 1 and trainer.exchange == "peer"))
     prof = None

@@ -190,7 +190,9 @@ def conv2d_fwd(x, w_mu, w_rho, eps_w, b_mu, b_rho, eps_b, stride=1, padding=0, d
     outs = []
     for m in range(mc):
         p, ho, wo = _im2col(x[m], k, stride, padding, dilation)     # [B,Ho,Wo,C,k,k]
-        y = np.einsum("bhwckl,ockl->bohw", p, w[m]) + b[m][None, :, None, None]
+        bsz = p.shape[0]
+        y = np.matmul(p.reshape(bsz * ho * wo, -1), w[m].reshape(w.shape[1], -1).T)     # [B*Ho*Wo, Cout] (BLAS)
+        y = y.reshape(bsz, ho, wo, -1).transpose(0, 3, 1, 2) + b[m][None, :, None, None]
         outs.append(y)
     return np.stack(outs, 0)
 
@@ -207,8 +209,11 @@ def conv2d_bwd(dy, x, w_mu, w_rho, eps_w, b_rho, eps_b, stride=1, padding=0, dil
     dw = np.zeros_like(w)
     for m in range(mc):
         p, ho, wo = _im2col(x[m], k, stride, padding, dilation)
-        dw[m] = np.einsum("bhwckl,bohw->ockl", p, dy[m])
-        dp = np.einsum("bohw,ockl->bhwckl", dy[m], w[m])            # grad wrt patches
+        cout = w.shape[1]
+        pm = p.reshape(bsz * ho * wo, -1)                            # [B*Ho*Wo, Cin*k*k]
+        dym = dy[m].transpose(0, 2, 3, 1).reshape(bsz * ho * wo, cout)
+        dw[m] = np.matmul(dym.T, pm).reshape(w[m].shape)
+        dp = np.matmul(dym, w[m].reshape(cout, -1)).reshape(p.shape)  # grad wrt patches
         dxp = np.zeros((bsz, cin, h + 2 * padding, wd + 2 * padding), dtype)
         for kh in range(k):
             for kw in range(k):

@@ -180,15 +180,22 @@ def test_tc_conv_injected_eps_matches_reference_golden(plb, name):
     (2, 2, 6, 33, 11, 3, 1, 2, 2, False),    # dilation 2
     (2, 32, 5, 32, 4, 3, 1, 1, 1, False),    # 4x4 planes: tiled col2im with several channels per CTA (cpb > Cin)
     (1, 4, 40, 64, 16, 5, 1, 2, 1, False),   # C3-like block: k5 p2, 16x16 planes, im2col with 4 output rows per CTA
+    # the REAL C3 layer shapes (experiments/BNN.py:232-247; K = 2400 / 3200 / 6400), MC = 2, reference initialisation
+    (2, 4, 96, 128, 16, 5, 1, 2, 1, "c3"),
+    (2, 4, 128, 256, 8, 5, 1, 2, 1, "c3"),
+    (2, 8, 256, 128, 4, 5, 1, 2, 1, "c3"),
 ])
 def test_tc_conv_philox_matches_fp64_oracle(plb, mc, b, cin, cout, hw, k, s, p, d, expand):
     torch.manual_seed(cout)
     plb.manual_seed(777 + cin)
     layer = plb.BayesConv2d(cin, cout, k, stride=s, padding=p, dilation=d, num_MC=mc).cuda()
     layer.precision = "bf16"
+    ref_init = expand == "c3"
+    expand = expand is True
     with torch.no_grad():
-        layer.weight.logscale.uniform_(-4, -1)
-        layer.bias.logscale.uniform_(-3, 0)
+        if not ref_init:
+            layer.weight.logscale.uniform_(-4, -1)
+            layer.bias.logscale.uniform_(-3, 0)
     if expand:
         x = torch.randn(b, cin, hw, hw, device="cuda").unsqueeze(0).expand(mc, b, cin, hw, hw)
     else:
