@@ -520,7 +520,8 @@ def run_b200(args, wl):
 
     pk = peaks()
 
-    def roofline_of(prof, prof_steps, tf32=False):
+    def roofline_of(prof, prof_steps, tf32=False, precision=None):
+        precision = precision or args.precision
         per_call = {k: v[1] / v[0] for k, v in prof.items()}                  # ms per call
         per_step = {k: v[1] / prof_steps for k, v in prof.items()}            # ms per step
         top = max(per_step, key=per_step.get)
@@ -535,6 +536,14 @@ def run_b200(args, wl):
                                 + ("; the TF32 tensor peak is half of it" if tf32 else ""),
                  "ms_per_launch": per_call[top], "algorithmic_flops_per_launch": amount,
                  "note": "C-ABI call = fused tcgen05 kernel + its HBM-bound pre-passes"}
+            # the split-operand forward / dX kernels execute the mean MMA and the noise MMA: twice the algorithmic FLOPs
+            split = DTYPES[precision] in ("bf16", "tf32") and not precision.endswith("fast") \
+                and not top.startswith("linear_bwd_dw") and top.startswith("linear_")
+            if split and not tf32:
+                r["executed_flops_per_launch"] = 2 * amount
+                r["frac_executed"] = 2 * achieved / pk["tf_sustained"]
+                r["note"] += ("; split operand: the tensor pipe executes 2x the algorithmic FLOPs (mean MMA + noise MMA), "
+                              "frac counts the algorithmic ones only")
         else:
             achieved = amount / (per_call[top] * 1e-3) / 1e9
             r = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": pk["hbm"],
@@ -622,7 +631,8 @@ def run_b200(args, wl):
             PF.profile_start()
             for _ in range(2):
                 tr2.step(x_dev, y_dev)
-            r2, _ = roofline_of(PF.profile_stop(), 2, tf32=precision.startswith("tf32") or precision == "auto_tf32")
+            r2, _ = roofline_of(PF.profile_stop(), 2, tf32=precision.startswith("tf32") or precision == "auto_tf32",
+                                precision=precision)
             out = {"precision": precision, "ms_per_step": ms2, "value": mc_total * batch / (ms2 * 1e-3), "unit": UNIT,
                    "steps": steps, "step_tflops": flops / (ms2 * 1e-3) / 1e12, "roofline": r2,
                    "final_stats": [float(v) for v in st2.tolist()]}
