@@ -15,8 +15,14 @@
 namespace pl {
 
 constexpr int kKlThreads = 256;
-constexpr int kKlBlocks = 148 * 4;
-constexpr int kKlUnroll = 2;  // float4 loads per array per thread per pipeline stage
+#ifndef PL_KL_BLOCKS_PER_SM
+#define PL_KL_BLOCKS_PER_SM 4
+#endif
+#ifndef PL_KL_UNROLL
+#define PL_KL_UNROLL 2
+#endif
+constexpr int kKlBlocks = 148 * PL_KL_BLOCKS_PER_SM;
+constexpr int kKlUnroll = PL_KL_UNROLL;  // float4 loads per array per thread per pipeline stage
 
 // sigma = softplus(rho) and log(sigma) with MUFU-rate math that stays accurate for sigma ~ 1e-6
 // (fresh-init rho ~ -12): series for log1p(e) below e = 1/16, lg2 above.
