@@ -23,6 +23,10 @@
 // sampler's ALU/MUFU budget: every generated element feeds only 2*B flops.
 #include "tc_kernels.cuh"
 
+#ifndef PL_DW_2CTA_DEFAULT
+#define PL_DW_2CTA_DEFAULT 0
+#endif
+
 namespace pl {
 
 // forward->backward state: parameters as the kernels read them | x as bf16 [x_rows*I]
@@ -343,6 +347,24 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
     if (p.atomic_out) {
       PL_CUDA(cudaMemsetAsync(a->dw_mu, 0, sizeof(float) * I * O, st));
       PL_CUDA(cudaMemsetAsync(a->dw_rho, 0, sizeof(float) * I * O, st));
+    }
+    // CTA pairs on a 256 x 128 weight tile (dw_tc2): 25 % fewer operand bytes per FLOP into each SM.  PL_DW_2CTA=0 / 1.
+    static int dw_pairs = -1;
+    if (dw_pairs < 0) {
+      const char* e = getenv("PL_DW_2CTA");
+      dw_pairs = e ? (e[0] == '1') : PL_DW_2CTA_DEFAULT;
+    }
+    if (dw_pairs && !tf32 && I >= 256 && O >= 128 && O % 8 == 0) {
+      dim3 grid2(2u * (unsigned)((I + 255) / 256), (unsigned)((O + 127) / 128), (unsigned)splits);
+      if (a->eps_w) {
+        PL_CUDA(cudaFuncSetAttribute(dw_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDw2SmemBytes));
+        dw_tc2<true><<<grid2, kTcThreads, kDw2SmemBytes, st>>>(tmx, tmdy, p);
+      } else {
+        PL_CUDA(cudaFuncSetAttribute(dw_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDw2SmemBytes));
+        dw_tc2<false><<<grid2, kTcThreads, kDw2SmemBytes, st>>>(tmx, tmdy, p);
+      }
+      PL_LAUNCH_CHECK("dw_tc2");
+      return PL_OK;
     }
     dim3 grid((unsigned)((O + 127) / 128), (unsigned)((I + 127) / 128), (unsigned)splits);
 #define PL_DW_LAUNCH(INJ, TF)                                                                          \

@@ -1271,6 +1271,189 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair version of dw_tc (cta_group::2): the pair owns a [256 in-rows x 128 out-cols] weight tile.  Each CTA stages
+// its own 128 in-features of X (16 KB per 64 batch rows) and HALF of the dY tile (64 out-features, 8 KB): 24 KB of operands
+// per CTA and k-block instead of 32 KB -- dw_tc is bound by what the L2 -> SM fabric delivers (12 TB/s chip-wide), so
+// fewer operand bytes per FLOP is the only lever.  The leader's MMA thread issues M = 256 x N = 128 MMAs that read both
+// CTAs' shared memory; every CTA gets its 128 accumulator rows in its own TMEM and runs the same epilogue as dw_tc on
+// them (eps regeneration, MC sums in registers), so the register budget is unchanged.
+//   full barriers live in the leader (both CTAs' TMA bytes are credited to it), empty / acc_full are multicast commits,
+//   acc_empty collects the arrivals of both CTAs' epilogue warps at the leader.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDw2Stages = 8;
+constexpr int kDw2StageBytes = kSubTileBytes + kSubTileBytes / 2;   // A [128 i x 64 b] + B [64 o x 64 b], bf16
+constexpr int kDw2SmemBytes = kDw2Stages * kDw2StageBytes + 1024 + 1024;
+
+template <bool kInjected>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+dw_tc2(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy, const TcDwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sStage = smem_base;
+  const uint32_t bar0 = sStage + kDw2Stages * kDw2StageBytes;
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (kDw2Stages + s); };
+  auto acc_full = [&](int b) { return bar0 + 8u * (2 * kDw2Stages + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (2 * kDw2Stages + 2 + b); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * kDw2Stages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                   // 0 = leader
+  const int i0 = ((int)blockIdx.x >> 1) * 256 + (int)rank * 128;   // this CTA's 128 weight rows (in-features)
+  const int o0 = blockIdx.y * 128;                           // the pair's 128 weight columns
+  const int ob0 = o0 + (int)rank * 64;                       // the 64 columns of dY this CTA stages
+  const int mc_begin = (int)blockIdx.z * p.mc_per_split;
+  const int mc_end = min(p.mc, mc_begin + p.mc_per_split);
+  const int num_kb = (p.batch + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDw2Stages; ++s) {
+      mbar_init(full(s), 2);                                 // leader producer (+tx of both CTAs) and peer producer
+      mbar_init(empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 2 * kGenWarps);                // the epilogue warps of both CTAs
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_dy);
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int mc = mc_begin; mc < mc_end; ++mc) {
+        const int xm = p.x_broadcast ? 0 : mc;
+        const int ym = p.dy_broadcast ? 0 : mc;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kDw2Stages, ph = (it / kDw2Stages) & 1;
+          mbar_wait(empty(s), ph ^ 1);
+          if (rank == 0) mbar_expect_tx(full(s), 2 * kDw2StageBytes);
+          else mbar_arrive_cluster(full(s), 0);
+          const uint32_t dst = sStage + s * kDw2StageBytes;
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            tma_load_3d_2cta(dst + g * (kSubTileBytes / 2), &tmap_x, full(s), i0 + g * 64, kb * kBK, xm);
+          tma_load_3d_2cta(dst + kSubTileBytes, &tmap_dy, full(s), ob0, kb * kBK, ym);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(256, 128, 1, 1);
+      int it = 0;
+      for (int mc = mc_begin, n = 0; mc < mc_end; ++mc, ++n) {
+        const int buf = n & 1;
+        mbar_wait_cluster(acc_empty(buf), ((n >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kDw2Stages, ph = (it / kDw2Stages) & 1;
+          mbar_wait_cluster(full(s), ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = sStage + s * kDw2StageBytes, b_addr = a_addr + kSubTileBytes;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            // both operands MN-major SW128: 16 batch rows = two 8-row swizzle groups = 2048 B per MMA k-step;
+            // A: this CTA's 128 features = two 64-feature groups 8192 B apart; B: this CTA's 64 features = one group
+            const uint64_t a_desc = smem_desc_sw128(a_addr + ks * 2048, 8192, 1024);
+            const uint64_t b_desc = smem_desc_sw128(b_addr + ks * 2048, 8192, 1024);
+            mma_bf16_ss_2cta(tmem_base + buf * 128, a_desc, b_desc, idesc, (kb > 0) || ks != 0);
+          }
+          mma_commit_2cta(empty(s));
+        }
+        mma_commit_2cta(acc_full(buf));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (both CTAs, own 128 rows): eps regeneration + MC reduction =====================
+    const int gw = warp - 2, q = warp & 3, h = gw >> 2;
+    const Sampler sw = live(p.sw);
+    constexpr int kCols = 128 / (kGenWarps / 4);   // weight columns per thread (32)
+    const int row = i0 + q * 32 + lane;
+    const int col0 = o0 + h * kCols;
+    float acc_mu[kCols], acc_rho[kCols];
+#pragma unroll
+    for (int j = 0; j < kCols; ++j) acc_mu[j] = acc_rho[j] = 0.f;
+    for (int mc = mc_begin, n = 0; mc < mc_end; ++mc, ++n) {
+      const int buf = n & 1;
+      mbar_wait(acc_full(buf), (n >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < kCols / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + h * kCols + c * 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int col = col0 + c * 16 + g * 8;
+          float e[8];
+          if (kInjected) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+              e[t] = (row < p.w_in && col + t < p.w_out)
+                         ? __ldg(p.eps_w + ((int64_t)mc * p.w_in + row) * p.w_out + col + t)
+                         : 0.f;
+          } else {
+            eps8(sw, mc, row, col >> 3, e);
+          }
+          const int j = c * 16 + g * 8;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float d = __uint_as_float(v[g * 8 + t]);
+            acc_mu[j + t] += d;
+            acc_rho[j + t] = fmaf(d, e[t], acc_rho[j + t]);
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc_empty(buf), 0);     // the leader's MMA thread owns the accumulator hand-back
+    }
+    if (row < p.w_in) {
+#pragma unroll
+      for (int j = 0; j < kCols; j += 4) {
+        const int col = col0 + j;
+        if (col < p.w_out) {      // w_out % 8 == 0 on this path
+          const int64_t idx = (int64_t)row * p.w_out + col;
+          float4 gm = make_float4(acc_mu[j], acc_mu[j + 1], acc_mu[j + 2], acc_mu[j + 3]);
+          float4 gr = make_float4(acc_rho[j], acc_rho[j + 1], acc_rho[j + 2], acc_rho[j + 3]);
+          if (p.w_rho) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(p.w_rho + idx));
+            gr.x *= sigmoid_f(r.x); gr.y *= sigmoid_f(r.y); gr.z *= sigmoid_f(r.z); gr.w *= sigmoid_f(r.w);
+          }
+          if (p.atomic_out) {
+            atomicAdd(p.dw_mu + idx + 0, gm.x); atomicAdd(p.dw_mu + idx + 1, gm.y);
+            atomicAdd(p.dw_mu + idx + 2, gm.z); atomicAdd(p.dw_mu + idx + 3, gm.w);
+            atomicAdd(p.dw_rho + idx + 0, gr.x); atomicAdd(p.dw_rho + idx + 1, gr.y);
+            atomicAdd(p.dw_rho + idx + 2, gr.z); atomicAdd(p.dw_rho + idx + 3, gr.w);
+          } else {
+            *reinterpret_cast<float4*>(p.dw_mu + idx) = gm;
+            *reinterpret_cast<float4*>(p.dw_rho + idx) = gr;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();     // the peer's smem / TMEM must outlive the leader's MMAs
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
