@@ -472,3 +472,20 @@ def test_cuda_graph_step_equals_eager_steps(plb):
             assert abs(u - v) <= 2e-4 * max(abs(u), 1e-6), (a, c)
     for a, c in zip(p0, p1):     # Adam turns last-bit gradient differences of near-zero gradients into O(lr) steps
         assert rel_err(c.cpu().numpy(), a.cpu().numpy()) < BF16_TOL
+
+
+@pytest.mark.parametrize("env", [{"PL_TC_2CTA": "1"}, {"PL_DW_2CTA": "1"}])
+def test_opt_in_cta_pair_kernels_pass_the_oracle_tests(env):
+    """The CTA-pair (cta_group::2) kernels are opt-in (they measured equal / slower, profiles/r02_experiments.md) but stay
+    parity-tested: the library reads the switches once per process, so the oracle tests run in a child process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.join(root, "tests", "test_gpu_tc.py"),
+                        os.path.join(root, "tests", "test_gpu_noise.py"), "-k",
+                        "philox_matches_fp64_oracle or baseline_shapes or fused_mlp_equals or noise_survives",
+                        "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=900, cwd=root, env=e)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
