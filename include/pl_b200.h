@@ -238,6 +238,13 @@ typedef struct pl_linear_args {
                           per-call parameter pre-pass, w_mu / w_rho are then not read by forward / dX.  NULL = pack here. */
   int64_t w_lp_half;
   int32_t dw_rho_raw;  /* != 0: dw_rho = sum_mc dW * eps (no sigmoid(rho) factor; w_rho is not read by the dW kernel) */
+  /* Reduce-scatter fused into the dW epilogue (tensor-core precisions, >= 148 weight tiles): the tile of (dw_mu, raw dw_rho)
+     is written straight into the staging rows  peers[owner] + *_off + (rank*chunk + j) * elem  of the ranks that own its
+     elements (pl_shard_seg.g_off / g2_off / chunk of this weight), as fp32 or bf16 (dw_scatter_bf16, = ctx.wire_bf16).
+     dw_mu / dw_rho may then be NULL and pl_shard_push skips this weight.  dw_scatter_world == 0: off. */
+  void* const* dw_scatter_peers;   /* HOST array of dw_scatter_world arena base pointers */
+  int64_t dw_scatter_mu_off, dw_scatter_rho_off, dw_scatter_chunk;
+  int32_t dw_scatter_rank, dw_scatter_world, dw_scatter_bf16;
 } pl_linear_args;
 
 size_t pl_linear_workspace_bytes(const pl_linear_args* a);

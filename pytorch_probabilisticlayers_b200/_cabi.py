@@ -52,6 +52,9 @@ class LinearArgs(C.Structure):
         ("dy_lp", C.c_void_p), ("dx_lp", C.c_void_p), ("x_act_slope", C.c_float),
         ("seed_dev", C.c_void_p),
         ("w_lp", C.c_void_p), ("w_lp_half", C.c_int64), ("dw_rho_raw", C.c_int32),
+        ("dw_scatter_peers", C.c_void_p), ("dw_scatter_mu_off", C.c_int64), ("dw_scatter_rho_off", C.c_int64),
+        ("dw_scatter_chunk", C.c_int64), ("dw_scatter_rank", C.c_int32), ("dw_scatter_world", C.c_int32),
+        ("dw_scatter_bf16", C.c_int32),
     ]
 
 

@@ -419,7 +419,7 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     if (rc != PL_OK) return rc;
     rc = make_tmap_bf16_3d(&tmdy, w.A, (uint64_t)g.mcx, (uint64_t)g.M, (uint64_t)g.Kp, kBK, 64);
     if (rc != PL_OK) return rc;
-    TcDwParams p;
+    TcDwParams p{};
     p.mc = g.mc; p.batch = (int)g.M; p.w_in = g.cout; p.w_out = g.K;
     p.x_broadcast = 0;
     p.dy_broadcast = g.mcx == 1;

@@ -309,8 +309,8 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
     rc = dispatch_gemm<true>(tm, p, st, state.mean, I, O, O, a->eps_w != nullptr, tf32, split);
     if (rc != PL_OK) return rc;
   }
-  if (a->dw_mu) {
-    PL_CHECK_ARG(a->dw_rho, "pl_linear_bwd: dw_mu/dw_rho must both be set or NULL");
+  if (a->dw_mu || a->dw_scatter_world > 0) {
+    PL_CHECK_ARG(a->dw_scatter_world > 0 || a->dw_rho, "pl_linear_bwd: dw_mu/dw_rho must both be set or NULL");
     CUtensorMap tmx, tmdy;
     const uint64_t mcx = a->x_mc_stride == 0 ? 1 : (uint64_t)MC;
     if (tf32) {
@@ -324,7 +324,7 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
       rc = make_tmap_bf16_3d(&tmdy, dy_bf16, (uint64_t)MC, (uint64_t)B, (uint64_t)O, kBK, 64);
     }
     if (rc != PL_OK) return rc;
-    TcDwParams p;
+    TcDwParams p{};
     p.mc = (int)MC; p.batch = (int)B; p.w_in = (int)I; p.w_out = (int)O;
     p.x_broadcast = a->x_mc_stride == 0;
     p.dy_broadcast = 0;
@@ -344,6 +344,16 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
     p.kb_per_split = (int)((B + (tf32 ? 32 : kBK) - 1) / (tf32 ? 32 : kBK));
     splits = (int)((MC + p.mc_per_split - 1) / p.mc_per_split);
     p.atomic_out = splits > 1;
+    if (a->dw_scatter_world > 0) {
+      // reduce-scatter fused into the epilogue (pl_linear_args.dw_scatter_*): needs the one-CTA-per-tile path
+      PL_CHECK_ARG(!p.atomic_out, "pl_linear_bwd: dw_scatter needs >= 148 weight tiles (no MC split)");
+      PL_CHECK_ARG(a->dw_scatter_world <= 8 && a->dw_scatter_peers && a->dw_scatter_chunk > 0 && a->dw_scatter_chunk % 8 == 0,
+                   "pl_linear_bwd: bad dw_scatter arguments");
+      for (int r = 0; r < a->dw_scatter_world; ++r) p.sc_peers[r] = a->dw_scatter_peers[r];
+      p.sc_mu_off = a->dw_scatter_mu_off; p.sc_rho_off = a->dw_scatter_rho_off; p.sc_chunk = a->dw_scatter_chunk;
+      p.sc_rank = a->dw_scatter_rank; p.sc_world = a->dw_scatter_world; p.sc_bf16 = a->dw_scatter_bf16;
+      p.w_rho = nullptr;           // the owners apply sigmoid(rho) after the cross-rank sum
+    }
     if (p.atomic_out) {
       PL_CUDA(cudaMemsetAsync(a->dw_mu, 0, sizeof(float) * I * O, st));
       PL_CUDA(cudaMemsetAsync(a->dw_rho, 0, sizeof(float) * I * O, st));
@@ -354,7 +364,7 @@ int linear_bwd_tc_launch(const pl_linear_args* a) {
       const char* e = getenv("PL_DW_2CTA");
       dw_pairs = e ? (e[0] == '1') : PL_DW_2CTA_DEFAULT;
     }
-    if (dw_pairs && !tf32 && I >= 256 && O >= 128 && O % 8 == 0) {
+    if (dw_pairs && !tf32 && I >= 256 && O >= 128 && O % 8 == 0 && a->dw_scatter_world == 0) {
       dim3 grid2(2u * (unsigned)((I + 255) / 256), (unsigned)((O + 127) / 128), (unsigned)splits);
       if (a->eps_w) {
         PL_CUDA(cudaFuncSetAttribute(dw_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDw2SmemBytes));

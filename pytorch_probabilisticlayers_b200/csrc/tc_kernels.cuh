@@ -1079,6 +1079,12 @@ struct TcDwParams {
   Sampler sw;
   float* dw_mu;
   float* dw_rho;
+  // MC-sharded training over peer memory (csrc/comm.cu): instead of writing [I, O] gradients locally, the tile goes straight
+  // into the staging rows of the ranks that own its elements (reduce-scatter fused into the dW epilogue); sc_world == 0: off
+  void* sc_peers[8];       // arena base of every rank
+  int64_t sc_mu_off, sc_rho_off;   // byte offsets of this weight's mean / rho staging [world][chunk] in the arenas
+  int64_t sc_chunk;        // elements per rank
+  int sc_rank, sc_world, sc_bf16;
 };
 
 template <bool kInjected, bool kTf32>
@@ -1224,6 +1230,51 @@ dw_tc(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtens
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
     }
+    if (p.sc_world > 0) {
+      // ---- reduce-scatter from the epilogue: tile -> shared memory -> full 256 / 512-byte rows into the owners' staging ----
+      // (every MMA has retired -- the last acc_full was waited for -- so the operand stages are free to reuse; a thread's
+      // own 32 columns would be 16-byte pieces 8 KB apart: partial-sector stores make poor NVLink packets)
+      const int esz = p.sc_bf16 ? 2 : 4;
+      const int pitch = 128 * esz + 16;                      // padded row: the 16-byte pieces of a warp spread over the banks
+      uint8_t* t_mu = smem + (sStage - smem_base);
+      uint8_t* t_rho = t_mu + 128 * pitch;
+      const int rl = q * 32 + lane;                          // row inside the tile
+#pragma unroll
+      for (int j = 0; j < kCols; j += 8) {
+        const int cl = h * kCols + j;                        // column inside the tile
+        if (p.sc_bf16) {
+          *reinterpret_cast<uint4*>(t_mu + rl * pitch + cl * 2) =
+              make_uint4(pack_bf16x2(acc_mu[j], acc_mu[j + 1]), pack_bf16x2(acc_mu[j + 2], acc_mu[j + 3]),
+                         pack_bf16x2(acc_mu[j + 4], acc_mu[j + 5]), pack_bf16x2(acc_mu[j + 6], acc_mu[j + 7]));
+          *reinterpret_cast<uint4*>(t_rho + rl * pitch + cl * 2) =
+              make_uint4(pack_bf16x2(acc_rho[j], acc_rho[j + 1]), pack_bf16x2(acc_rho[j + 2], acc_rho[j + 3]),
+                         pack_bf16x2(acc_rho[j + 4], acc_rho[j + 5]), pack_bf16x2(acc_rho[j + 6], acc_rho[j + 7]));
+        } else {
+#pragma unroll
+          for (int t = 0; t < 8; t += 4) {
+            *reinterpret_cast<float4*>(t_mu + rl * pitch + (cl + t) * 4) =
+                make_float4(acc_mu[j + t], acc_mu[j + t + 1], acc_mu[j + t + 2], acc_mu[j + t + 3]);
+            *reinterpret_cast<float4*>(t_rho + rl * pitch + (cl + t) * 4) =
+                make_float4(acc_rho[j + t], acc_rho[j + t + 1], acc_rho[j + t + 2], acc_rho[j + t + 3]);
+          }
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kGenWarps * 32) : "memory");     // the 16 epilogue warps only
+      const int per_piece = 16 / esz;                        // elements per 16-byte piece
+      const int ppr = 128 / per_piece;                       // pieces per tile row
+      const int et = threadIdx.x - 64;                       // 0 .. 511
+      for (int pc = et; pc < 128 * ppr; pc += kGenWarps * 32) {
+        const int r = pc / ppr, c = (pc - r * ppr) * per_piece;
+        const int grow = i0 + r, gcol = o0 + c;
+        if (grow >= p.w_in || gcol >= p.w_out) continue;     // w_out % 8 == 0: a piece is inside or outside
+        const int64_t f = (int64_t)grow * p.w_out + gcol;
+        const int owner = (int)(f / p.sc_chunk);             // chunk % 8 == 0: a piece never straddles two owners
+        const int64_t jj = f - (int64_t)owner * p.sc_chunk + (int64_t)p.sc_rank * p.sc_chunk;
+        uint8_t* base = (uint8_t*)p.sc_peers[owner];
+        *reinterpret_cast<uint4*>(base + p.sc_mu_off + jj * esz) = *reinterpret_cast<const uint4*>(t_mu + r * pitch + c * esz);
+        *reinterpret_cast<uint4*>(base + p.sc_rho_off + jj * esz) = *reinterpret_cast<const uint4*>(t_rho + r * pitch + c * esz);
+      }
+    } else
     if (row < p.w_in) {
 #pragma unroll
       for (int j = 0; j < kCols; j += 4) {

@@ -30,6 +30,8 @@ class SampleSpec:
     dw_rho_raw: int = 0                # drho leaves the dW kernel as sum dW*eps (the shard owner applies sigmoid(rho))
     grad_out: Optional[tuple] = None   # (dw_mu, dw_rho, db_mu, db_rho) tensors the backward writes straight into
     after_bwd: Optional[object] = None  # callable run right after this layer's backward kernels are enqueued
+    dw_scatter: Optional[dict] = None   # reduce-scatter fused into the dW epilogue: peers (ctypes array), mu_off, rho_off,
+                                        # chunk, rank, world, bf16 (pl_linear_args.dw_scatter_*)
 
 
 # ---- optional per-call CUDA-event timing (bench.py's roofline leg) -----------------------------

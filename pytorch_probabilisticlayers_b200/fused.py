@@ -115,6 +115,18 @@ class _FusedMLPFn(torch.autograd.Function):
                     dw_mu, dw_rho = torch.empty_like(w_mu), torch.empty_like(w_rho)
                     db_mu, db_rho = torch.empty_like(b_mu), torch.empty_like(b_rho)
                 a.dw_mu, a.dw_rho, a.db_mu, a.db_rho = (_cabi.ptr(t) for t in (dw_mu, dw_rho, db_mu, db_rho))
+                sc = sp.dw_scatter
+
+                def set_scatter(on):
+                    if sc is None:
+                        return
+                    a.dw_scatter_world = sc["world"] if on else 0
+                    if on:                      # the weight gradients go straight to their owners' staging rows
+                        a.dw_scatter_peers = C.cast(sc["peers"], C.c_void_p)
+                        a.dw_scatter_mu_off, a.dw_scatter_rho_off = sc["mu_off"], sc["rho_off"]
+                        a.dw_scatter_chunk, a.dw_scatter_rank, a.dw_scatter_bf16 = sc["chunk"], sc["rank"], sc["bf16"]
+                        a.dw_mu = a.dw_rho = None
+                set_scatter(True)
                 dx_lp = None
                 if li > 0:                              # dX * act'(x) as the bf16 dY of layer li-1
                     dx_lp = torch.empty((mc, batch, fin), dtype=torch.bfloat16, device=dev)
@@ -133,7 +145,8 @@ class _FusedMLPFn(torch.autograd.Function):
                     outs = (a.dx_lp, a.dw_mu, a.dw_rho, a.db_mu, a.db_rho, a.dx)
                     for tag, keep in (("dx", (0, 5)), ("dw", (1, 2)), ("db", (3, 4))):
                         sel = [o if i in keep else None for i, o in enumerate(outs)]
-                        if all(v is None for v in sel):
+                        set_scatter(tag == "dw")
+                        if all(v is None for v in sel) and not (tag == "dw" and sc is not None):
                             continue
                         a.dx_lp, a.dw_mu, a.dw_rho, a.db_mu, a.db_rho, a.dx = sel
                         PF._timed(f"linear_bwd_{tag}{shape}",
@@ -188,6 +201,7 @@ class FusedBayesMLP(torch.nn.Module):
                 spec.w_lp, spec.w_lp_half, spec.dw_rho_raw = sh.get("w_lp", 0), sh.get("w_lp_half", 0), sh.get("dw_rho_raw", 0)
                 spec.grad_out = sh.get("grad_out")
                 spec.after_bwd = sh.get("after_bwd")
+                spec.dw_scatter = sh.get("dw_scatter")
             specs.append(spec)
             l._remember(mc, None, None, spec)
             params += [l.weight.loc, l.weight.logscale, l.bias.loc, l.bias.logscale]

@@ -200,7 +200,7 @@ class ELBOTrainStep:
                     sh["grad_out"] = tuple(p.grad for p in ps)
                     l._shard = sh
 
-    def _setup_peer_exchange(self, overlap_push=True):
+    def _setup_peer_exchange(self, overlap_push=True, scatter_from_dw=True):
         """Builds the shard plan (shard.ShardPlan), moves parameters and gradients to its layout, maps the peers."""
         from . import shard as S
         if self.world > 1 and any(isinstance(m, SIVILayer) for m in self.net.modules()):
@@ -258,6 +258,7 @@ class ELBOTrainStep:
         # tcgen05 CTA per SM); only the first layer's transfer and the small tensors stay on the critical path
         self._side = torch.cuda.Stream(device=dev)
         self._pushed = []                  # unit ranges already handed to the side stream in this step
+        self._scattered = []               # unit ranges the dW kernels deliver themselves (never pushed)
         # per-layer optimiser pass + operand gather on the side stream as well: implemented and parity-tested, but measured
         # zero-sum at N = 8 (2.22 vs 2.18 ms/step): the gather competes with the backward kernels for the same HBM / NVLink
         # ingress, so it stays off
@@ -270,7 +271,19 @@ class ELBOTrainStep:
                 if s is not None and s.gather:
                     ptr, half = self.shard.lp_pointers(s)
                     sh.update(w_lp=ptr, w_lp_half=half, dw_rho_raw=1)
-                if s is not None and overlap_push:
+                tiles = -(-l.dim_input // 128) * -(-l.dim_output // 128)
+                import os
+                if os.environ.get("PL_SHARD_NO_DW_SCATTER", "0") == "1":     # A/B switch: separate push kernel
+                    scatter_from_dw = False
+                if s is not None and s.gather and scatter_from_dw and tiles >= 148:
+                    # reduce-scatter fused into the dW epilogue: the tile goes straight into the owners' staging rows, no
+                    # push kernel (and no local gradient buffer traffic) for this weight
+                    import ctypes as C
+                    peers = (C.c_void_p * 8)(*[int(p_) for p_ in self.shard.peers])
+                    sh["dw_scatter"] = dict(peers=peers, mu_off=s.g_off, rho_off=s.g2_off, chunk=s.chunk, rank=self.rank,
+                                            world=self.world, bf16=1 if self.shard.wire_bf16 else 0)
+                    self._scattered.append(self.shard.seg_units(k))
+                elif s is not None and overlap_push:
                     sh["after_bwd"] = self._make_push_hook(self.shard.seg_units(k), k)
                 l._shard = sh
         self._direct_grads()
@@ -485,7 +498,8 @@ class ELBOTrainStep:
             out[3] = out[0] + out[1]
             return out
         # what the side stream has not taken already (+ the statistics), then join it
-        done = sorted(self._pushed)
+        done = sorted(self._pushed + self._scattered)
+        side_used = bool(self._pushed)
         self._pushed = []
         cur, rest = 0, []
         for lo, hi in done:
@@ -501,7 +515,7 @@ class ELBOTrainStep:
         def push_rest():
             for i, r in enumerate(rest):
                 sh.push(self.flat, self.stats if i == 0 else None, r)
-            if done:
+            if side_used:
                 ev = torch.cuda.Event()
                 ev.record(self._side)
                 torch.cuda.current_stream(self.flat.device).wait_event(ev)

@@ -37,17 +37,18 @@ def single(tmp_path_factory):
     return _run(1, str(d / "n1.npz")), d
 
 
-@pytest.mark.parametrize("exchange,graph,ipc", [("peer", 0, 0), ("peer", 1, 0), ("peer", 0, 1), ("nccl", 0, 0)])
+@pytest.mark.parametrize("exchange,graph,ipc", [("peer", 0, 0), ("peer", 1, 0), ("peer", 0, 1), ("peer", 0, 2), ("nccl", 0, 0)])
 def test_two_ranks_follow_the_single_gpu_trajectory(single, exchange, graph, ipc):
     """peer: arenas in torch symmetric memory (all-gather through the NVLS multicast mapping where the fabric offers one) or,
-    ipc=1, plain CUDA-IPC peer mappings (one store per peer)."""
+    ipc=1, plain CUDA-IPC peer mappings (one store per peer); ipc=2: symmetric memory with the separate push kernel instead of
+    the reduce-scatter fused into the dW epilogue."""
     ref, d = single
     got = _run(2, str(d / f"n2_{exchange}_{graph}_{ipc}.npz"), "--exchange", exchange, "--graph", str(graph),
                port=29731 + 7 * graph + (3 if exchange == "nccl" else 0) + 11 * ipc,
-               env_extra={"PL_SHARD_NO_SYMM": "1"} if ipc else None)
+               env_extra={1: {"PL_SHARD_NO_SYMM": "1"}, 2: {"PL_SHARD_NO_DW_SCATTER": "1"}}.get(ipc))
     assert str(got["exchange"]) == exchange and int(got["status"]) == 0, (got["exchange"], got["fallback"])
     if exchange == "peer":
-        assert str(got["transport"]).startswith("cuda_ipc" if ipc else "symmetric_memory"), got["transport"]
+        assert str(got["transport"]).startswith("cuda_ipc" if ipc == 1 else "symmetric_memory"), got["transport"]
     s1, s2 = ref["stats"], got["stats"]
     for t in range(len(s1)):
         if np.isnan(s2[t]).any():
