@@ -283,6 +283,8 @@ class ELBOTrainStep:
                     sh["dw_scatter"] = dict(peers=peers, mu_off=s.g_off, rho_off=s.g2_off, chunk=s.chunk, rank=self.rank,
                                             world=self.world, bf16=1 if self.shard.wire_bf16 else 0)
                     self._scattered.append(self.shard.seg_units(k))
+                    if os.environ.get("PL_SHARD_OVERLAP_ADAM", "0") == "1":     # experiment switch, see _make_adam_hook
+                        sh["after_bwd"] = self._make_adam_hook(k)
                 elif s is not None and overlap_push:
                     sh["after_bwd"] = self._make_push_hook(self.shard.seg_units(k), k)
                 l._shard = sh
@@ -310,6 +312,22 @@ class ELBOTrainStep:
                                     segs=(seg_index, seg_index + 1), zero_kl=False)
                     self._adam_done.append(seg_index)
             self._pushed.append(units)
+        return hook
+
+    def _make_adam_hook(self, seg_index):
+        """Experiment (PL_SHARD_OVERLAP_ADAM=1): a scattered layer's barrier + optimiser pass + operand gather on the side
+        stream, under the backward of the layers before it."""
+        def hook():
+            main = torch.cuda.current_stream(self.flat.device)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self._side.wait_event(ev)
+            with torch.cuda.stream(self._side):
+                self.shard.barrier(1)
+                self.shard.adam(1.0 / self.num_samples, self.lr, self.betas, self.eps, self.adam_t, self._sched_cur,
+                                segs=(seg_index, seg_index + 1), zero_kl=False)
+            self._adam_done.append(seg_index)
+            self._side_used = True
         return hook
 
     def _begin_opt_step(self):
@@ -499,7 +517,8 @@ class ELBOTrainStep:
             return out
         # what the side stream has not taken already (+ the statistics), then join it
         done = sorted(self._pushed + self._scattered)
-        side_used = bool(self._pushed)
+        side_used = bool(self._pushed) or getattr(self, "_side_used", False)
+        self._side_used = False
         self._pushed = []
         cur, rest = 0, []
         for lo, hi in done:
