@@ -463,6 +463,9 @@ def run_b200(args, wl):
     weak = None
     exchange = getattr(trainer, "exchange", None)
     transport = getattr(trainer.shard, "transport", None) if trainer.shard is not None else None
+    # 0 = every device-side barrier of the run completed; 1 = one timed out (a peer never arrived: the numbers are void)
+    peer_status = trainer.shard.status() if (trainer.shard is not None and world > 1) else None
+    assert not peer_status, "a cross-GPU barrier timed out"
     if world > 1 and not wl.get("conv") and not args.no_weak:
         if trainer.shard is not None:
             torch.cuda.synchronize()
@@ -706,7 +709,7 @@ def run_b200(args, wl):
                         "cuda_graph": bool(use_graph), "cuda_graph_error": graph_error,
                         "parallelism": f"mc-shard x{world}" if world > 1 else "single",
                         "grad_exchange": exchange, "grad_wire": args.grad_wire if exchange == "peer" else None,
-                        "peer_transport": transport if world > 1 else None},
+                        "peer_transport": transport if world > 1 else None, "peer_barrier_status": peer_status},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size(),
                 "d2h_bytes_per_step": 16,
