@@ -543,10 +543,15 @@ def run_b200(args, wl):
             split = DTYPES[precision] in ("bf16", "tf32") and not precision.endswith("fast") \
                 and not top.startswith("linear_bwd_dw") and top.startswith("linear_")
             if split and not tf32:
-                r["executed_flops_per_launch"] = 2 * amount
-                r["frac_executed"] = 2 * achieved / pk["tf_sustained"]
-                r["note"] += ("; split operand: the tensor pipe executes 2x the algorithmic FLOPs (mean MMA + noise MMA), "
-                              "frac counts the algorithmic ones only")
+                # layer 1 reads an MC-broadcast input: its mean MMA is hoisted (executed once, not per sample)
+                calls = prof[top][0] / prof_steps
+                first = f"linear_fwd[{mc_total // world}x{batch}x{dims[0]}x{dims[1]}]"
+                mult = (2 * calls - 1) / calls if (top == first and not wl.get("conv")) else 2.0
+                r["executed_flops_per_launch"] = mult * amount
+                r["frac_executed"] = mult * achieved / pk["tf_sustained"]
+                r["note"] += (f"; split operand: the tensor pipe executes the mean MMA and the noise MMA, {mult:.2f}x the "
+                              "algorithmic FLOPs averaged over this tag's calls (the MC-broadcast first layer's mean MMA is "
+                              "hoisted out of the per-sample launches); frac counts the algorithmic FLOPs only")
         else:
             achieved = amount / (per_call[top] * 1e-3) / 1e9
             r = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": pk["hbm"],
