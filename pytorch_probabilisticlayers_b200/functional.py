@@ -53,7 +53,20 @@ def profile_stop():
     return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (prof or {}).items()}
 
 
+_NVTX = __import__("os").environ.get("PL_NVTX", "0") == "1"    # PL_NVTX=1: one NVTX range per C-ABI call (ncu --nvtx)
+
+
 def _timed(tag, fn, work=None):
+    if _NVTX:
+        torch.cuda.nvtx.range_push(tag)
+        try:
+            return _timed_inner(tag, fn, work)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    return _timed_inner(tag, fn, work)
+
+
+def _timed_inner(tag, fn, work=None):
     if _PROFILE is None:
         return fn()
     if work is not None:
