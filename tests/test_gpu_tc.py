@@ -489,3 +489,32 @@ def test_opt_in_cta_pair_kernels_pass_the_oracle_tests(env):
                         "philox_matches_fp64_oracle or baseline_shapes or fused_mlp_equals or noise_survives",
                         "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=900, cwd=root, env=e)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("mc,b,i,o", [(4, 256, 1200, 10), (2, 128, 256, 3), (2, 160, 512, 20)])
+def test_narrow_head_runs_on_tensor_cores_through_padded_views(plb, mc, b, i, o):
+    """'auto' pads a narrow classifier head (C2's 1200 -> 10) to a multiple of 8 columns for the tcgen05 kernels; the first
+    `o` columns draw the eps of the unpadded layer, so outputs, dX and parameter gradients match the fp32 path on the same
+    eps within the bf16 tolerance, and the lazily dumped eps is the unpadded one."""
+    from pytorch_probabilisticlayers_b200 import _cabi
+    res = {}
+    for prec in ("fp32", "auto"):
+        torch.manual_seed(i + o)
+        plb.manual_seed(2024)
+        layer = plb.BayesLinear(i, o).cuda()
+        layer.layer_id = 6000 + o
+        layer.precision = prec
+        with torch.no_grad():
+            layer.weight.logscale.fill_(-4.0)
+        x = torch.randn(mc, b, i, device="cuda", requires_grad=True)
+        gy = torch.randn(mc, b, o, device="cuda")
+        out = layer(x)
+        assert out.shape == (mc, b, o)
+        (out * gy).sum().backward()
+        res[prec] = [t.detach().cpu().numpy() for t in (out, x.grad, layer.weight.loc.grad, layer.weight.logscale.grad,
+                                                        layer.bias.loc.grad, layer.bias.logscale.grad, layer.weight.eps)]
+        if prec == "auto":
+            assert layer._last[3].precision == _cabi.PREC_BF16, "the narrow head did not take the tensor-core path"
+    for a, b_ in zip(res["auto"][:6], res["fp32"][:6]):
+        assert rel_err(a, b_) < BF16_TOL
+    assert np.array_equal(res["auto"][6], res["fp32"][6])          # the same eps stream
