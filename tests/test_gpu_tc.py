@@ -450,7 +450,8 @@ def test_cuda_graph_step_equals_eager_steps(plb):
             layers = [m for m in net.modules() if isinstance(m, plb.BayesLinear)]
             for k, l in enumerate(layers):
                 l.layer_id = 2000 + k                                # same eps stream in both runs
-            net = fuse_bayes_mlp(net, b)
+            layers[-1].precision = "fp32"     # the 16-wide head in exact arithmetic (under 'auto' it would run as a padded
+            net = fuse_bayes_mlp(net, b)      # tensor-core head whose atomic MC-split dW order changes from run to run)
             tr = ELBOTrainStep(net, plb.MC_CrossEntropyLoss(ns), ns, lr=1e-3)
             x = torch.randn(b, dims[0], device="cuda")
             y = torch.randint(0, dims[-1], (b,), device="cuda")
