@@ -134,3 +134,20 @@ def test_fused_bn_act_pool_module_on_cpu_equals_the_three_modules():
     got = fused[0](x)
     assert torch.allclose(got, want, atol=1e-6)
     assert torch.allclose(net[0].running_var, ref_bn.running_var)
+
+
+def test_integration_md_struct_mirror_matches_the_library():
+    """The ctypes mirror of pl_linear_args printed in INTEGRATION.md (the stub a maintainer of the reference would paste)
+    has the size the built library reports: the document cannot drift from include/pl_b200.h unnoticed."""
+    import ctypes as C
+    import os
+    import re
+    from pytorch_probabilisticlayers_b200 import _cabi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "INTEGRATION.md")).read()
+    m = re.search(r"class pl_linear_args\(C.Structure\):.*?\n    _fields_ = (\[.*?\])\n", src, re.S)
+    assert m, "INTEGRATION.md no longer shows the pl_linear_args mirror"
+
+    class Mirror(C.Structure):
+        _fields_ = eval(m.group(1), {"C": C})
+    assert C.sizeof(Mirror) == _cabi.lib().pl_struct_size(0) == C.sizeof(_cabi.LinearArgs)
