@@ -338,8 +338,8 @@ typedef struct pl_shard_ctx {
   void* mc_base;                     /* optional NVLS multicast mapping of the arenas (one store lands in every rank's
                                         arena, replicated by the NVSwitch): the all-gather then leaves each GPU once
                                         instead of once per peer; NULL = one store per peer                             */
-  int64_t stats_off;                 /* float [world][4]: per-rank LL, -, ACC, -                                       */
-  int64_t kl_off;                    /* double [world]: per-rank KL partial                                            */
+  int64_t stats_off;                 /* float [2][8][4]: per-rank LL, -, ACC, - ; two slots alternating by step        */
+  int64_t kl_off;                    /* double [2][8]: per-rank KL partial, two slots alternating by step              */
   int64_t flags_off;                 /* 4 channels x uint32 [16]: epoch, status, -, ..., then one arrival flag per rank  */
   int64_t push_units, adam_units;    /* totals of the two prefix arrays                                                */
   int64_t push_prefix[2 * PL_SHARD_MAX_SEGS + 1]; /* 8-element units of every tensor (2 slots per segment)            */

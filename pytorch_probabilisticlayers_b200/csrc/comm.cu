@@ -127,7 +127,11 @@ __global__ void __launch_bounds__(256) shard_push_kernel(const pl_shard_ctx c, c
     }
   }
   if (blockIdx.x == 0 && (int)threadIdx.x < c.world && stats4) {
-    float* dst = (float*)((uint8_t*)c.peers[threadIdx.x] + c.stats_off) + 4 * c.rank;
+    // two statistics slots, alternating by step: a rank that is already pushing step k+1 cannot overwrite what a slower
+    // peer is still summing for step k (channel-0 epoch: two barriers per step, so bit 1 is the step parity)
+    const uint32_t epoch = *(const uint32_t*)((const uint8_t*)c.peers[c.rank] + c.flags_off);
+    const int slot = (epoch >> 1) & 1;
+    float* dst = (float*)((uint8_t*)c.peers[threadIdx.x] + c.stats_off) + 4 * (slot * PL_SHARD_MAX_RANKS + c.rank);
 #pragma unroll
     for (int t = 0; t < 4; ++t) dst[t] = stats4[t];
   }
@@ -371,15 +375,19 @@ __global__ void __launch_bounds__(256, 2) shard_adam_kernel(const pl_shard_ctx c
 __global__ void shard_finish_kernel(const pl_shard_ctx c, const double* __restrict__ kl_acc, double kl_const, double inv_ns,
                                     float* __restrict__ stats_out) {
   __shared__ uint32_t s_epoch;
+  // step parity from the channel-0 epoch BEFORE this kernel's barrier (odd here: the step's first barrier is behind us)
+  const uint32_t epoch0 = *(const uint32_t*)((const uint8_t*)c.peers[c.rank] + c.flags_off);
+  const int slot = (epoch0 >> 1) & 1;
   if ((int)threadIdx.x < c.world) {
-    double* dst = (double*)((uint8_t*)c.peers[threadIdx.x] + c.kl_off) + c.rank;
+    double* dst = (double*)((uint8_t*)c.peers[threadIdx.x] + c.kl_off) + slot * PL_SHARD_MAX_RANKS + c.rank;
     *dst = kl_acc ? *kl_acc : 0.0;
   }
+  __syncthreads();
   grid_barrier_block(c, &s_epoch);
   if (threadIdx.x == 0 && stats_out) {
     const uint8_t* base = (const uint8_t*)c.peers[c.rank];
-    const float* st = (const float*)(base + c.stats_off);
-    const double* kls = (const double*)(base + c.kl_off);
+    const float* st = (const float*)(base + c.stats_off) + 4 * slot * PL_SHARD_MAX_RANKS;
+    const double* kls = (const double*)(base + c.kl_off) + slot * PL_SHARD_MAX_RANKS;
     float ll = 0.f, acc = 0.f;
     double kl = 0.0;
     for (int r = 0; r < c.world; ++r) {       // fixed order

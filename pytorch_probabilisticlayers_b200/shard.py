@@ -116,9 +116,9 @@ class ShardPlan:
                 s.lp_half = s.numel * 2 if s.gather == 1 else 0
                 off += _align(s.numel * 4)
         self.stats_off = off
-        off += _align(self.world * 16)
+        off += _align(2 * MAX_RANKS * 16)   # two slots (alternating by step) x 8 ranks x 4 floats
         self.kl_off = off
-        off += _align(self.world * 8)
+        off += _align(2 * MAX_RANKS * 8)
         self.flags_off = off
         off += _align(4 * 64)               # 4 barrier channels x 16 words
         self.arena_bytes = off

@@ -42,7 +42,7 @@ def test_plan_partitions_every_tensor_once(world):
         if s.gather:
             spans.append((s.lp_off, s.lp_off + s.numel * 4))
             assert s.lp_half == s.numel * 2
-    spans += [(plan.stats_off, plan.stats_off + world * 16), (plan.kl_off, plan.kl_off + world * 8),
+    spans += [(plan.stats_off, plan.stats_off + 2 * 8 * 16), (plan.kl_off, plan.kl_off + 2 * 8 * 8),
               (plan.flags_off, plan.flags_off + 4 * 64)]
     spans.sort()
     for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
