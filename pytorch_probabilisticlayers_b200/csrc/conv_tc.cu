@@ -59,104 +59,127 @@ __global__ void __launch_bounds__(256) im2col_bf16_kernel(const float* __restric
   }
 }
 
-// Same matrix, one CTA per (image, output row).  The k input rows that output row needs are staged in shared
-// memory WITH their zero padding ([Cin*k + 1][ws] fp32, ws = w + 2*pad; the extra row is all zero and serves the
-// K..Kp tail), next to a table off[kidx] = (c*k + kh)*ws + kw*dil (uint16).  An output chunk of 8 consecutive
-// kidx is then one 16-byte table read, eight shared-memory loads at off + ow*stride, four packs and one 16-byte
-// store: ~40 instructions instead of ~430 (the first version recomputed (c, kh, kw) and bounds per element and
-// was issue bound: 2.1 ms for C3's layer 2, profiles/r01_experiments.md).
-// grid (ho, mcx*batch), dynamic smem = (Cin*k + 1)*ws*4 + Kp*2 bytes.
-// kK: compile-time kernel size (divisions by k and k*k become multiply-shift); 0 = run-time k.  All index
-// arithmetic is per (warp, row) or per (warp, output pixel), never per element.  A CTA produces `rpb` consecutive
-// output rows from one staging of (rpb-1)*stride + (k-1)*dil + 1 input rows per channel (4 output rows share
-// 8 staged rows at k = 5 instead of staging 5 rows for each).
+// Same matrix, one CTA per (image, `rpb` consecutive output rows).  The (rpb-1)*stride + (k-1)*dil + 1 input rows
+// those output rows need are staged in shared memory WITH their zero padding ([Cin*rin][ws] fp32, ws = w + 2*pad;
+// 16-byte global loads when the rows allow it), followed by a zero region that serves the K..Kp tail, next to two
+// tables: off[kidx] = byte offset of (c, kh, kw) in the staging, pshift[px] = byte shift of output pixel px.
+// A lane keeps the eight offsets of its 16-byte output chunk in registers and walks over the CTA's pixels: per
+// chunk one broadcast table read, eight (add, shared load) pairs, four packs and one 16-byte store - 25 instructions
+// where the first version (recomputing (c, kh, kw) and the bounds per element) needed ~430 and the second ~70 plus
+// a scalar staging loop that cost as much again (profiles/r01_experiments.md, r02_experiments.md).
+// grid (ceil(ho / rpb), mcx*batch); dynamic smem = im2col_rows_smem().
+// kK: compile-time kernel size (divisions by k and k*k become multiply-shift); 0 = run-time k.
 template <int kK>
 __global__ void __launch_bounds__(256) im2col_rows_bf16_kernel(const float* __restrict__ x,
                                                                int64_t x_mc_stride,
-                                                               __nv_bfloat16* __restrict__ A, ConvGeom g, int rpb) {
+                                                               __nv_bfloat16* __restrict__ A, ConvGeom g, int rpb,
+                                                               int vec4) {
   extern __shared__ __align__(16) uint8_t im2col_smem[];
   const int k = kK ? kK : g.k;
   const int ws = g.w + 2 * g.pad;
   const int rin = (rpb - 1) * g.stride + (k - 1) * g.dil + 1;   // staged input rows per channel
   const int nrow = g.cin * rin;
-  uint16_t* off = reinterpret_cast<uint16_t*>(im2col_smem);                 // [Kp]
-  float* rows = reinterpret_cast<float*>(im2col_smem + (((size_t)g.Kp * 2 + 15) & ~(size_t)15));   // [nrow + 1][ws]
+  const int zr = (rpb - 1) * g.stride * ws + (g.wo - 1) * g.stride + 1;   // zero region: any pixel shift stays inside
+  const int nfloat = (nrow * ws + zr + 3) & ~3;
+  uint32_t* off = reinterpret_cast<uint32_t*>(im2col_smem);                                   // [Kp]
+  uint32_t* pshift = off + ((g.Kp + 3) & ~3);                                                // [rpb * wo]
+  float* rows = reinterpret_cast<float*>(pshift + ((rpb * g.wo + 3) & ~3));                   // [nfloat]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int oh0 = blockIdx.x * rpb, img = blockIdx.y, mc = img / g.batch, b = img - mc * g.batch;
   const float* xb = x + (int64_t)mc * x_mc_stride + (int64_t)b * g.cin * g.h * g.w;
   const int ih0 = oh0 * g.stride - g.pad;
-  // staged rows: a warp pass covers 32 / cw rows of cw (8, 16 or 32) columns each, so narrow planes keep the lanes busy
-  const int cw = ws <= 8 ? 8 : (ws <= 16 ? 16 : 32), rpp = 32 / cw;
-  const int sub = lane / cw, col0 = lane - sub * cw;
-  for (int rw = warp * rpp + sub; rw <= nrow; rw += 8 * rpp) {   // row nrow = zeros
-    const int c = rw / rin, r = rw - c * rin, ih = ih0 + r;
-    const bool row_ok = rw < nrow && ih >= 0 && ih < g.h;
-    const float* src = xb + ((int64_t)c * g.h + ih) * g.w - g.pad;
-    for (int col = col0; col < ws; col += cw)
-      rows[rw * ws + col] = (row_ok && col >= g.pad && col < g.w + g.pad) ? __ldg(src + col) : 0.f;
-  }
+  for (int t = threadIdx.x; t < (nfloat >> 2); t += 256) reinterpret_cast<uint4*>(rows)[t] = make_uint4(0u, 0u, 0u, 0u);
   const int kk2 = k * k;
   for (int kidx = threadIdx.x; kidx < g.Kp; kidx += 256) {
-    int o = nrow * ws;                                   // the zero row
+    int o = nrow * ws;                                   // the zero region
     if (kidx < g.K) {
       const int c = kidx / kk2, r = kidx - c * kk2, kh = r / k, kw = r - kh * k;
       o = (c * rin + kh * g.dil) * ws + kw * g.dil;
     }
-    off[kidx] = (uint16_t)o;
+    off[kidx] = (uint32_t)o * 4u;
+  }
+  for (int px = threadIdx.x; px < rpb * g.wo; px += 256) {
+    const int j = px / g.wo, ow = px - j * g.wo;
+    pshift[px] = (uint32_t)(j * g.stride * ws + ow * g.stride) * 4u;
+  }
+  __syncthreads();
+  if (vec4) {   // rows of w % 4 == 0 floats, 16-byte aligned: one 16-byte load per four columns
+    const int wq = g.w >> 2;
+    for (int u = threadIdx.x; u < nrow * wq; u += 256) {
+      const int rw = u / wq, q = u - rw * wq;
+      const int c = rw / rin, ih = ih0 + (rw - c * rin);
+      if (ih < 0 || ih >= g.h) continue;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xb + ((int64_t)c * g.h + ih) * g.w) + q);
+      float* d = rows + rw * ws + g.pad + (q << 2);
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+  } else {
+    for (int u = threadIdx.x; u < nrow * g.w; u += 256) {
+      const int rw = u / g.w, col = u - rw * g.w;
+      const int c = rw / rin, ih = ih0 + (rw - c * rin);
+      if (ih < 0 || ih >= g.h) continue;
+      rows[rw * ws + g.pad + col] = __ldg(xb + ((int64_t)c * g.h + ih) * g.w + col);
+    }
   }
   __syncthreads();
   const int chunks = g.Kp >> 3;
-  const int64_t m_img = ((int64_t)mc * g.batch + b) * g.ho * g.wo;
+  // lanes per pixel: 32 when a row has >= 32 chunks, else the next power of two (narrow rows share a warp pass)
+  int cpl = 32;
+  while ((cpl >> 1) >= chunks) cpl >>= 1;
+  const int ppw = 32 / cpl, sub = lane / cpl, kc0 = lane - sub * cpl;
   const int npix = min(rpb, g.ho - oh0) * g.wo;           // output pixels of this CTA (last block may be short)
-  for (int px = warp; px < npix; px += 8) {
-    const int j = px / g.wo, ow = px - j * g.wo;
-    // rows of the zero row must stay inside it: the shift below is only applied to real offsets (< nrow * ws)
-    const int shift = j * g.stride * ws + ow * g.stride;
-    const int zero_off = nrow * ws;
-    __nv_bfloat16* dst = A + (m_img + (int64_t)(oh0 + j) * g.wo + ow) * (int64_t)g.Kp;
-    for (int kc = lane; kc < chunks; kc += 32) {
-      const uint4 o8 = *reinterpret_cast<const uint4*>(off + (kc << 3));
-      const uint32_t ov[8] = {o8.x & 0xffffu, o8.x >> 16, o8.y & 0xffffu, o8.y >> 16,
-                              o8.z & 0xffffu, o8.z >> 16, o8.w & 0xffffu, o8.w >> 16};
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = rows[ov[e] == (uint32_t)zero_off ? zero_off : (int)ov[e] + shift];
-      *reinterpret_cast<uint4*>(dst + (kc << 3)) =
-          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  __nv_bfloat16* dst0 = A + (((int64_t)mc * g.batch + b) * g.ho * g.wo + (int64_t)oh0 * g.wo) * (int64_t)g.Kp;
+  const uint8_t* rb = reinterpret_cast<const uint8_t*>(rows);
+  for (int kc = kc0; kc < chunks; kc += cpl) {
+    const uint4 oa = *reinterpret_cast<const uint4*>(off + (kc << 3));
+    const uint4 ob = *reinterpret_cast<const uint4*>(off + (kc << 3) + 4);
+    __nv_bfloat16* dst = dst0 + (kc << 3);
+#pragma unroll 2
+    for (int px = warp * ppw + sub; px < npix; px += 8 * ppw) {
+      const uint8_t* r = rb + pshift[px];
+      const float v0 = *reinterpret_cast<const float*>(r + oa.x), v1 = *reinterpret_cast<const float*>(r + oa.y);
+      const float v2 = *reinterpret_cast<const float*>(r + oa.z), v3 = *reinterpret_cast<const float*>(r + oa.w);
+      const float v4 = *reinterpret_cast<const float*>(r + ob.x), v5 = *reinterpret_cast<const float*>(r + ob.y);
+      const float v6 = *reinterpret_cast<const float*>(r + ob.z), v7 = *reinterpret_cast<const float*>(r + ob.w);
+      *reinterpret_cast<uint4*>(dst + (int64_t)px * g.Kp) =
+          make_uint4(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3), pack_bf16x2(v4, v5), pack_bf16x2(v6, v7));
     }
   }
 }
 
-// output rows per CTA: as many (<= 4) as keep the staging under ~96 KB
-static int im2col_rpb(const ConvGeom& g) {
-  for (int rpb = 4; rpb > 1; rpb >>= 1) {
-    const size_t rin = (size_t)(rpb - 1) * g.stride + (size_t)(g.k - 1) * g.dil + 1;
-    if ((g.cin * rin + 2) * (size_t)(g.w + 2 * g.pad) * 4 + (size_t)g.Kp * 2 <= 96 * 1024 && g.ho >= rpb) return rpb;
-  }
-  return 1;
+static size_t im2col_rows_smem(const ConvGeom& g, int rpb) {
+  const size_t ws = (size_t)(g.w + 2 * g.pad);
+  const size_t rin = (size_t)(rpb - 1) * g.stride + (size_t)(g.k - 1) * g.dil + 1;
+  const size_t zr = (size_t)(rpb - 1) * g.stride * ws + (size_t)(g.wo - 1) * g.stride + 1;
+  const size_t nfloat = (g.cin * rin * ws + zr + 3) & ~(size_t)3;
+  return ((((size_t)g.Kp + 3) & ~(size_t)3) + (((size_t)rpb * g.wo + 3) & ~(size_t)3) + nfloat) * 4;
 }
 
-static size_t im2col_rows_smem(const ConvGeom& g, int rpb) {
-  const size_t rin = (size_t)(rpb - 1) * g.stride + (size_t)(g.k - 1) * g.dil + 1;
-  return (((size_t)g.Kp * 2 + 15) & ~(size_t)15) + (g.cin * rin + 1) * (size_t)(g.w + 2 * g.pad) * sizeof(float);
+// output rows per CTA: as many (<= 4) as keep the staging + tables under ~100 KB (two CTAs per SM)
+static int im2col_rpb(const ConvGeom& g) {
+  for (int rpb = 4; rpb > 1; rpb >>= 1)
+    if (im2col_rows_smem(g, rpb) <= 100 * 1024 && g.ho >= rpb) return rpb;
+  return 1;
 }
 
 static int launch_im2col(const pl_conv2d_args* a, const ConvGeom& g, __nv_bfloat16* A, cudaStream_t st) {
   const int rpb = im2col_rpb(g);
   const size_t smem = im2col_rows_smem(g, rpb);
-  const size_t rin = (size_t)(rpb - 1) * g.stride + (size_t)(g.k - 1) * g.dil + 1;
-  // the row kernel needs the staged rows + table in shared memory, uint16 offsets, and the standard output width
+  // the row kernel needs the staged rows + tables in shared memory and the standard output width;
+  // PL_IM2COL_GENERIC=1 (read per call: a test flips it) forces the element-wise kernel
+  const char* generic = getenv("PL_IM2COL_GENERIC");
   const bool rows_ok = smem <= 200 * 1024 && (int64_t)g.mcx * g.batch <= 65535 &&
-                       (g.cin * rin + 2) * (size_t)(g.w + 2 * g.pad) < 65536 &&
-                       (g.wo - 1) * g.stride + (g.k - 1) * g.dil < g.w + 2 * g.pad;
+                       (g.wo - 1) * g.stride + (g.k - 1) * g.dil < g.w + 2 * g.pad &&
+                       !(generic && generic[0] == '1');
   if (rows_ok) {
+    const int vec4 = (g.w % 4 == 0) && ((uintptr_t)a->x % 16 == 0) && (a->x_mc_stride % 4 == 0);
     dim3 grid((unsigned)((g.ho + rpb - 1) / rpb), (unsigned)(g.mcx * g.batch));
 #define PL_IM2COL(KK)                                                                                      \
   do {                                                                                                    \
     if (smem > 48 * 1024)   /* per call: the attribute is per device, a process-wide cache would miss GPU #2 */ \
       PL_CUDA(cudaFuncSetAttribute(im2col_rows_bf16_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)smem));                                                           \
-    im2col_rows_bf16_kernel<KK><<<grid, 256, smem, st>>>(a->x, a->x_mc_stride, A, g, rpb);                \
+    im2col_rows_bf16_kernel<KK><<<grid, 256, smem, st>>>(a->x, a->x_mc_stride, A, g, rpb, vec4);          \
   } while (0)
     if (g.k == 5) PL_IM2COL(5);
     else if (g.k == 3) PL_IM2COL(3);

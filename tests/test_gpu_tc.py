@@ -218,6 +218,51 @@ def test_tc_conv_philox_matches_fp64_oracle(plb, mc, b, cin, cout, hw, k, s, p, 
     assert rel_err(n(layer.bias.logscale.grad), bw["db_rho"]) < 1e-4
 
 
+@pytest.mark.parametrize("mc,b,cin,cout,hw,k,s,p,d,expand", [
+    (2, 3, 8, 16, 12, 3, 1, 1, 1, False),     # 16-byte staged loads, three output-row blocks
+    (2, 3, 3, 16, 32, 5, 1, 2, 1, True),      # K = 75: tail chunk reads the zero region; 10 chunks share a warp pass
+    (2, 3, 7, 16, 10, 3, 1, 1, 1, False),     # w % 4 != 0: scalar staging; ho = 10 leaves a short last block
+    (2, 3, 16, 24, 9, 3, 2, 1, 1, False),     # stride 2
+    (2, 2, 6, 16, 11, 3, 1, 2, 2, False),     # dilation 2
+    (1, 2, 256, 16, 16, 5, 1, 2, 1, False),   # staging too large for several output rows per CTA
+    (2, 4, 96, 128, 16, 5, 1, 2, 1, False),   # C3 layer 2
+    (2, 8, 256, 128, 4, 5, 1, 2, 1, False),   # C3 layer 4 (4x4 planes)
+])
+def test_im2col_row_kernel_equals_elementwise_kernel(plb, monkeypatch, mc, b, cin, cout, hw, k, s, p, d, expand):
+    """The staged im2col kernel and the element-wise one build the same bf16 matrix (PL_IM2COL_GENERIC=1, read per call
+    by conv_tc.cu, selects the latter): the forward output is bit-identical, the weight gradients (pixel reduction split
+    over CTAs with fp32 atomics, so order-dependent in the last bits) agree to 1e-5."""
+    torch.manual_seed(cin + hw)
+    layer = plb.BayesConv2d(cin, cout, k, stride=s, padding=p, dilation=d, num_MC=mc).cuda()
+    layer.precision = "bf16"
+    if expand:
+        x0 = torch.randn(b, cin, hw, hw, device="cuda")
+    else:
+        x0 = torch.randn(mc, b, cin, hw, hw, device="cuda")
+
+    def run(generic):
+        if generic:
+            monkeypatch.setenv("PL_IM2COL_GENERIC", "1")
+        else:
+            monkeypatch.delenv("PL_IM2COL_GENERIC", raising=False)
+        plb.manual_seed(4242)
+        layer._calls = 0          # same eps in both runs (the per-call seed counts forward calls)
+        for q in layer.parameters():
+            q.grad = None
+        x = x0.unsqueeze(0).expand(mc, b, cin, hw, hw) if expand else x0.clone().requires_grad_(True)
+        out = layer(x)
+        gy = torch.sin(torch.arange(out.numel(), device="cuda", dtype=torch.float32)).view_as(out)
+        (out * gy).sum().backward()
+        torch.cuda.synchronize()
+        return out.detach().clone(), layer.weight.loc.grad.clone(), layer.weight.logscale.grad.clone()
+
+    a, g = run(False), run(True)
+    assert torch.equal(a[0], g[0])
+    assert torch.isfinite(a[0]).all() and a[0].abs().max() > 0
+    for t_rows, t_generic in zip(a[1:], g[1:]):
+        assert rel_err(t_rows.cpu().numpy(), t_generic.cpu().numpy()) < 1e-5
+
+
 # ---------------------------------------------------------------------------------------------
 # TF32 tensor-core mode (kind::tf32, fp32 operands straight from the caller's tensors)
 # ---------------------------------------------------------------------------------------------
