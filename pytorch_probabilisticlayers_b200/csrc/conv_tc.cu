@@ -250,40 +250,64 @@ __global__ void __launch_bounds__(256) col2im_kernel(const __nv_bfloat16* __rest
   }
 }
 
-// Tiled col2im for stride 1 / dilation 1: a CTA takes `cpb` consecutive input channels of one (mc, image), copies
-// their k*k dA planes ([kk][ho*wo] bf16, contiguous 2*ho*wo-byte rows) into shared memory with 16-byte loads and
-// gathers from there.  The element-wise kernel above reads dA with 2-byte loads (1.5 TB/s at C3's layer 2).
-// grid (ceil(cin / cpb), batch, mc); dynamic smem = cpb * k*k * ho*wo * 2 bytes; needs ho*wo % 8 == 0, M % 8 == 0.
-__global__ void __launch_bounds__(256) col2im_tile_kernel(const __nv_bfloat16* __restrict__ dA,
-                                                          float* __restrict__ dx, ConvGeom g, int cpb) {
+// Pipelined col2im for stride 1 / dilation 1.  A CTA owns `cpc` consecutive input channels of `nb` consecutive images
+// of one MC sample and walks over the channels: the k*k dA rows of a channel (each nb*ho*wo bf16, contiguous in the
+// K-major dA) arrive by 1-D bulk copies (cp.async.bulk + mbarrier) in one of two shared-memory stages while the
+// threads gather the previous channel from the other, so loads never stop (the first tiled version loaded, synced
+// and gathered in turn; the element-wise kernel above reads dA with 2-byte loads).  CTA order (channel- or
+// image-major), compile-time k and mask-predicated taps all measured the same (profiles/r02_experiments.md).
+// Several images per CTA keep the copied pieces >= 512 bytes on small planes.  Same summation order (kh, kw
+// ascending) as col2im_kernel: bit-identical results.
+// grid (ceil(cin / cpc), ceil(batch / bpc), mc); dynamic smem = 2 * k*k * bpc*ho*wo * 2 + 16 bytes;
+// needs (ho*wo) % 8 == 0 (16-byte aligned pieces; M = batch*ho*wo is then a multiple of 8 as well).
+__global__ void __launch_bounds__(256, 8) col2im_pipe_kernel(const __nv_bfloat16* __restrict__ dA,
+                                                             float* __restrict__ dx, ConvGeom g, int cpc, int bpc) {
   extern __shared__ __align__(16) uint8_t col2im_smem[];
-  __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>(col2im_smem);   // [cpb][kk2][hwo]
-  const int kk2 = g.k * g.k, hwo = g.ho * g.wo, hw = g.h * g.w;
-  const int c0 = blockIdx.x * cpb, b = blockIdx.y, mc = blockIdx.z;
-  const int nc = min(cpb, g.cin - c0);
-  const __nv_bfloat16* base = dA + ((int64_t)mc * g.K + (int64_t)c0 * kk2) * g.M + (int64_t)b * hwo;
-  const int chunks_per_row = hwo >> 3;                       // 16-byte chunks per (c, kk) row
-  const int rows = nc * kk2;
-  for (int t = threadIdx.x; t < rows * chunks_per_row; t += 256) {
-    const int r = t / chunks_per_row, ch = t - r * chunks_per_row;
-    reinterpret_cast<uint4*>(planes)[t] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)r * g.M) + ch);
+  const int k = g.k;
+  const int kk2 = k * k, hwo = g.ho * g.wo, hw = g.h * g.w;
+  const int c0 = blockIdx.x * cpc, b0 = blockIdx.y * bpc, mc = blockIdx.z;
+  const int nc = min(cpc, g.cin - c0), nb = min(bpc, g.batch - b0);
+  const int piece = nb * hwo;                                   // bf16 elements per (channel, tap) row of this CTA
+  const uint32_t stage_bytes = (uint32_t)kk2 * piece * 2u;
+  __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>(col2im_smem);          // [2][kk2][piece]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(col2im_smem + 2 * (size_t)kk2 * bpc * hwo * 2);
+  const uint32_t bar0 = smem_u32(bars), planes0 = smem_u32(planes);
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_mbar_init();
   }
   __syncthreads();
-  float* out = dx + (((int64_t)mc * g.batch + b) * g.cin + c0) * hw;
-  for (int t = threadIdx.x; t < nc * hw; t += 256) {
-    const int c = t / hw, p = t - c * hw, ih = p / g.w, iw = p - ih * g.w;
-    const __nv_bfloat16* pc = planes + (int64_t)c * kk2 * hwo;
-    float s = 0.f;
-    for (int kh = 0; kh < g.k; ++kh) {
-      const int oh = ih + g.pad - kh;
-      if (oh < 0 || oh >= g.ho) continue;
-      for (int kw = 0; kw < g.k; ++kw) {
-        const int ow = iw + g.pad - kw;
-        if (ow < 0 || ow >= g.wo) continue;
-        s += __bfloat162float(pc[(kh * g.k + kw) * hwo + oh * g.wo + ow]);
+  const __nv_bfloat16* base = dA + ((int64_t)mc * g.K + (int64_t)c0 * kk2) * g.M + (int64_t)b0 * hwo;
+  auto issue = [&](int ci, int s) {     // warp 0: the k*k rows of channel c0 + ci -> stage s
+    if (threadIdx.x == 0) mbar_expect_tx(bar0 + 8 * s, stage_bytes);
+    __syncwarp();
+    for (int r = threadIdx.x; r < kk2; r += 32)
+      bulk_load_1d(planes0 + (uint32_t)s * stage_bytes + (uint32_t)r * piece * 2u,
+                   base + ((int64_t)ci * kk2 + r) * g.M, (uint32_t)piece * 2u, bar0 + 8 * s);
+  };
+  if (threadIdx.x < 32) issue(0, 0);
+  for (int ci = 0; ci < nc; ++ci) {
+    const int s = ci & 1;
+    if (threadIdx.x < 32 && ci + 1 < nc) issue(ci + 1, s ^ 1);   // stage s^1 was drained before the sync below
+    mbar_wait(bar0 + 8 * s, (ci >> 1) & 1);
+    const __nv_bfloat16* pc = planes + (size_t)s * kk2 * piece;
+    for (int t = threadIdx.x; t < nb * hw; t += 256) {
+      const int bl = t / hw, p = t - bl * hw, ih = p / g.w, iw = p - ih * g.w;
+      const __nv_bfloat16* pb = pc + bl * hwo;
+      float sum = 0.f;
+      for (int kh = 0; kh < k; ++kh) {
+        const int oh = ih + g.pad - kh;
+        if (oh < 0 || oh >= g.ho) continue;
+        for (int kw = 0; kw < k; ++kw) {
+          const int ow = iw + g.pad - kw;
+          if (ow < 0 || ow >= g.wo) continue;
+          sum += __bfloat162float(pb[(kh * k + kw) * piece + oh * g.wo + ow]);
+        }
       }
+      dx[(((int64_t)mc * g.batch + b0 + bl) * g.cin + c0 + ci) * hw + p] = sum;
     }
-    out[t] = s;
+    __syncthreads();
   }
 }
 
@@ -508,15 +532,20 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     if (rc != PL_OK) return rc;
     const int64_t n = (int64_t)g.mc * g.batch * g.cin * g.h * g.w;
     const int hwo = g.ho * g.wo, hw = g.h * g.w;
-    int cpb = hw >= 256 ? 1 : (256 + hw - 1) / hw;            // channels per CTA: at least 256 input pixels
-    if (cpb > g.cin) cpb = g.cin;
-    const size_t tile_smem = (size_t)cpb * g.k * g.k * hwo * 2;
-    if (g.stride == 1 && g.dil == 1 && (hwo & 7) == 0 && (g.M & 7) == 0 && tile_smem <= 96 * 1024 &&
-        g.batch <= 65535 && g.mc <= 65535) {
+    // images per CTA: pieces of >= 256 pixels (512 bytes) where the batch allows it; 8 channels per CTA
+    int bpc = hwo >= 256 ? 1 : (256 + hwo - 1) / hwo;
+    if (bpc > g.batch) bpc = g.batch;
+    const int cpc = g.cin < 8 ? g.cin : 8;
+    const size_t stage = (size_t)g.k * g.k * bpc * hwo * 2;
+    const size_t tile_smem = 2 * stage + 16;
+    const char* generic = getenv("PL_COL2IM_GENERIC");   // =1 (read per call: a test flips it): element-wise kernel
+    const int force = generic ? atoi(generic) : 0;
+    const unsigned gc = (unsigned)((g.cin + cpc - 1) / cpc), gb = (unsigned)((g.batch + bpc - 1) / bpc);
+    if (g.stride == 1 && g.dil == 1 && (hwo & 7) == 0 && tile_smem <= 200 * 1024 && stage < (1u << 20) &&
+        gb <= 65535 && gc <= 65535 && g.mc <= 65535 && force != 1) {
       if (tile_smem > 48 * 1024)   // per call: the attribute is per device
-        PL_CUDA(cudaFuncSetAttribute(col2im_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-      dim3 grid((unsigned)((g.cin + cpb - 1) / cpb), (unsigned)g.batch, (unsigned)g.mc);
-      col2im_tile_kernel<<<grid, 256, tile_smem, st>>>(w.dA, a->dx, g, cpb);
+        PL_CUDA(cudaFuncSetAttribute(col2im_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+      col2im_pipe_kernel<<<dim3(gc, gb, (unsigned)g.mc), 256, tile_smem, st>>>(w.dA, a->dx, g, cpc, bpc);
     } else if (g.stride == 1 && g.dil == 1) {
       col2im_kernel<true><<<ew_grid(n, 256), 256, 0, st>>>(w.dA, a->dx, g);
     } else {

@@ -263,6 +263,46 @@ def test_im2col_row_kernel_equals_elementwise_kernel(plb, monkeypatch, mc, b, ci
         assert rel_err(t_rows.cpu().numpy(), t_generic.cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("mc,b,cin,cout,hw,k,p", [
+    (2, 3, 8, 16, 12, 3, 1),       # 144-pixel planes: two images per CTA, the last image group is short
+    (2, 5, 16, 24, 4, 3, 1),       # 4x4 planes: the whole batch in one CTA
+    (1, 2, 20, 16, 16, 5, 2),      # channel groups 8 + 8 + 4
+    (2, 4, 8, 16, 8, 1, 0),        # 1x1 kernel: one row per channel
+    (2, 3, 8, 16, 8, 3, 2),        # padding = k - 1: the output planes are larger than the input planes
+    (2, 5, 12, 16, 16, 3, 0),      # no padding: 14x14 output planes fall back to the element-wise kernel (196 % 8)
+    (2, 5, 12, 16, 10, 3, 0),      # no padding, 8x8 output planes from 10x10 inputs
+    (2, 3, 7, 16, 10, 3, 1),       # 100-pixel planes (not a multiple of 8): both runs take the element-wise kernel
+    (2, 4, 96, 128, 16, 5, 2),     # C3 layer 2
+    (2, 4, 128, 256, 8, 5, 2),     # C3 layer 3
+    (2, 8, 256, 128, 4, 5, 2),     # C3 layer 4
+])
+def test_col2im_pipelined_kernel_equals_elementwise_kernel(plb, monkeypatch, mc, b, cin, cout, hw, k, p):
+    """dX of the bf16 conv path: the bulk-copy pipelined col2im and the element-wise gather (PL_COL2IM_GENERIC=1, read
+    per call by conv_tc.cu) sum the same bf16 dA entries in the same order -> bit-identical input gradients."""
+    torch.manual_seed(cin * 3 + hw)
+    layer = plb.BayesConv2d(cin, cout, k, stride=1, padding=p, num_MC=mc).cuda()
+    layer.precision = "bf16"
+    x0 = torch.randn(mc, b, cin, hw, hw, device="cuda")
+
+    def run(generic):
+        if generic:
+            monkeypatch.setenv("PL_COL2IM_GENERIC", generic)
+        else:
+            monkeypatch.delenv("PL_COL2IM_GENERIC", raising=False)
+        plb.manual_seed(99)
+        layer._calls = 0
+        x = x0.clone().requires_grad_(True)
+        out = layer(x)
+        gy = torch.cos(torch.arange(out.numel(), device="cuda", dtype=torch.float32)).view_as(out)
+        (out * gy).sum().backward()
+        torch.cuda.synchronize()
+        return x.grad.clone()
+
+    dx_default, dx_generic = run(None), run("1")
+    assert torch.equal(dx_default, dx_generic)
+    assert torch.isfinite(dx_default).all() and dx_default.abs().max() > 0
+
+
 # ---------------------------------------------------------------------------------------------
 # TF32 tensor-core mode (kind::tf32, fp32 operands straight from the caller's tensors)
 # ---------------------------------------------------------------------------------------------
