@@ -260,10 +260,35 @@ __global__ void __launch_bounds__(256) col2im_kernel(const __nv_bfloat16* __rest
 // ascending) as col2im_kernel: bit-identical results.
 // grid (ceil(cin / cpc), ceil(batch / bpc), mc); dynamic smem = 2 * k*k * bpc*ho*wo * 2 + 16 bytes;
 // needs (ho*wo) % 8 == 0 (16-byte aligned pieces; M = batch*ho*wo is then a multiple of 8 as well).
-__global__ void __launch_bounds__(256, 8) col2im_pipe_kernel(const __nv_bfloat16* __restrict__ dA,
+// One tap of the unrolled gather: returns the bf16 at shared address `addr` as fp32 bits when bit 0 of `mask` is set,
+// else +0; then shifts the mask and advances the address (inside the statement, so the compiler does not precompute
+// 25 addresses and predicates and spill them).  Only the load is predicated; every temporary is defined
+// unconditionally.  The branchy C loop costs ~18 instructions per tap (ncu: 700 thread instructions per output,
+// issue slots 92 % busy).
+__device__ __forceinline__ float lds_bf16_tap(uint32_t& addr, uint32_t& mask, uint32_t step) {
+  uint32_t bits;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b16 h;\n\t.reg .b32 w;\n\t"
+      "and.b32 w, %2, 1;\n\t"
+      "setp.ne.u32 p, w, 0;\n\t"
+      "mov.b16 h, 0;\n\t"
+      "@p ld.shared.u16 h, [%1];\n\t"
+      "cvt.u32.u16 w, h;\n\t"
+      "shl.b32 %0, w, 16;\n\t"
+      "shr.u32 %2, %2, 1;\n\t"
+      "add.u32 %1, %1, %3;\n\t}"
+      : "=r"(bits), "+r"(addr), "+r"(mask)
+      : "r"(step));
+  return __uint_as_float(bits);
+}
+
+// kK: compile-time kernel size (3, 5): the k*k taps unroll into predicated (load, convert, add) triples driven by a
+// k*k-bit validity mask, addresses advance by constant steps; 0 = run-time k, plain loops.
+template <int kK>
+__global__ void __launch_bounds__(256, 6) col2im_pipe_kernel(const __nv_bfloat16* __restrict__ dA,
                                                              float* __restrict__ dx, ConvGeom g, int cpc, int bpc) {
   extern __shared__ __align__(16) uint8_t col2im_smem[];
-  const int k = g.k;
+  const int k = kK ? kK : g.k;
   const int kk2 = k * k, hwo = g.ho * g.wo, hw = g.h * g.w;
   const int c0 = blockIdx.x * cpc, b0 = blockIdx.y * bpc, mc = blockIdx.z;
   const int nc = min(cpc, g.cin - c0), nb = min(bpc, g.batch - b0);
@@ -287,22 +312,43 @@ __global__ void __launch_bounds__(256, 8) col2im_pipe_kernel(const __nv_bfloat16
                    base + ((int64_t)ci * kk2 + r) * g.M, (uint32_t)piece * 2u, bar0 + 8 * s);
   };
   if (threadIdx.x < 32) issue(0, 0);
+#pragma unroll 1
   for (int ci = 0; ci < nc; ++ci) {
     const int s = ci & 1;
     if (threadIdx.x < 32 && ci + 1 < nc) issue(ci + 1, s ^ 1);   // stage s^1 was drained before the sync below
     mbar_wait(bar0 + 8 * s, (ci >> 1) & 1);
-    const __nv_bfloat16* pc = planes + (size_t)s * kk2 * piece;
+#pragma unroll 1
     for (int t = threadIdx.x; t < nb * hw; t += 256) {
       const int bl = t / hw, p = t - bl * hw, ih = p / g.w, iw = p - ih * g.w;
-      const __nv_bfloat16* pb = pc + bl * hwo;
       float sum = 0.f;
-      for (int kh = 0; kh < k; ++kh) {
-        const int oh = ih + g.pad - kh;
-        if (oh < 0 || oh >= g.ho) continue;
-        for (int kw = 0; kw < k; ++kw) {
-          const int ow = iw + g.pad - kw;
-          if (ow < 0 || ow >= g.wo) continue;
-          sum += __bfloat162float(pb[(kh * k + kw) * piece + oh * g.wo + ow]);
+      if (kK) {
+        // tap (kh, kw) reads plane[kh*k + kw][ih + pad - kh][iw + pad - kw]: valid = row bit kh & column bit kw
+        uint32_t cm = 0, m = 0;
+#pragma unroll
+        for (int j = 0; j < kK; ++j) cm |= ((unsigned)(iw + g.pad - j) < (unsigned)g.wo ? 1u : 0u) << j;
+#pragma unroll
+        for (int j = 0; j < kK; ++j)
+          if ((unsigned)(ih + g.pad - j) < (unsigned)g.ho) m |= cm << (j * kK);
+        uint32_t addr = planes0 + (uint32_t)s * stage_bytes +
+                        (uint32_t)(bl * hwo + (ih + g.pad) * g.wo + iw + g.pad) * 2u;      // tap (0, 0)
+        const uint32_t step_kw = (uint32_t)(piece - 1) * 2u;                                // next plane, ow - 1
+        const uint32_t step_kh = (uint32_t)(kK - g.wo) * 2u;   // after k kw-steps: back k columns, up one row (mod 2^32)
+#pragma unroll
+        for (int kh = 0; kh < kK; ++kh) {
+#pragma unroll
+          for (int kw = 0; kw < kK; ++kw)   // the last tap of a row also moves back k columns and up one row
+            sum += lds_bf16_tap(addr, m, kw == kK - 1 ? step_kw + step_kh : step_kw);
+        }
+      } else {
+        const __nv_bfloat16* pb = planes + (size_t)s * kk2 * piece + bl * hwo;
+        for (int kh = 0; kh < k; ++kh) {
+          const int oh = ih + g.pad - kh;
+          if (oh < 0 || oh >= g.ho) continue;
+          for (int kw = 0; kw < k; ++kw) {
+            const int ow = iw + g.pad - kw;
+            if (ow < 0 || ow >= g.wo) continue;
+            sum += __bfloat162float(pb[(kh * k + kw) * piece + oh * g.wo + ow]);
+          }
         }
       }
       dx[(((int64_t)mc * g.batch + b0 + bl) * g.cin + c0 + ci) * hw + p] = sum;
@@ -543,9 +589,17 @@ int conv_bwd_tc_launch(const pl_conv2d_args* a) {
     const unsigned gc = (unsigned)((g.cin + cpc - 1) / cpc), gb = (unsigned)((g.batch + bpc - 1) / bpc);
     if (g.stride == 1 && g.dil == 1 && (hwo & 7) == 0 && tile_smem <= 200 * 1024 && stage < (1u << 20) &&
         gb <= 65535 && gc <= 65535 && g.mc <= 65535 && force != 1) {
-      if (tile_smem > 48 * 1024)   // per call: the attribute is per device
-        PL_CUDA(cudaFuncSetAttribute(col2im_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-      col2im_pipe_kernel<<<dim3(gc, gb, (unsigned)g.mc), 256, tile_smem, st>>>(w.dA, a->dx, g, cpc, bpc);
+#define PL_COL2IM(KK)                                                                                       \
+  do {                                                                                                     \
+    if (tile_smem > 48 * 1024)   /* per call: the attribute is per device */                               \
+      PL_CUDA(cudaFuncSetAttribute(col2im_pipe_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                   (int)tile_smem));                                                       \
+    col2im_pipe_kernel<KK><<<dim3(gc, gb, (unsigned)g.mc), 256, tile_smem, st>>>(w.dA, a->dx, g, cpc, bpc); \
+  } while (0)
+      if (g.k == 5) PL_COL2IM(5);
+      else if (g.k == 3) PL_COL2IM(3);
+      else PL_COL2IM(0);
+#undef PL_COL2IM
     } else if (g.stride == 1 && g.dil == 1) {
       col2im_kernel<true><<<ew_grid(n, 256), 256, 0, st>>>(w.dA, a->dx, g);
     } else {
