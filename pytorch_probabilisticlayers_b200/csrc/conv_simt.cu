@@ -275,9 +275,25 @@ __global__ void __launch_bounds__(256) conv_bias_colsum_kernel(ConvParams p) {
   const int co = blockIdx.x, mc = blockIdx.y, hwo = p.ho * p.wo;
   const float* dyp = p.dy + (int64_t)mc * p.batch * p.cout * hwo;
   float s = 0.f;
-  for (int i = threadIdx.x; i < p.batch * hwo; i += 256) {
-    const int b = i / hwo, pix = i - b * hwo;
-    s += __ldg(dyp + ((int64_t)b * p.cout + co) * hwo + pix);
+  if ((hwo & 3) == 0 && hwo >= 128 && (reinterpret_cast<uintptr_t>(p.dy) & 15) == 0) {
+    // large planes: a warp per image, 16-byte loads, four independent partial sums per lane (the scalar loop below
+    // is one dependent add per 4-byte load: 2.4 TB/s on C3's first layer)
+    const int hwo4 = hwo >> 2, lane = threadIdx.x & 31;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = threadIdx.x >> 5; b < p.batch; b += 8) {
+      const float4* src = reinterpret_cast<const float4*>(dyp + ((int64_t)b * p.cout + co) * hwo);
+#pragma unroll 4
+      for (int q = lane; q < hwo4; q += 32) {
+        const float4 v = __ldg(src + q);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    s = (acc.x + acc.y) + (acc.z + acc.w);
+  } else {
+    for (int i = threadIdx.x; i < p.batch * hwo; i += 256) {
+      const int b = i / hwo, pix = i - b * hwo;
+      s += __ldg(dyp + ((int64_t)b * p.cout + co) * hwo + pix);
+    }
   }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
